@@ -1,0 +1,477 @@
+"""Python face of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package never does.
+
+Two layers:
+  * ctypes bindings to oracle/libsage_oracle.so (sage_oracle.c / oracle_body.inc): the
+    factor kernels a1-a5 of SURVEY.md section 8, restated from
+    /root/reference/system/sources/cuda/*.cpp.
+  * numpy/torch restatements of the host-side pieces around them: camera pyramid
+    (common/camera_pyramid.h:18-32), Gaussian pyramid + gradients
+    (core/mapping/mapper.cpp:1385-1426, mapping_utils.h:236-252), valid locations
+    (mapping_utils.h:254-287), SE(3) exp / retract (mapping_utils.h:316-346,
+    gtsam/gtsam_traits.h:45-70), NearestPsd (mapping_utils.h:104-128), the tracker's LM
+    loop (core/system/camera_tracker.cpp:1156-1279) and a dense fp64 normal-equation
+    solve that stands in for the (unbuildable) GTSAM solve.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libsage_oracle.so")
+    srcs = [os.path.join(HERE, f) for f in ("sage_oracle.c", "oracle_body.inc", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []))
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.oracle_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+# --------------------------------------------------------------------------------------
+# ctypes plumbing
+# --------------------------------------------------------------------------------------
+def _suffix(dtype):
+    return "_f32" if np.dtype(dtype) == np.float32 else "_f64"
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _r(a, dtype):
+    return np.ascontiguousarray(np.asarray(a, dtype=dtype))
+
+
+def _s(v, dtype):
+    return ctypes.c_float(float(v)) if np.dtype(dtype) == np.float32 else ctypes.c_double(float(v))
+
+
+def _jac_strides(jac):
+    """jac0 is [HW, C] with arbitrary strides (the reference's is a (1, HW) permuted view)."""
+    item = jac.dtype.itemsize
+    return ctypes.c_long(jac.strides[0] // item), ctypes.c_long(jac.strides[1] // item)
+
+
+def _out(D):
+    return np.zeros((D, D), np.float64), np.zeros((D,), np.float64), ctypes.c_double(0), ctypes.c_double(0)
+
+
+def _cams(cams, dtype):
+    return _r(np.asarray(cams, dtype=np.float64).reshape(-1, 6), dtype)
+
+
+def photometric_jac_error(R10, t10, R0, t0, R1, t1, bias0, jac0, code0, mask1, loc1d, homo, feat0, feat1, grad1,
+                          level_offsets, scale0, cams, eps, weights, dtype=np.float32):
+    """df::photometric_jac_error_calculate<CS,FS>; returns (AtA, Atb, error, n_inliers)."""
+    f = getattr(lib(), "oracle_photometric_jac_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    N, CS = len(loc1d), jac0.shape[1]
+    feat0, feat1, grad1 = _r(feat0, dtype), _r(feat1, dtype), _r(grad1, dtype)
+    FS, SP = feat0.shape
+    cams = _cams(cams, dtype)
+    L = cams.shape[0]
+    A, b, e, n = _out(13 + CS)
+    sr, sc = _jac_strides(jac0)
+    args = [_r(x, dtype) for x in (R10, t10, R0, t0, R1, t1, bias0)]
+    code0, mask1, homo, weights = _r(code0, dtype), _r(mask1, dtype), _r(homo, dtype), _r(weights, dtype)
+    loc1d = _r(loc1d, np.int64)
+    lo = _r(level_offsets, np.int32)
+    f(_p(A), _p(b), ctypes.byref(e), ctypes.byref(n), *[_p(x) for x in args], _p(jac0), sr, sc, _p(code0), _p(mask1),
+      _p(loc1d), _p(homo), _p(feat0), _p(feat1), _p(grad1), _p(lo), _s(scale0, dtype), _p(cams), _s(eps, dtype),
+      _p(weights), ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(FS), ctypes.c_int(CS), ctypes.c_long(SP))
+    return A, b, e.value, n.value
+
+
+def photometric_error(R10, t10, bias0, jac0, code0, mask1, loc1d, homo, feat0, feat1, level_offsets, scale0, cams,
+                      eps, weights, dtype=np.float32):
+    f = getattr(lib(), "oracle_photometric_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    N, CS = len(loc1d), jac0.shape[1]
+    feat0, feat1 = _r(feat0, dtype), _r(feat1, dtype)
+    FS, SP = feat0.shape
+    cams = _cams(cams, dtype)
+    L = cams.shape[0]
+    e, n = ctypes.c_double(0), ctypes.c_double(0)
+    sr, sc = _jac_strides(jac0)
+    R10, t10, bias0, code0, mask1, homo, weights = [_r(x, dtype) for x in (R10, t10, bias0, code0, mask1, homo, weights)]
+    loc1d = _r(loc1d, np.int64)
+    lo = _r(level_offsets, np.int32)
+    f(ctypes.byref(e), ctypes.byref(n), _p(R10), _p(t10), _p(bias0), _p(jac0), sr, sc, _p(code0), _p(mask1), _p(loc1d),
+      _p(homo), _p(feat0), _p(feat1), _p(lo), _s(scale0, dtype), _p(cams), _s(eps, dtype), _p(weights),
+      ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(FS), ctypes.c_int(CS), ctypes.c_long(SP))
+    return e.value, n.value
+
+
+def tracker_photo_jac_error(R, t, mask1, dpts0, homo, sfeat0, feat1, grad1, level_offsets, cams, eps, weights,
+                            scale0=None, dtype=np.float32):
+    """tracker_photo_jac_error_calculate (scale0 None) or ..._with_scale (scale0 given)."""
+    f = getattr(lib(), "oracle_tracker_photo_jac_error" + _suffix(dtype))
+    with_scale = scale0 is not None
+    D = 7 if with_scale else 6
+    feat1, grad1, sfeat0 = _r(feat1, dtype), _r(grad1, dtype), _r(sfeat0, dtype)
+    FS, SP = feat1.shape
+    cams = _cams(cams, dtype)
+    L, N = cams.shape[0], len(dpts0)
+    A, b, e, n = _out(D)
+    R, t, mask1, dpts0, homo, weights = [_r(x, dtype) for x in (R, t, mask1, dpts0, homo, weights)]
+    lo = _r(level_offsets, np.int32)
+    f(_p(A), _p(b), ctypes.byref(e), ctypes.byref(n), _p(R), _p(t), _p(mask1), _p(dpts0), _p(homo), _p(sfeat0),
+      _p(feat1), _p(grad1), _p(lo), _p(cams), _s(scale0 if with_scale else 1.0, dtype), _s(eps, dtype), _p(weights),
+      ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(FS), ctypes.c_long(SP), ctypes.c_int(int(with_scale)))
+    return A, b, e.value, n.value
+
+
+def tracker_photo_error(R, t, mask1, dpts0, homo, sfeat0, feat1, level_offsets, cams, eps, weights, dtype=np.float32):
+    f = getattr(lib(), "oracle_tracker_photo_error" + _suffix(dtype))
+    feat1, sfeat0 = _r(feat1, dtype), _r(sfeat0, dtype)
+    FS, SP = feat1.shape
+    cams = _cams(cams, dtype)
+    L, N = cams.shape[0], len(dpts0)
+    e, n = ctypes.c_double(0), ctypes.c_double(0)
+    R, t, mask1, dpts0, homo, weights = [_r(x, dtype) for x in (R, t, mask1, dpts0, homo, weights)]
+    lo = _r(level_offsets, np.int32)
+    f(ctypes.byref(e), ctypes.byref(n), _p(R), _p(t), _p(mask1), _p(dpts0), _p(homo), _p(sfeat0), _p(feat1), _p(lo),
+      _p(cams), _s(eps, dtype), _p(weights), ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(FS), ctypes.c_long(SP))
+    return e.value, n.value
+
+
+def geometric_jac_error(R10, t10, R0, t0, R1, t1, bias0, jac0, code0, dpt1, dgrad1, basis1, mask1, loc1d, homo,
+                        scale0, scale1, cam, eps, loss_param, weight, dtype=np.float32):
+    f = getattr(lib(), "oracle_geometric_jac_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    N, CS = len(loc1d), jac0.shape[1]
+    A, b, e, n = _out(14 + 2 * CS)
+    sr, sc = _jac_strides(jac0)
+    a = [_r(x, dtype) for x in (R10, t10, R0, t0, R1, t1, bias0)]
+    code0, dpt1, dgrad1, basis1, mask1, homo = [_r(x, dtype) for x in (code0, dpt1, dgrad1, basis1, mask1, homo)]
+    loc1d = _r(loc1d, np.int32)
+    cam = _cams(cam, dtype)
+    f(_p(A), _p(b), ctypes.byref(e), ctypes.byref(n), *[_p(x) for x in a], _p(jac0), sr, sc, _p(code0), _p(dpt1),
+      _p(dgrad1), _p(basis1), _p(mask1), _p(loc1d), _p(homo), _s(scale0, dtype), _s(scale1, dtype), _p(cam),
+      _s(eps, dtype), _s(loss_param, dtype), _s(weight, dtype), ctypes.c_int(N), ctypes.c_int(CS))
+    return A, b, e.value, n.value
+
+
+def geometric_error(R10, t10, bias0, jac0, code0, dpt1, mask1, loc1d, homo, scale0, cam, eps, loss_param, weight,
+                    dtype=np.float32):
+    f = getattr(lib(), "oracle_geometric_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    N, CS = len(loc1d), jac0.shape[1]
+    e, n = ctypes.c_double(0), ctypes.c_double(0)
+    sr, sc = _jac_strides(jac0)
+    R10, t10, bias0, code0, dpt1, mask1, homo = [_r(x, dtype) for x in (R10, t10, bias0, code0, dpt1, mask1, homo)]
+    loc1d = _r(loc1d, np.int32)
+    cam = _cams(cam, dtype)
+    f(ctypes.byref(e), ctypes.byref(n), _p(R10), _p(t10), _p(bias0), _p(jac0), sr, sc, _p(code0), _p(dpt1), _p(mask1),
+      _p(loc1d), _p(homo), _s(scale0, dtype), _p(cam), _s(eps, dtype), _s(loss_param, dtype), _s(weight, dtype),
+      ctypes.c_int(N), ctypes.c_int(CS))
+    return e.value, n.value
+
+
+def reprojection_jac_error(R10, t10, R0, t0, R1, t1, bias0, jac0, code0, loc1d, homo, match2d, scale0, cam, eps,
+                           loss_param, weight, dtype=np.float32):
+    f = getattr(lib(), "oracle_reprojection_jac_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    M, CS = len(loc1d), jac0.shape[1]
+    A, b, e, n = _out(13 + CS)
+    sr, sc = _jac_strides(jac0)
+    a = [_r(x, dtype) for x in (R10, t10, R0, t0, R1, t1, bias0)]
+    code0, homo, match2d = [_r(x, dtype) for x in (code0, homo, match2d)]
+    loc1d = _r(loc1d, np.int32)
+    cam = _cams(cam, dtype)
+    f(_p(A), _p(b), ctypes.byref(e), ctypes.byref(n), *[_p(x) for x in a], _p(jac0), sr, sc, _p(code0), _p(loc1d),
+      _p(homo), _p(match2d), _s(scale0, dtype), _p(cam), _s(eps, dtype), _s(loss_param, dtype), _s(weight, dtype),
+      ctypes.c_int(M), ctypes.c_int(CS))
+    return A, b, e.value, n.value
+
+
+def reprojection_error(R10, t10, bias0, jac0, code0, loc1d, homo, match2d, scale0, cam, eps, loss_param, weight,
+                       dtype=np.float32):
+    f = getattr(lib(), "oracle_reprojection_error" + _suffix(dtype))
+    jac0 = np.asarray(jac0, dtype=dtype)
+    M, CS = len(loc1d), jac0.shape[1]
+    e, n = ctypes.c_double(0), ctypes.c_double(0)
+    sr, sc = _jac_strides(jac0)
+    R10, t10, bias0, code0, homo, match2d = [_r(x, dtype) for x in (R10, t10, bias0, code0, homo, match2d)]
+    loc1d = _r(loc1d, np.int32)
+    cam = _cams(cam, dtype)
+    f(ctypes.byref(e), ctypes.byref(n), _p(R10), _p(t10), _p(bias0), _p(jac0), sr, sc, _p(code0), _p(loc1d), _p(homo),
+      _p(match2d), _s(scale0, dtype), _p(cam), _s(eps, dtype), _s(loss_param, dtype), _s(weight, dtype),
+      ctypes.c_int(M), ctypes.c_int(CS))
+    return e.value, n.value
+
+
+def tracker_reproj_jac_error(R, t, dpts0, homo, match2d, cam, eps, loss_param, weight, dtype=np.float32):
+    f = getattr(lib(), "oracle_tracker_reproj_jac_error" + _suffix(dtype))
+    M = len(dpts0)
+    A, b, e, n = _out(6)
+    R, t, dpts0, homo, match2d = [_r(x, dtype) for x in (R, t, dpts0, homo, match2d)]
+    cam = _cams(cam, dtype)
+    f(_p(A), _p(b), ctypes.byref(e), ctypes.byref(n), _p(R), _p(t), _p(dpts0), _p(homo), _p(match2d), _p(cam),
+      _s(eps, dtype), _s(loss_param, dtype), _s(weight, dtype), ctypes.c_int(M))
+    return A, b, e.value, n.value
+
+
+def tracker_reproj_error(R, t, dpts0, homo, match2d, cam, eps, loss_param, weight, dtype=np.float32):
+    f = getattr(lib(), "oracle_tracker_reproj_error" + _suffix(dtype))
+    M = len(dpts0)
+    e, n = ctypes.c_double(0), ctypes.c_double(0)
+    R, t, dpts0, homo, match2d = [_r(x, dtype) for x in (R, t, dpts0, homo, match2d)]
+    cam = _cams(cam, dtype)
+    f(ctypes.byref(e), ctypes.byref(n), _p(R), _p(t), _p(dpts0), _p(homo), _p(match2d), _p(cam), _s(eps, dtype),
+      _s(loss_param, dtype), _s(weight, dtype), ctypes.c_int(M))
+    return e.value, n.value
+
+
+# --------------------------------------------------------------------------------------
+# host-side restatements
+# --------------------------------------------------------------------------------------
+def camera_pyramid(cam, levels):
+    """CameraPyramid<float>(cam, levels): common/camera_pyramid.h:18-32 +
+    PinholeCamera::ResizeViewport (common/pinhole_camera_impl.h:120-132).  fp32 arithmetic,
+    integer-halved width/height stored back as float."""
+    f = np.float32
+    cams = [np.array(cam, dtype=f)]
+    for i in range(1, levels):
+        fx, fy, u0, v0, w, h = cams[i - 1]
+        nw, nh = f(int(w) // 2), f(int(h) // 2)  # size_t division of the float width/height
+        xr, yr = f(nw / w), f(nh / h)
+        cams.append(np.array([fx * xr, fy * yr, u0 * xr, v0 * yr, nw, nh], dtype=f))
+    return np.stack(cams)
+
+
+def level_offsets(cams):
+    """core/mapping/mapper.cpp:88-97"""
+    off, out = 0, []
+    for c in cams:
+        out.append(off)
+        off += int(c[4]) * int(c[5])
+    return np.array(out, np.int32), off
+
+
+def spatial_grad(x):
+    """ComputeSpatialGrad (core/mapping/mapping_utils.h:236-252): central differences with
+    replicate padding.  x: torch [1,C,H,W] -> [1,2C,H,W] (all d/dx first, then all d/dy)."""
+    import torch
+    import torch.nn.functional as F
+
+    H, W = x.shape[2], x.shape[3]
+    p = F.pad(x, (1, 1, 1, 1), mode="replicate")
+    gx = 0.5 * (p[:, :, 1:H + 1, 2:W + 2] - p[:, :, 1:H + 1, 0:W])
+    gy = 0.5 * (p[:, :, 2:H + 2, 1:W + 1] - p[:, :, 0:H, 1:W + 1])
+    return torch.cat([gx, gy], 1)
+
+
+def mask_pyramid(mask, levels):
+    """GenerateMaskPyramid (core/mapping/mapping_utils.cpp:321-342): nearest resize by halving."""
+    import torch.nn.functional as F
+
+    out = [mask]
+    h, w = mask.shape[2], mask.shape[3]
+    cur = mask
+    for _ in range(levels - 1):
+        h //= 2
+        w //= 2
+        cur = F.interpolate(cur, size=(h, w), mode="nearest")
+        out.append(cur)
+    return out
+
+
+def gaussian_pyramid_with_grad(feat, masks):
+    """Mapper::GenerateGaussianPyramidWithGrad (core/mapping/mapper.cpp:1385-1426).
+    feat: torch [1,F,H,W]; masks: list of [1,1,h,w].  Kernel: 3x3 [1 2 1]^2/16, stride 2, pad 1
+    (mapper.cpp:99-110).  Returns feat_pyr [F, SP], grad_pyr [2, F, SP]."""
+    import torch
+    import torch.nn.functional as F
+
+    C, H, W = feat.shape[1], feat.shape[2], feat.shape[3]
+    k = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], dtype=feat.dtype).reshape(1, 1, 3, 3) / 16.0
+    cur = feat.reshape(C, 1, H, W)
+    feats = [cur.reshape(C, H * W)]
+    grads = [spatial_grad(cur.reshape(1, C, H, W)).reshape(2, C, H * W)]
+    for i in range(len(masks) - 1):
+        m = masks[i]
+        raw = F.conv2d(cur * m, k, stride=2, padding=1)
+        rm = F.conv2d(m, k, stride=2, padding=1)
+        h, w = raw.shape[2], raw.shape[3]
+        cur = raw / (rm + 1.0e-8)
+        feats.append(cur.reshape(C, h * w))
+        grads.append(spatial_grad(cur.reshape(1, C, h, w)).reshape(2, C, h * w))
+    return torch.cat(feats, 1).contiguous(), torch.cat(grads, 2).contiguous()
+
+
+def valid_locations(mask, cam):
+    """GenerateValidLocations (core/mapping/mapping_utils.h:254-287): idx = v*W+u,
+    homo = ((u-u0)/fx, (v-v0)/fy, 1) in fp32."""
+    f = np.float32
+    m = np.asarray(mask).reshape(-1)
+    loc1d = np.nonzero(m > 0.5)[0].astype(np.int64)
+    W = f(cam[4])
+    x = np.fmod(loc1d.astype(f), W)
+    y = np.floor(loc1d.astype(f) / W)
+    homo = np.stack([(x - f(cam[2])) / f(cam[0]), (y - f(cam[3])) / f(cam[1]), np.ones_like(x)], 1).astype(f)
+    return loc1d, homo
+
+
+def so3_hat(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=w.dtype)
+
+
+def se3_exp(omega, v):
+    """se3_exp (core/mapping/mapping_utils.h:316-346); dtype follows the inputs."""
+    omega = np.asarray(omega)
+    v = np.asarray(v, dtype=omega.dtype)
+    dt = omega.dtype.type
+    theta = dt(np.linalg.norm(omega))
+    n = omega / theta if theta > 0 else np.array([1, 0, 0], dtype=omega.dtype)
+    theta = max(theta, dt(1.0e-14))
+    s, c = dt(np.sin(theta)), dt(np.cos(theta))
+    K = so3_hat(n)
+    K2 = K @ K
+    I = np.eye(3, dtype=omega.dtype)
+    R = I + s * K + (dt(1) - c) * K2
+    V = I + ((dt(1) - c) / theta) * K + ((theta - s) / theta) * K2
+    return R, V @ v
+
+
+def retract(R, t, delta):
+    """Left-multiplicative SE(3) retraction, delta = [v, omega]
+    (core/gtsam/gtsam_traits.h:45-70; camera_tracker.cpp:491-512)."""
+    dR, dt_ = se3_exp(np.asarray(delta[3:6]), np.asarray(delta[0:3]))
+    return dR @ R, dR @ t + dt_
+
+
+def relative_pose(R0, t0, R1, t1):
+    """T10 = T1^-1 T0 as the factors compute it (core/gtsam/photometric_factor.cpp:280-281)."""
+    return R1.T @ R0, R1.T @ (t0 - t1)
+
+
+def rotation_to_angle_axis(R, eps=1.0e-6):
+    """RotationToAngleAxis (core/mapping/mapping_utils.h:145-214) for the generic branch
+    structure of the reference (quaternion via the transposed matrix, then angle-axis)."""
+    m = np.asarray(R, dtype=np.float64).T
+    d2 = m[2, 2] < eps
+    d0_d1 = m[0, 0] > m[1, 1]
+    d0_nd1 = m[0, 0] < -m[1, 1]
+    t0 = 1 + m[0, 0] - m[1, 1] - m[2, 2]
+    q0 = np.array([m[1, 2] - m[2, 1], t0, m[0, 1] + m[1, 0], m[2, 0] + m[0, 2]])
+    t1 = 1 - m[0, 0] + m[1, 1] - m[2, 2]
+    q1 = np.array([m[2, 0] - m[0, 2], m[0, 1] + m[1, 0], t1, m[1, 2] + m[2, 1]])
+    t2 = 1 - m[0, 0] - m[1, 1] + m[2, 2]
+    q2 = np.array([m[0, 1] - m[1, 0], m[2, 0] + m[0, 2], m[1, 2] + m[2, 1], t2])
+    t3 = 1 + m[0, 0] + m[1, 1] + m[2, 2]
+    q3 = np.array([t3, m[1, 2] - m[2, 1], m[2, 0] - m[0, 2], m[0, 1] - m[1, 0]])
+    c0, c1 = d2 and d0_d1, d2 and not d0_d1
+    c2, c3 = (not d2) and d0_nd1, (not d2) and not d0_nd1
+    q = q0 * c0 + q1 * c1 + q2 * c2 + q3 * c3
+    # NOTE reference quirk (mapping_utils.h:187): t0 is multiplied by mask_c1, not mask_c0.
+    q = 0.5 * q / np.sqrt(t0 * c1 + t1 * c1 + t2 * c2 + t3 * c3)
+    s2 = q[1] ** 2 + q[2] ** 2 + q[3] ** 2
+    s = np.sqrt(s2)
+    two_theta = np.arctan2(-s, -q[0]) if q[0] < 0 else np.arctan2(s, q[0])
+    k = two_theta / s if s2 > 0 else 2.0
+    return k * q[1:4]
+
+
+def nearest_psd(M, reference_faithful=True):
+    """NearestPsd (core/mapping/mapping_utils.h:104-128).  reference_faithful=True keeps the
+    reference's V^T S V; False is Higham's V S V^T."""
+    M = np.asarray(M, dtype=np.float64)
+    B = (M + M.T) / 2
+    _, s, Vt = np.linalg.svd(B)
+    V = Vt.T
+    Hm = (V.T @ np.diag(s) @ V) if reference_faithful else (V @ np.diag(s) @ V.T)
+    A2 = (B + Hm) / 2
+    A3 = (A2 + A2.T) / 2
+    k = 1
+    I = np.eye(M.shape[0])
+
+    def is_psd(A):
+        try:
+            np.linalg.cholesky(A)
+            return True
+        except np.linalg.LinAlgError:
+            return False
+
+    while not is_psd(A3):
+        A3 = A3 + I * (-np.linalg.eigvalsh(A3).min() * k + 1e-15)
+        k *= 2
+    return A3
+
+
+def tracker_lm(jac_fn, err_fn, R, t, init_damp=1e-4, min_damp=1e-6, max_damp=1e-2, damp_dec=10.0, damp_inc=100.0,
+               max_iters=40, jac_thresh=1e-2, min_grad=1e-8, min_param_inc=1e-8):
+    """CameraTracker::TrackNewFrame LM loop (core/system/camera_tracker.cpp:1156-1279) over
+    user-supplied jac_fn(R,t)->(AtA,Atb,err) / err_fn(R,t)->err.  fp32 state like the reference.
+    Returns (R, t, error, trace) where trace records (iter, damp, accepted, error)."""
+    f = np.float32
+    R, t = np.asarray(R, f), np.asarray(t, f)
+    prev_error, curr_error = f(0), f(1)
+    damp, it = f(init_damp), 0
+    AtA = Atb = None
+    trace = []
+    cand_err = curr_error
+    while True:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = abs(curr_error - prev_error) / prev_error
+        if ratio > jac_thresh:
+            A, b, e = jac_fn(R, t)
+            AtA, Atb = np.asarray(A, f), np.asarray(b, f).reshape(-1)
+            if it == 0:
+                curr_error = f(e)
+            update_jac = True
+        else:
+            update_jac = False
+        it += 1
+        diag = np.diag(np.diag(AtA))
+        sol = np.linalg.solve((AtA + damp * diag).astype(np.float64), Atb.astype(np.float64)).astype(f)
+        rotvec = rotation_to_angle_axis(R).astype(f)
+        max_grad = np.abs(Atb).max()
+        max_inc = (sol / (np.abs(np.concatenate([t.reshape(-1), rotvec])) + f(1e-8))).max()
+        if max_grad < min_grad or max_inc < min_param_inc:
+            break
+        while True:
+            Rc, tc = retract(R, t, sol)
+            Rc, tc = Rc.astype(f), tc.astype(f)
+            cand_err = f(err_fn(Rc, tc))
+            if cand_err < curr_error:
+                break
+            elif damp < max_damp:
+                damp = f(min(max(min_damp, damp * damp_inc), max_damp))
+                sol = np.linalg.solve((AtA + damp * diag).astype(np.float64), Atb.astype(np.float64)).astype(f)
+            else:
+                break
+        accepted = not (cand_err >= curr_error and damp >= max_damp)
+        trace.append((it, float(damp), bool(accepted), float(cand_err)))
+        if not accepted:
+            break
+        R, t = Rc, tc
+        if update_jac:
+            prev_error = curr_error
+        curr_error = cand_err
+        damp = f(min(max(min_damp, damp / damp_dec), max_damp))
+        if it >= max_iters:
+            break
+    return R, t, float(curr_error), trace
