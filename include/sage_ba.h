@@ -1,0 +1,281 @@
+/*
+ * sage_ba.h -- C ABI of the B200-native dense bundle-adjustment backend for SAGE-SLAM.
+ *
+ * This is the drop-in boundary for the reference's `df_cuda` static library
+ * (/root/reference/system/sources/cuda/CMakeLists.txt:37-46): every `df::*_calculate` free
+ * function the factor classes (core/gtsam/*_factor.cpp) and the camera tracker
+ * (core/system/camera_tracker.cpp) call has one entry point below, with plain pointers and
+ * sizes only -- no torch / ATen / Eigen types.  INTEGRATION.md shows the `df::` shim a
+ * maintainer links in place of df_cuda.
+ *
+ * Conventions
+ *   - All arithmetic is fp32 (the reference hard-codes <float>, photometric_factor_kernels.cpp:1111).
+ *   - Rotations are row-major float[9], translations float[3]; poses are keyframe->world
+ *     (pose_wk); T10 = T1^-1 T0 (gtsam/photometric_factor.cpp:280-281).
+ *   - AtA is row-major [D,D], Atb is [D]; variable order inside a factor is the reference's:
+ *       photometric / reprojection: [pose0(v,w) pose1(v,w) code0(C) scale0]          D = 13+C
+ *       geometric:                  [pose0 pose1 code0(C) code1(C) scale0 scale1]    D = 14+2C
+ *       tracker:                    [rel. pose (v,w)] (+ scale0)                     D = 6 / 7
+ *   - Every function returns 0 on success, non-zero on failure; sage_ba_last_error() gives
+ *     the message.  (The reference prints and exit()s on CUDA errors,
+ *     photometric_factor_kernels.cpp:23-31; the df:: shim maps non-zero to the same.)
+ *   - Calls on one context are serialised on that context's stream; use one context per
+ *     host thread (the reference is called from up to 4 threads, deepfactors.cpp:1497-1505).
+ *   - Pointers are HOST pointers unless the parameter is documented as device memory.
+ */
+#ifndef SAGE_BA_H_
+#define SAGE_BA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGE_BA_MAX_LEVELS 8
+#define SAGE_BA_MAX_CODE 32
+
+enum { SAGE_BA_HOST = 0, SAGE_BA_DEVICE = 1 };
+
+/* df::PinholeCamera<float> (common/pinhole_camera.h:124-130): width/height stored as float. */
+typedef struct sage_ba_camera
+{
+  float fx, fy, u0, v0, width, height;
+} sage_ba_camera;
+
+typedef struct sage_ba_context sage_ba_context;
+typedef struct sage_ba_keyframe sage_ba_keyframe;
+typedef struct sage_ba_problem sage_ba_problem;
+
+/* ------------------------------------------------------------------------------------------
+ * Context: device, stream, workspaces, cuBLAS/cuSOLVER handles.
+ * stream: a cudaStream_t to run on, or NULL to create a private non-blocking stream.
+ * ---------------------------------------------------------------------------------------- */
+int sage_ba_create(sage_ba_context **ctx, int device, void *stream);
+void sage_ba_destroy(sage_ba_context *ctx);
+const char *sage_ba_last_error(const sage_ba_context *ctx);
+const char *sage_ba_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches counter) */
+long sage_ba_launch_count(const sage_ba_context *ctx);
+int sage_ba_synchronize(sage_ba_context *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Keyframe: the immutable per-frame tensors of df::Frame<float> (core/mapping/frame.h:16-125),
+ * handed over in the REFERENCE layouts and re-laid-out once on the device (channel-last
+ * feature+gradient pyramid, pixel-major depth basis).  `memory` says where the pointers live.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sage_ba_keyframe_desc
+{
+  int memory;                          /* SAGE_BA_HOST or SAGE_BA_DEVICE for every pointer below */
+  int height, width, levels;           /* level-0 size, pyramid levels L                          */
+  int feat_channels, code_size;        /* F (16 or 32), C (8, 16 or 32)                           */
+  sage_ba_camera camera;               /* level-0 camera; the pyramid is derived like CameraPyramid */
+  const float *feat_map_pyramid;       /* [F, SP]      Frame::feat_map_pyramid                    */
+  const float *feat_map_grad_pyramid;  /* [2, F, SP]   Frame::feat_map_grad_pyramid (0:dx 1:dy)   */
+  const float *dpt_map_bias;           /* [H*W]        Frame::dpt_map_bias (may be NULL for a tracked frame) */
+  const float *dpt_jac_code;           /* [H*W, C] addressed with the two strides below (elements) */
+  long jac_stride_row, jac_stride_col; /* reference view: (1, H*W) (code_depth_network.cpp:38-39)  */
+  const float *video_mask;             /* [H, W] float 0/1   *Frame::video_mask_ptr               */
+  const int64_t *sampled_locations_1d; /* [N] int64    Frame::sampled_locations_1d (may be NULL)  */
+  const float *sampled_locations_homo; /* [N, 3]       Frame::sampled_locations_homo              */
+  int num_samples;                     /* N                                                       */
+} sage_ba_keyframe_desc;
+
+int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *desc, sage_ba_keyframe **kf);
+void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf);
+/* the CameraPyramid<float> derived for this keyframe (common/camera_pyramid.h:18-32) */
+int sage_ba_keyframe_cameras(const sage_ba_keyframe *kf, sage_ba_camera *cams /* [levels] */, int *level_offsets);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-factor entry points == the reference operator API.  Synchronous: results are in the
+ * HOST output buffers on return (the reference's callers copy them to the host immediately,
+ * gtsam/photometric_factor.cpp:304-306).  n_inliers may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+
+/* df::photometric_jac_error_calculate<CS,FS>  cuda/photometric_factor_kernels.cpp:1061-1164 */
+int sage_ba_photometric_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                  const float *R10, const float *t10, const float *R0, const float *t0,
+                                  const float *R1, const float *t1, const float *code0, float scale0, float eps,
+                                  const float *weights /* [L] */, float *AtA, float *Atb, float *error,
+                                  float *n_inliers);
+
+/* df::photometric_error_calculate<FS>  cuda/photometric_factor_kernels.cpp:990-1059 */
+int sage_ba_photometric_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                              const float *R10, const float *t10, const float *code0, float scale0, float eps,
+                              const float *weights, float *error, float *n_inliers);
+
+/* df::tracker_photo_jac_error_calculate<FS> (:1166-1245) and ..._with_scale (:1247-1325).
+ * with_scale != 0 -> 7x7 system with the scale column (scale0 used), else 6x6.
+ * sampled_dpts_0 [N], sampled_locations_homo_0 [N,3], sampled_features_0 [L,N,F] are DEVICE
+ * pointers (they are device tensors in the tracker, camera_tracker.cpp:1086-1123). */
+int sage_ba_tracker_photo_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *frame1, const float *R,
+                                    const float *t, const float *sampled_dpts_0, const float *sampled_locations_homo_0,
+                                    const float *sampled_features_0, int num_samples, int with_scale, float scale0,
+                                    float eps, const float *weights, float *AtA, float *Atb, float *error,
+                                    float *n_inliers);
+
+/* df::tracker_photo_error_calculate<FS>  (:1327-1384) */
+int sage_ba_tracker_photo_error(sage_ba_context *ctx, const sage_ba_keyframe *frame1, const float *R, const float *t,
+                                const float *sampled_dpts_0, const float *sampled_locations_homo_0,
+                                const float *sampled_features_0, int num_samples, float eps, const float *weights,
+                                float *error, float *n_inliers);
+
+/* The tracker's one-time pre-sampling of the keyframe features at its own sample points
+ * (camera_tracker.cpp:1104-1123: grid_sample, bilinear, zeros padding, align_corners=false),
+ * producing the DEVICE tensors the two calls above take.  out_* are device buffers owned by the
+ * caller: dpts [N], homo [N,3], feats [L,N,F].  dpts = Keyframe::dpt_map at the sample points
+ * = scale0 * (bias + jac . code0). */
+int sage_ba_tracker_presample(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *code0, float scale0,
+                              float *out_dpts, float *out_homo, float *out_feats);
+
+/* df::geometric_jac_error_calculate<CS>  cuda/geometric_factor_kernels.cpp:882-950.
+ * The per-call preparation the reference caller does (depth map of KF1 from code1, its spatial
+ * gradient, the pixel-major basis copy; gtsam/geometric_factor.cpp:317-320,340-342) happens
+ * inside, from code1/scale1. */
+int sage_ba_geometric_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                const float *R10, const float *t10, const float *R0, const float *t0,
+                                const float *R1, const float *t1, const float *code0, const float *code1,
+                                float scale0, float scale1, float eps, float loss_param, float weight, float *AtA,
+                                float *Atb, float *error, float *n_inliers);
+
+/* df::geometric_error_calculate<CS>  (:837-880) */
+int sage_ba_geometric_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                            const float *R10, const float *t10, const float *code0, const float *code1, float scale0,
+                            float scale1, float eps, float loss_param, float weight, float *error,
+                            float *n_inliers);
+
+/* df::reprojection_jac_error_calculate<CS>  cuda/reprojection_factor_kernels.cpp:467-538.
+ * matched_locations_1d_0 [M] int32, matched_locations_homo_0 [M,3], matched_locations_2d_1 [M,2]
+ * are HOST arrays (M <= 4096). */
+int sage_ba_reprojection_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *R10,
+                                   const float *t10, const float *R0, const float *t0, const float *R1,
+                                   const float *t1, const float *code0, float scale0, const int32_t *loc1d,
+                                   const float *homo, const float *match2d, int num_matches, float eps,
+                                   float loss_param, float weight, float *AtA, float *Atb, float *error,
+                                   float *n_inliers);
+
+/* df::reprojection_error_calculate<CS>  (:421-465) */
+int sage_ba_reprojection_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *R10, const float *t10,
+                               const float *code0, float scale0, const int32_t *loc1d, const float *homo,
+                               const float *match2d, int num_matches, float eps, float loss_param, float weight,
+                               float *error, float *n_inliers);
+
+/* df::tracker_reproj_jac_error_calculate (:540-600) / df::tracker_reproj_error_calculate (:602-642).
+ * dpts [M], homo [M,3], match2d [M,2] are HOST arrays. */
+int sage_ba_tracker_reproj_jac_error(sage_ba_context *ctx, const sage_ba_camera *camera, const float *R,
+                                     const float *t, const float *dpts, const float *homo, const float *match2d,
+                                     int num_matches, float eps, float loss_param, float weight, float *AtA,
+                                     float *Atb, float *error, float *n_inliers);
+int sage_ba_tracker_reproj_error(sage_ba_context *ctx, const sage_ba_camera *camera, const float *R, const float *t,
+                                 const float *dpts, const float *homo, const float *match2d, int num_matches,
+                                 float eps, float loss_param, float weight, float *error, float *n_inliers);
+
+/* ------------------------------------------------------------------------------------------
+ * CameraTracker::TrackNewFrame LM loop (core/system/camera_tracker.cpp:1034-1310, loop
+ * :1156-1279): damped Gauss-Newton on the 6-DoF relative pose T_ck of `frame1` w.r.t. `kf0`,
+ * photometric (+ optional reprojection) terms, same damping / acceptance / convergence rules.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sage_ba_tracker_config
+{                                    /* TrackerConfig, configs/slam_run.flags:17-23 */
+  int max_num_iters;                 /* 40   */
+  float init_damp, min_damp, max_damp; /* 1e-4, 1e-6, 1e-2 */
+  float damp_dec_factor, damp_inc_factor; /* 10, 100 */
+  float jac_update_err_inc_threshold; /* 1e-2 */
+  float min_grad_thresh, min_param_inc_thresh;
+  float dpt_eps;
+  float photo_weights[SAGE_BA_MAX_LEVELS];
+  int use_photo, use_reproj;
+  float reproj_loss_param, reproj_weight; /* loss param and inlier_multiplier*factor weight */
+} sage_ba_tracker_config;
+
+typedef struct sage_ba_tracker_report
+{
+  int iterations, jacobian_evals, error_evals;
+  float final_error, final_damp;
+} sage_ba_tracker_report;
+
+/* R, t: in = initial guess of T10 (frame1 <- kf0), out = estimate.  Match arrays (HOST) may be
+ * NULL when use_reproj == 0. */
+int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *frame1,
+                            const float *code0, float scale0, const sage_ba_tracker_config *cfg, float *R, float *t,
+                            const float *match_dpts, const float *match_homo, const float *match2d, int num_matches,
+                            sage_ba_tracker_report *report);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched local bundle adjustment (new; the reference delegates this to GTSAM ISAM2,
+ * core/mapping/mapper.cpp:544).  A problem owns K keyframes' states (pose_wk, code, scale) on
+ * the device and a factor list; one launch linearises every factor of a kind.
+ * Global variable order: [pose_0 .. pose_{K-1} (6 each) | (code_k (C), scale_k) for k = 0..K-1].
+ * ---------------------------------------------------------------------------------------- */
+int sage_ba_problem_create(sage_ba_context *ctx, int num_keyframes, sage_ba_keyframe *const *kfs,
+                           sage_ba_problem **problem);
+void sage_ba_problem_destroy(sage_ba_problem *problem);
+
+int sage_ba_problem_add_photometric(sage_ba_problem *p, int kf0, int kf1, const float *weights /* [L] */);
+int sage_ba_problem_add_geometric(sage_ba_problem *p, int kf0, int kf1, float loss_param, float weight);
+int sage_ba_problem_add_reprojection(sage_ba_problem *p, int kf0, int kf1, const int32_t *loc1d, const float *homo,
+                                     const float *match2d, int num_matches, float loss_param, float weight);
+/* CodeFactor (gtsam/code_factor.cpp:42-104): AtA = w I, Atb = w (init - code), err = w mean((init-code)^2) */
+int sage_ba_problem_add_code_prior(sage_ba_problem *p, int kf, const float *init_code, float weight);
+/* ScaleFactor (gtsam/scale_factor.cpp:115-130) */
+int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale, float weight);
+/* hold a keyframe's pose (and optionally scale) fixed: the gauge anchor (mapper.cpp:190-192) */
+int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale);
+/* restrict this process to the factors with index % world == rank (multi-GPU sharding) */
+int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);
+
+int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses /* [K,12] R row-major then t */,
+                              const float *codes /* [K,C] */, const float *scales /* [K] */, float eps);
+int sage_ba_problem_get_state(sage_ba_problem *p, float *poses, float *codes, float *scales);
+
+int sage_ba_problem_dim(const sage_ba_problem *p);         /* K * (7 + C)                       */
+int sage_ba_problem_num_factors(const sage_ba_problem *p); /* all kinds, priors included        */
+long sage_ba_problem_num_residuals(const sage_ba_problem *p); /* scalar residual rows per linearisation */
+/* packed per-factor output buffer (DEVICE, fp32): every factor's [AtA | Atb | error | inliers];
+ * this is the buffer a multi-GPU host all-reduces (sum) once per LM iteration. */
+int sage_ba_problem_factor_buffer(sage_ba_problem *p, float **device_ptr, size_t *count);
+/* packed per-factor [error | inliers] buffer of the last cost evaluation (DEVICE, fp32) */
+int sage_ba_problem_cost_buffer(sage_ba_problem *p, float **device_ptr, size_t *count);
+
+/* stage 1: linearise this shard's factors at the current state into the factor buffer (async) */
+int sage_ba_problem_linearize(sage_ba_problem *p);
+/* stage 2: assemble H (fp64, dense) and g from the (reduced) factor buffer, add priors (async).
+ * H/g out may be NULL; otherwise HOST buffers [dim*dim] / [dim] filled synchronously. */
+int sage_ba_problem_assemble(sage_ba_problem *p, double *H, double *g, double *cost);
+/* stage 3: solve (H + damp diag(H)) d = g by Schur complement of the code+scale block onto the
+ * pose block (cuSOLVER potrf/potrs), write the candidate state x (+) d; delta may be NULL. */
+int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta /* HOST [dim] or NULL */);
+/* stage 4: evaluate this shard's factor errors at the candidate (which=1) or current (which=0)
+ * state into the cost buffer (async) */
+int sage_ba_problem_evaluate(sage_ba_problem *p, int which);
+/* stage 5: sum the (reduced) cost buffer + priors -> total cost (synchronous) */
+int sage_ba_problem_cost(sage_ba_problem *p, int which, double *cost);
+/* stage 6: make the candidate the current state */
+int sage_ba_problem_accept(sage_ba_problem *p);
+
+typedef int (*sage_ba_allreduce_fn)(void *device_buffer, size_t count, void *user); /* fp32 sum, on ctx stream */
+int sage_ba_problem_set_allreduce(sage_ba_problem *p, sage_ba_allreduce_fn fn, void *user);
+
+typedef struct sage_ba_lm_options
+{
+  int max_iters;
+  double init_damp, min_damp, max_damp, damp_dec_factor, damp_inc_factor;
+  double min_rel_decrease; /* stop when an accepted step lowers the cost by less than this fraction */
+  int max_trials;          /* damping increases per iteration before giving up */
+} sage_ba_lm_options;
+
+typedef struct sage_ba_lm_report
+{
+  int iterations, linearizations, evaluations, accepted;
+  double initial_cost, final_cost, final_damp;
+} sage_ba_lm_report;
+
+/* Full LM loop (linearize -> [allreduce] -> assemble -> solve -> evaluate -> [allreduce] ->
+ * accept/reject), acceptance rule as the tracker's (camera_tracker.cpp:1218-1245). */
+int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_ba_lm_report *report);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGE_BA_H_ */

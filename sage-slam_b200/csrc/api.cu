@@ -1,0 +1,670 @@
+// api.cu -- C ABI (include/sage_ba.h): context, keyframes, the single-factor operator entry points that
+// replace the reference's df::*_calculate functions, and the tracker's LM loop.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sage_internal.h"
+
+using namespace sage;
+
+#define SAGE_TRY(ctx_) \
+  sage_ba_context *ctx__ = (ctx_); \
+  try                  \
+  {
+#define SAGE_CATCH                                   \
+  }                                                  \
+  catch (const sage::Error &e)                       \
+  {                                                  \
+    if (ctx__)                                       \
+      ctx__->err = e.msg;                            \
+    return 1;                                        \
+  }                                                  \
+  catch (const std::exception &e)                    \
+  {                                                  \
+    if (ctx__)                                       \
+      ctx__->err = e.what();                         \
+    return 1;                                        \
+  }                                                  \
+  return 0;
+
+namespace sage
+{
+
+CamPyr make_campyr(const sage_ba_camera &cam, int levels, sage_ba_camera *cams_out)
+{
+  // CameraPyramid<float> (common/camera_pyramid.h:18-32) + ResizeViewport (pinhole_camera_impl.h:120-132)
+  CamPyr p;
+  memset(&p, 0, sizeof(p));
+  p.L = levels;
+  sage_ba_camera c = cam;
+  int off = 0;
+  for (int i = 0; i < levels; ++i)
+  {
+    if (i != 0)
+    {
+      const float nw = (float)((size_t)c.width / 2), nh = (float)((size_t)c.height / 2);
+      const float xr = nw / c.width, yr = nh / c.height;
+      c.fx *= xr;
+      c.fy *= yr;
+      c.u0 *= xr;
+      c.v0 *= yr;
+      c.width = nw;
+      c.height = nh;
+    }
+    if (cams_out)
+      cams_out[i] = c;
+    p.fx[i] = c.fx;
+    p.fy[i] = c.fy;
+    p.w[i] = (int)c.width;
+    p.h[i] = (int)c.height;
+    p.off[i] = off;
+    off += p.w[i] * p.h[i];
+  }
+  p.ofx = cam.fx;
+  p.ofy = cam.fy;
+  p.ocx = cam.u0;
+  p.ocy = cam.v0;
+  p.ow = (int)cam.width;
+  p.oh = (int)cam.height;
+  return p;
+}
+
+static int pick_slices(const sage_ba_context *ctx, int N, int samples_per_step)
+{
+  const int steps = (N + samples_per_step - 1) / samples_per_step;
+  return std::max(1, std::min(steps, 2 * ctx->num_sms));
+}
+
+// run one photometric-type factor and bring [AtA | Atb | error | inliers] to the host
+static void run_photo_single(sage_ba_context *ctx, int mode, int F, int C, const PhotoFactor &f, const CamPyr &pyr, int D, float *AtA,
+                             float *Atb, float *error, float *n_inl)
+{
+  const bool jac = (mode == PH_MAP_JAC || mode == PH_TRK_JAC);
+  const int WP = photo_row_width(mode, C);
+  const int sps = (32 / (F / 4)) * (SAGE_CTA / 32);
+  const int slices = pick_slices(ctx, f.N, sps);
+  const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
+  float *partH = ctx->partH.ensure(jac ? (size_t)slices * WP * WP : 4);
+  float *partE = ctx->partE.ensure((size_t)slices * 2);
+  float *out = ctx->out.ensure(nout);
+  PhotoFactor *df = reinterpret_cast<PhotoFactor *>(ctx->factor.ensure(sizeof(PhotoFactor) > 1024 ? sizeof(PhotoFactor) : 1024));
+  PhotoFactor *hf = reinterpret_cast<PhotoFactor *>(ctx->hfactor.ensure(1024));
+  *hf = f;
+  hf->out = 0;
+  SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(PhotoFactor), cudaMemcpyHostToDevice, ctx->stream));
+  SAGE_CHECK(launch_photo(mode, F, C, df, 1, pyr, slices, partH, partE, out, 1, D, ctx->stream) == 0,
+             "unsupported (feat_channels, code_size) combination");
+  ctx->launches += 2;
+  SAGE_CUDA(cudaGetLastError());
+  float *h = ctx->hout.ensure(nout);
+  SAGE_CUDA(cudaMemcpyAsync(h, out, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  SAGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (jac)
+  {
+    memcpy(AtA, h, sizeof(float) * D * D);
+    memcpy(Atb, h + D * D, sizeof(float) * D);
+  }
+  *error = h[nout - 2];
+  if (n_inl)
+    *n_inl = h[nout - 1];
+}
+
+static void fill_pose(float *dR, float *dt, const float *R, const float *t)
+{
+  memcpy(dR, R, 9 * sizeof(float));
+  if (dt && t)
+    memcpy(dt, t, 3 * sizeof(float));
+}
+
+static void check_pair(const sage_ba_keyframe *a, const sage_ba_keyframe *b)
+{
+  SAGE_CHECK(a && b, "null keyframe");
+  SAGE_CHECK(a->H == b->H && a->W == b->W && a->L == b->L && a->F == b->F && a->C == b->C, "keyframes have different shapes");
+}
+
+} // namespace sage
+
+extern "C" {
+
+const char *sage_ba_version(void) { return "sage-ba-b200 0.1 (sm_100a)"; }
+
+int sage_ba_create(sage_ba_context **out, int device, void *stream)
+{
+  if (!out)
+    return 1;
+  *out = nullptr;
+  sage_ba_context *ctx = new sage_ba_context();
+  sage_ba_context *ctx__ = ctx;
+  try
+  {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw Error{std::string("no CUDA device available: ") + cudaGetErrorString(e)};
+    SAGE_CHECK(device >= 0 && device < count, "device index out of range");
+    ctx->device = device;
+    SAGE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SAGE_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream)
+      ctx->stream = (cudaStream_t)stream;
+    else
+    {
+      SAGE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    SAGE_CHECK(cublasCreate(&ctx->cublas) == CUBLAS_STATUS_SUCCESS, "cublasCreate failed");
+    SAGE_CHECK(cusolverDnCreate(&ctx->cusolver) == CUSOLVER_STATUS_SUCCESS, "cusolverDnCreate failed");
+    cublasSetStream(ctx->cublas, ctx->stream);
+    cusolverDnSetStream(ctx->cusolver, ctx->stream);
+    *out = ctx;
+    return 0;
+  }
+  catch (const Error &e)
+  {
+    fprintf(stderr, "sage_ba_create: %s\n", e.msg.c_str());
+    delete ctx;
+    (void)ctx__;
+    return 1;
+  }
+}
+
+void sage_ba_destroy(sage_ba_context *ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->cublas)
+    cublasDestroy(ctx->cublas);
+  if (ctx->cusolver)
+    cusolverDnDestroy(ctx->cusolver);
+  if (ctx->own_stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *sage_ba_last_error(const sage_ba_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+long sage_ba_launch_count(const sage_ba_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int sage_ba_synchronize(sage_ba_context *ctx)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  SAGE_CATCH
+}
+
+int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d, sage_ba_keyframe **out)
+{
+  SAGE_TRY(ctx)
+  SAGE_CHECK(d && out, "null argument");
+  SAGE_CHECK(d->levels >= 1 && d->levels <= SAGE_BA_MAX_LEVELS, "levels out of range");
+  SAGE_CHECK(d->feat_channels == 16 || d->feat_channels == 32, "feat_channels must be 16 or 32");
+  SAGE_CHECK(d->code_size == 8 || d->code_size == 16 || d->code_size == 32, "code_size must be 8, 16 or 32");
+  SAGE_CHECK((int)d->camera.width == d->width && (int)d->camera.height == d->height, "camera size does not match the maps");
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  sage_ba_keyframe *kf = new sage_ba_keyframe();
+  kf->H = d->height;
+  kf->W = d->width;
+  kf->L = d->levels;
+  kf->F = d->feat_channels;
+  kf->C = d->code_size;
+  kf->N = d->num_samples;
+  kf->pyr = make_campyr(d->camera, d->levels, kf->cams);
+  kf->SP = kf->pyr.off[kf->L - 1] + (long)kf->pyr.w[kf->L - 1] * kf->pyr.h[kf->L - 1];
+  const long SP = kf->SP, HW = (long)kf->H * kf->W;
+  const int F = kf->F, C = kf->C, N = kf->N;
+  cudaStream_t s = ctx->stream;
+  const bool host = d->memory == SAGE_BA_HOST;
+  std::vector<void *> temps;
+  auto stage = [&](const void *src, size_t bytes) -> const void * {
+    if (!host || !src)
+      return src;
+    void *t = nullptr;
+    SAGE_CUDA(cudaMalloc(&t, bytes));
+    temps.push_back(t);
+    SAGE_CUDA(cudaMemcpyAsync(t, src, bytes, cudaMemcpyHostToDevice, s));
+    return t;
+  };
+  try
+  {
+    SAGE_CHECK(d->feat_map_pyramid && d->video_mask, "feat_map_pyramid and video_mask are required");
+    SAGE_CUDA(cudaMalloc(&kf->fg, sizeof(float) * SP * 3 * F));
+    SAGE_CUDA(cudaMalloc(&kf->mask, sizeof(float) * HW));
+    const float *feat = (const float *)stage(d->feat_map_pyramid, sizeof(float) * F * SP);
+    if (d->feat_map_grad_pyramid)
+    {
+      const float *grad = (const float *)stage(d->feat_map_grad_pyramid, sizeof(float) * 2 * F * SP);
+      launch_relayout_fg(feat, grad, kf->fg, F, SP, s);
+      ctx->launches += 3;
+    }
+    else
+    {
+      SAGE_CUDA(cudaMemsetAsync(kf->fg, 0, sizeof(float) * SP * 3 * F, s));
+      launch_relayout_fg(feat, nullptr, kf->fg, F, SP, s);
+      ctx->launches += 1;
+    }
+    SAGE_CUDA(cudaMemcpyAsync(kf->mask, d->video_mask, sizeof(float) * HW, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    if (d->dpt_map_bias)
+    {
+      SAGE_CHECK(d->dpt_jac_code, "dpt_jac_code is required with dpt_map_bias");
+      SAGE_CUDA(cudaMalloc(&kf->bias, sizeof(float) * HW));
+      SAGE_CUDA(cudaMalloc(&kf->basis, sizeof(float) * HW * C));
+      SAGE_CUDA(cudaMalloc(&kf->dgm, sizeof(float4) * HW));
+      SAGE_CUDA(cudaMalloc(&kf->dscr, sizeof(float) * HW));
+      SAGE_CUDA(cudaMemcpyAsync(kf->bias, d->dpt_map_bias, sizeof(float) * HW, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+      // the strided view may address any element of the C*HW block
+      const float *jac = (const float *)stage(d->dpt_jac_code, sizeof(float) * HW * C);
+      launch_relayout_basis(jac, d->jac_stride_row, d->jac_stride_col, kf->basis, (int)HW, C, s);
+      ctx->launches += 1;
+    }
+    if (N > 0)
+    {
+      SAGE_CHECK(d->sampled_locations_homo, "sampled_locations_homo is required when num_samples > 0");
+      SAGE_CUDA(cudaMalloc(&kf->homo, sizeof(float4) * N));
+      const float *h3 = (const float *)stage(d->sampled_locations_homo, sizeof(float) * 3 * N);
+      launch_pack_homo(h3, kf->homo, N, s);
+      ctx->launches += 1;
+      if (d->sampled_locations_1d)
+      {
+        SAGE_CUDA(cudaMalloc(&kf->loc1d, sizeof(int) * N));
+        const int64_t *l64 = (const int64_t *)stage(d->sampled_locations_1d, sizeof(int64_t) * N);
+        launch_convert_loc(l64, kf->loc1d, N, s);
+        ctx->launches += 1;
+      }
+    }
+    SAGE_CUDA(cudaGetLastError());
+    SAGE_CUDA(cudaStreamSynchronize(s));
+  }
+  catch (...)
+  {
+    for (void *t : temps)
+      cudaFree(t);
+    sage_ba_keyframe_destroy(ctx, kf);
+    throw;
+  }
+  for (void *t : temps)
+    cudaFree(t);
+  *out = kf;
+  SAGE_CATCH
+}
+
+void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf)
+{
+  if (!kf)
+    return;
+  if (ctx)
+    cudaSetDevice(ctx->device);
+  cudaFree(kf->fg);
+  cudaFree(kf->bias);
+  cudaFree(kf->basis);
+  cudaFree(kf->mask);
+  cudaFree(kf->loc1d);
+  cudaFree(kf->homo);
+  cudaFree(kf->dgm);
+  cudaFree(kf->dscr);
+  delete kf;
+}
+
+int sage_ba_keyframe_cameras(const sage_ba_keyframe *kf, sage_ba_camera *cams, int *level_offsets)
+{
+  if (!kf)
+    return 1;
+  for (int i = 0; i < kf->L; ++i)
+  {
+    if (cams)
+      cams[i] = kf->cams[i];
+    if (level_offsets)
+      level_offsets[i] = kf->pyr.off[i];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-factor operator API
+// ------------------------------------------------------------------------------------------------
+static PhotoFactor photo_map_factor(const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10, const float *t10,
+                                    const float *R0, const float *t0, const float *R1, const float *code0, float scale0, float eps,
+                                    const float *weights)
+{
+  check_pair(kf0, kf1);
+  SAGE_CHECK(kf0->bias && kf0->basis && kf0->loc1d && kf0->homo, "kf0 lacks depth / sample data");
+  PhotoFactor f;
+  memset(&f, 0, sizeof(f));
+  f.fg0 = kf0->fg;
+  f.fg1 = kf1->fg;
+  f.mask1 = kf1->mask;
+  f.bias0 = kf0->bias;
+  f.basis0 = kf0->basis;
+  f.loc1d = kf0->loc1d;
+  f.homo = kf0->homo;
+  f.N = kf0->N;
+  fill_pose(f.R10, f.t10, R10, t10);
+  if (R0)
+    fill_pose(f.R0, f.t0, R0, t0);
+  if (R1)
+    fill_pose(f.R1, nullptr, R1, nullptr);
+  memcpy(f.code0, code0, sizeof(float) * kf0->C);
+  f.scale0 = scale0;
+  f.eps = eps;
+  memcpy(f.w, weights, sizeof(float) * kf0->L);
+  return f;
+}
+
+int sage_ba_photometric_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                                  const float *t10, const float *R0, const float *t0, const float *R1, const float *t1,
+                                  const float *code0, float scale0, float eps, const float *weights, float *AtA, float *Atb,
+                                  float *error, float *n_inliers)
+{
+  (void)t1;
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  PhotoFactor f = photo_map_factor(kf0, kf1, R10, t10, R0, t0, R1, code0, scale0, eps, weights);
+  run_photo_single(ctx, PH_MAP_JAC, kf0->F, kf0->C, f, kf1->pyr, 13 + kf0->C, AtA, Atb, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_photometric_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                              const float *t10, const float *code0, float scale0, float eps, const float *weights, float *error,
+                              float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  PhotoFactor f = photo_map_factor(kf0, kf1, R10, t10, nullptr, nullptr, nullptr, code0, scale0, eps, weights);
+  run_photo_single(ctx, PH_MAP_ERR, kf0->F, kf0->C, f, kf1->pyr, 0, nullptr, nullptr, error, n_inliers);
+  SAGE_CATCH
+}
+
+static PhotoFactor photo_trk_factor(const sage_ba_keyframe *fr1, const float *R, const float *t, const float *dpts, const float *homo4,
+                                    const float *feats, int N, float scale0, float eps, const float *weights)
+{
+  SAGE_CHECK(fr1, "null frame");
+  PhotoFactor f;
+  memset(&f, 0, sizeof(f));
+  f.fg1 = fr1->fg;
+  f.mask1 = fr1->mask;
+  f.homo = reinterpret_cast<const float4 *>(homo4);
+  f.sfeat0 = feats;
+  f.dpts0 = dpts;
+  f.N = N;
+  fill_pose(f.R10, f.t10, R, t);
+  f.scale0 = scale0;
+  f.eps = eps;
+  memcpy(f.w, weights, sizeof(float) * fr1->L);
+  return f;
+}
+
+// homo [N,3] (device) -> packed float4 in the context scratch
+static const float *pack_homo_scratch(sage_ba_context *ctx, const float *homo3, int N)
+{
+  float *h4 = ctx->scratch.ensure((size_t)N * 4);
+  launch_pack_homo(homo3, reinterpret_cast<float4 *>(h4), N, ctx->stream);
+  ctx->launches += 1;
+  return h4;
+}
+
+int sage_ba_tracker_photo_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *frame1, const float *R, const float *t,
+                                    const float *sampled_dpts_0, const float *sampled_locations_homo_0, const float *sampled_features_0,
+                                    int num_samples, int with_scale, float scale0, float eps, const float *weights, float *AtA,
+                                    float *Atb, float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(!with_scale || scale0 != 0.f, "scale0 must be non-zero");
+  const float *h4 = pack_homo_scratch(ctx, sampled_locations_homo_0, num_samples);
+  PhotoFactor f = photo_trk_factor(frame1, R, t, sampled_dpts_0, h4, sampled_features_0, num_samples, with_scale ? scale0 : 0.f, eps, weights);
+  run_photo_single(ctx, PH_TRK_JAC, frame1->F, frame1->C, f, frame1->pyr, with_scale ? 7 : 6, AtA, Atb, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_tracker_photo_error(sage_ba_context *ctx, const sage_ba_keyframe *frame1, const float *R, const float *t,
+                                const float *sampled_dpts_0, const float *sampled_locations_homo_0, const float *sampled_features_0,
+                                int num_samples, float eps, const float *weights, float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  const float *h4 = pack_homo_scratch(ctx, sampled_locations_homo_0, num_samples);
+  PhotoFactor f = photo_trk_factor(frame1, R, t, sampled_dpts_0, h4, sampled_features_0, num_samples, 0.f, eps, weights);
+  run_photo_single(ctx, PH_TRK_ERR, frame1->F, frame1->C, f, frame1->pyr, 0, nullptr, nullptr, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_tracker_presample(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *code0, float scale0, float *out_dpts,
+                              float *out_homo, float *out_feats)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(kf0 && kf0->bias && kf0->loc1d, "kf0 lacks depth / sample data");
+  float *dcode = ctx->tmp_code.ensure(SAGE_MAX_CODE);
+  float *hc = reinterpret_cast<float *>(ctx->hfactor.ensure(1024));
+  memcpy(hc, code0, sizeof(float) * kf0->C);
+  SAGE_CUDA(cudaMemcpyAsync(dcode, hc, sizeof(float) * kf0->C, cudaMemcpyHostToDevice, ctx->stream));
+  launch_presample(kf0->fg, kf0->bias, kf0->basis, kf0->loc1d, kf0->homo, dcode, scale0, kf0->pyr, kf0->F, kf0->C, kf0->N, out_dpts,
+                   out_homo, out_feats, ctx->stream);
+  ctx->launches += 1;
+  SAGE_CUDA(cudaGetLastError());
+  SAGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  SAGE_CATCH
+}
+
+// geometric ---------------------------------------------------------------------------------------
+static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                           const float *t10, const float *R0, const float *t0, const float *R1, const float *code0, const float *code1,
+                           float scale0, float scale1, float eps, float loss_param, float weight, float *AtA, float *Atb, float *error,
+                           float *n_inl)
+{
+  check_pair(kf0, kf1);
+  SAGE_CHECK(kf0->bias && kf0->loc1d && kf1->bias, "keyframes lack depth / sample data");
+  const int C = kf0->C, D = 14 + 2 * C;
+  cudaStream_t s = ctx->stream;
+  // KF1's depth map + gradient from (code1) -- gtsam/geometric_factor.cpp:317-320 moved inside
+  float *dcode = ctx->tmp_code.ensure(SAGE_MAX_CODE);
+  float *hc = reinterpret_cast<float *>(ctx->hfactor.ensure(1024));
+  memcpy(hc + 512 / 4, code1, sizeof(float) * C);
+  SAGE_CUDA(cudaMemcpyAsync(dcode, hc + 512 / 4, sizeof(float) * C, cudaMemcpyHostToDevice, s));
+  launch_depth_maps(kf1->bias, kf1->basis, dcode, kf1->mask, kf1->dgm, kf1->dscr, kf1->H, kf1->W, C, s);
+  ctx->launches += 2;
+
+  GeoFactor f;
+  memset(&f, 0, sizeof(f));
+  f.bias0 = kf0->bias;
+  f.basis0 = kf0->basis;
+  f.loc1d = kf0->loc1d;
+  f.homo = kf0->homo;
+  f.dgm1 = kf1->dgm;
+  f.basis1 = kf1->basis;
+  f.N = kf0->N;
+  fill_pose(f.R10, f.t10, R10, t10);
+  if (R0)
+    fill_pose(f.R0, f.t0, R0, t0);
+  if (R1)
+    fill_pose(f.R1, nullptr, R1, nullptr);
+  memcpy(f.code0, code0, sizeof(float) * C);
+  f.scale0 = scale0;
+  f.scale1 = scale1;
+  f.dscale = scale1;
+  f.eps = eps;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  f.out = 0;
+
+  const int WP = geo_row_width(C);
+  const int sps = (32 / (C / 4)) * (SAGE_CTA / 32);
+  const int slices = pick_slices(ctx, f.N, sps);
+  const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
+  float *partH = ctx->partH.ensure(jac ? (size_t)slices * WP * WP : 4);
+  float *partE = ctx->partE.ensure((size_t)slices * 2);
+  float *out = ctx->out.ensure(nout);
+  GeoFactor *df = reinterpret_cast<GeoFactor *>(ctx->factor.ensure(1024));
+  GeoFactor *hf = reinterpret_cast<GeoFactor *>(ctx->hfactor.ensure(1024));
+  static_assert(sizeof(GeoFactor) <= 512 && sizeof(PhotoFactor) <= 1024 && sizeof(ReprojFactor) <= 1024, "factor struct too large");
+  *hf = f;
+  SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(GeoFactor), cudaMemcpyHostToDevice, s));
+  const sage_ba_camera &cam = kf1->cams[0];
+  SAGE_CHECK(launch_geo(jac, C, df, 1, kf1->W, kf1->H, cam.fx, cam.fy, cam.u0, cam.v0, slices, partH, partE, out, 1, s) == 0,
+             "unsupported code_size");
+  ctx->launches += 2;
+  SAGE_CUDA(cudaGetLastError());
+  float *h = ctx->hout.ensure(nout);
+  SAGE_CUDA(cudaMemcpyAsync(h, out, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  if (jac)
+  {
+    memcpy(AtA, h, sizeof(float) * D * D);
+    memcpy(Atb, h + D * D, sizeof(float) * D);
+  }
+  *error = h[nout - 2];
+  if (n_inl)
+    *n_inl = h[nout - 1];
+}
+
+int sage_ba_geometric_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                                const float *t10, const float *R0, const float *t0, const float *R1, const float *t1,
+                                const float *code0, const float *code1, float scale0, float scale1, float eps, float loss_param,
+                                float weight, float *AtA, float *Atb, float *error, float *n_inliers)
+{
+  (void)t1;
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  run_geo_single(ctx, true, kf0, kf1, R10, t10, R0, t0, R1, code0, code1, scale0, scale1, eps, loss_param, weight, AtA, Atb, error,
+                 n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_geometric_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                            const float *t10, const float *code0, const float *code1, float scale0, float scale1, float eps,
+                            float loss_param, float weight, float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  run_geo_single(ctx, false, kf0, kf1, R10, t10, nullptr, nullptr, nullptr, code0, code1, scale0, scale1, eps, loss_param, weight,
+                 nullptr, nullptr, error, n_inliers);
+  SAGE_CATCH
+}
+
+// reprojection ------------------------------------------------------------------------------------
+static void run_reproj_single(sage_ba_context *ctx, bool jac, bool tracker, const sage_ba_keyframe *kf0, const sage_ba_camera &cam,
+                              const float *R10, const float *t10, const float *R0, const float *t0, const float *R1, const float *code0,
+                              float scale0, const int32_t *loc1d, const float *dpts, const float *homo, const float *match2d, int M,
+                              float eps, float loss_param, float weight, float *AtA, float *Atb, float *error, float *n_inl)
+{
+  SAGE_CHECK(M >= 0 && M <= 4096, "num_matches out of range");
+  cudaStream_t s = ctx->stream;
+  const int C = tracker ? 8 : kf0->C;
+  const int D = tracker ? 6 : 13 + C;
+  // upload the match arrays (they live on the host in this entry point)
+  float *dm = ctx->trk_m_homo.ensure((size_t)std::max(M, 1) * 8);
+  float *hm = ctx->hout.ensure(std::max<size_t>((size_t)M * 8, (size_t)D * D + D + 2));
+  // layout: homo [M,3] | match2d [M,2] | dpts-or-loc [M] (as raw 32-bit)
+  memcpy(hm, homo, sizeof(float) * 3 * M);
+  memcpy(hm + 3 * M, match2d, sizeof(float) * 2 * M);
+  if (tracker)
+    memcpy(hm + 5 * M, dpts, sizeof(float) * M);
+  else
+    memcpy(hm + 5 * M, loc1d, sizeof(int32_t) * M);
+  SAGE_CUDA(cudaMemcpyAsync(dm, hm, sizeof(float) * 6 * M, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaStreamSynchronize(s)); // hm is reused for the result below
+
+  ReprojFactor f;
+  memset(&f, 0, sizeof(f));
+  f.homo = dm;
+  f.match2d = dm + 3 * M;
+  if (tracker)
+    f.dpts0 = dm + 5 * M;
+  else
+  {
+    SAGE_CHECK(kf0 && kf0->bias, "kf0 lacks depth data");
+    f.loc1d = reinterpret_cast<const int *>(dm + 5 * M);
+    f.bias0 = kf0->bias;
+    f.basis0 = kf0->basis;
+    memcpy(f.code0, code0, sizeof(float) * C);
+  }
+  f.M = M;
+  fill_pose(f.R10, f.t10, R10, t10);
+  if (R0)
+    fill_pose(f.R0, f.t0, R0, t0);
+  if (R1)
+    fill_pose(f.R1, nullptr, R1, nullptr);
+  f.scale0 = scale0;
+  f.eps = eps;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  f.fx = cam.fx;
+  f.fy = cam.fy;
+  f.cx = cam.u0;
+  f.cy = cam.v0;
+  f.out = 0;
+  const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
+  float *out = ctx->out.ensure(nout);
+  ReprojFactor *df = reinterpret_cast<ReprojFactor *>(ctx->factor.ensure(1024));
+  ReprojFactor *hf = reinterpret_cast<ReprojFactor *>(ctx->hfactor.ensure(1024));
+  *hf = f;
+  SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(ReprojFactor), cudaMemcpyHostToDevice, s));
+  SAGE_CHECK(launch_reproj(jac, tracker, C, df, 1, out, 1, s) == 0, "unsupported code_size");
+  ctx->launches += 1;
+  SAGE_CUDA(cudaGetLastError());
+  SAGE_CUDA(cudaMemcpyAsync(hm, out, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  if (jac)
+  {
+    memcpy(AtA, hm, sizeof(float) * D * D);
+    memcpy(Atb, hm + D * D, sizeof(float) * D);
+  }
+  *error = hm[nout - 2];
+  if (n_inl)
+    *n_inl = hm[nout - 1];
+}
+
+int sage_ba_reprojection_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *R10, const float *t10,
+                                   const float *R0, const float *t0, const float *R1, const float *t1, const float *code0,
+                                   float scale0, const int32_t *loc1d, const float *homo, const float *match2d, int num_matches,
+                                   float eps, float loss_param, float weight, float *AtA, float *Atb, float *error, float *n_inliers)
+{
+  (void)t1;
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(kf0, "null keyframe");
+  run_reproj_single(ctx, true, false, kf0, kf0->cams[0], R10, t10, R0, t0, R1, code0, scale0, loc1d, nullptr, homo, match2d, num_matches,
+                    eps, loss_param, weight, AtA, Atb, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_reprojection_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const float *R10, const float *t10, const float *code0,
+                               float scale0, const int32_t *loc1d, const float *homo, const float *match2d, int num_matches, float eps,
+                               float loss_param, float weight, float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(kf0, "null keyframe");
+  run_reproj_single(ctx, false, false, kf0, kf0->cams[0], R10, t10, nullptr, nullptr, nullptr, code0, scale0, loc1d, nullptr, homo,
+                    match2d, num_matches, eps, loss_param, weight, nullptr, nullptr, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_tracker_reproj_jac_error(sage_ba_context *ctx, const sage_ba_camera *camera, const float *R, const float *t,
+                                     const float *dpts, const float *homo, const float *match2d, int num_matches, float eps,
+                                     float loss_param, float weight, float *AtA, float *Atb, float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(camera, "null camera");
+  run_reproj_single(ctx, true, true, nullptr, *camera, R, t, nullptr, nullptr, nullptr, nullptr, 1.f, nullptr, dpts, homo, match2d,
+                    num_matches, eps, loss_param, weight, AtA, Atb, error, n_inliers);
+  SAGE_CATCH
+}
+
+int sage_ba_tracker_reproj_error(sage_ba_context *ctx, const sage_ba_camera *camera, const float *R, const float *t, const float *dpts,
+                                 const float *homo, const float *match2d, int num_matches, float eps, float loss_param, float weight,
+                                 float *error, float *n_inliers)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(camera, "null camera");
+  run_reproj_single(ctx, false, true, nullptr, *camera, R, t, nullptr, nullptr, nullptr, nullptr, 1.f, nullptr, dpts, homo, match2d,
+                    num_matches, eps, loss_param, weight, nullptr, nullptr, error, n_inliers);
+  SAGE_CATCH
+}
+
+} // extern "C"

@@ -1,0 +1,1073 @@
+// problem.cu -- batched local bundle adjustment: device-resident state, one launch per factor kind,
+// dense fp64 normal equations, Schur complement of the code+scale block onto the pose block with
+// cuSOLVER, and the host LM loop.  New design: the reference hands this to GTSAM ISAM2
+// (core/mapping/mapper.cpp:544); the per-factor arithmetic is the reference's (a1, a4, a5 of SURVEY.md
+// section 8), the priors are CodeFactor / ScaleFactor (core/gtsam/code_factor.cpp:42-104,
+// scale_factor.cpp:115-130) and the retraction is the left-multiplicative one of
+// core/gtsam/gtsam_traits.h:45-70.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sage_internal.h"
+
+using namespace sage;
+
+namespace sage
+{
+
+struct FactorMeta
+{
+  int kind; // 0 photometric, 1 geometric, 2 reprojection
+  int i, j;
+  int D;
+  int off;      // offset of [AtA | Atb | error | inliers] in the factor buffer
+  int cost_off; // offset of [error | inliers] in the cost buffer
+};
+
+struct PriorSpec
+{
+  int kind; // 0 code, 1 scale
+  int kf;
+  float weight;
+  float init_scale;
+  float init_code[SAGE_MAX_CODE];
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rel_pose(const float *P0, const float *P1, float *R10, float *t10)
+{
+  // R10 = R1^T R0, t10 = R1^T (t0 - t1)   (core/gtsam/photometric_factor.cpp:280-281), fp32
+  const float *R0 = P0, *t0 = P0 + 9, *R1 = P1, *t1 = P1 + 9;
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int c = 0; c < 3; ++c)
+      R10[r * 3 + c] = R1[0 * 3 + r] * R0[0 * 3 + c] + R1[1 * 3 + r] * R0[1 * 3 + c] + R1[2 * 3 + r] * R0[2 * 3 + c];
+    t10[r] = R1[0 * 3 + r] * (t0[0] - t1[0]) + R1[1 * 3 + r] * (t0[1] - t1[1]) + R1[2 * 3 + r] * (t0[2] - t1[2]);
+  }
+}
+
+__global__ void setup_photo_kernel(PhotoFactor *f, const int2 *ij, const int2 *offs, int n, const float *poses, const float *codes,
+                                   const float *scales, int C, float eps, int jac)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n)
+    return;
+  const int i = ij[t].x, j = ij[t].y;
+  const float *P0 = poses + i * 12, *P1 = poses + j * 12;
+  PhotoFactor &o = f[t];
+  rel_pose(P0, P1, o.R10, o.t10);
+  for (int k = 0; k < 9; ++k)
+  {
+    o.R0[k] = P0[k];
+    o.R1[k] = P1[k];
+  }
+  for (int k = 0; k < 3; ++k)
+    o.t0[k] = P0[9 + k];
+  for (int k = 0; k < C; ++k)
+    o.code0[k] = codes[i * C + k];
+  o.scale0 = scales[i];
+  o.eps = eps;
+  o.out = jac ? offs[t].x : offs[t].y;
+}
+
+__global__ void setup_geo_kernel(GeoFactor *f, const int2 *ij, const int2 *offs, int n, const float *poses, const float *codes,
+                                 const float *scales, int C, float eps, int jac)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n)
+    return;
+  const int i = ij[t].x, j = ij[t].y;
+  const float *P0 = poses + i * 12, *P1 = poses + j * 12;
+  GeoFactor &o = f[t];
+  rel_pose(P0, P1, o.R10, o.t10);
+  for (int k = 0; k < 9; ++k)
+  {
+    o.R0[k] = P0[k];
+    o.R1[k] = P1[k];
+  }
+  for (int k = 0; k < 3; ++k)
+    o.t0[k] = P0[9 + k];
+  for (int k = 0; k < C; ++k)
+    o.code0[k] = codes[i * C + k];
+  o.scale0 = scales[i];
+  o.scale1 = scales[j];
+  o.dscale = scales[j];
+  o.eps = eps;
+  o.out = jac ? offs[t].x : offs[t].y;
+}
+
+__global__ void setup_reproj_kernel(ReprojFactor *f, const int2 *ij, const int2 *offs, int n, const float *poses, const float *codes,
+                                    const float *scales, int C, float eps, int jac)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n)
+    return;
+  const int i = ij[t].x, j = ij[t].y;
+  const float *P0 = poses + i * 12, *P1 = poses + j * 12;
+  ReprojFactor &o = f[t];
+  rel_pose(P0, P1, o.R10, o.t10);
+  for (int k = 0; k < 9; ++k)
+  {
+    o.R0[k] = P0[k];
+    o.R1[k] = P1[k];
+  }
+  for (int k = 0; k < 3; ++k)
+    o.t0[k] = P0[9 + k];
+  for (int k = 0; k < C; ++k)
+    o.code0[k] = codes[i * C + k];
+  o.scale0 = scales[i];
+  o.eps = eps;
+  o.out = jac ? offs[t].x : offs[t].y;
+}
+
+// D[k][p] = bias_k[p] + basis_k[p,:] . code_k   for every keyframe k (grid.y)
+struct KfMaps
+{
+  const float *bias, *basis, *mask;
+  float4 *dgm;
+  float *dscr;
+};
+
+__global__ void depth_unscaled_batched_kernel(const KfMaps *maps, const float *codes, int HW, int C)
+{
+  __shared__ float sc[SAGE_MAX_CODE];
+  const int k = blockIdx.y;
+  if (threadIdx.x < C)
+    sc[threadIdx.x] = codes[k * C + threadIdx.x];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW)
+    return;
+  const KfMaps m = maps[k];
+  float acc = 0.f;
+  const float4 *row = reinterpret_cast<const float4 *>(m.basis + (size_t)p * C);
+  for (int q = 0; q < C / 4; ++q)
+  {
+    const float4 v = __ldg(row + q);
+    acc += v.x * sc[4 * q] + v.y * sc[4 * q + 1] + v.z * sc[4 * q + 2] + v.w * sc[4 * q + 3];
+  }
+  m.dscr[p] = __ldg(m.bias + p) + acc;
+}
+
+__global__ void depth_pack_batched_kernel(const KfMaps *maps, int H, int W)
+{
+  const KfMaps m = maps[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W)
+    return;
+  const int y = p / W, x = p - y * W;
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  const float *D = m.dscr;
+  m.dgm[p] = make_float4(D[p], 0.5f * (D[y * W + xp] - D[y * W + xm]), 0.5f * (D[yp * W + x] - D[ym * W + x]), m.mask[p]);
+}
+
+__device__ __forceinline__ int var_index(const FactorMeta &m, int c, int K, int C)
+{
+  const int cb_i = 6 * K + m.i * (C + 1), cb_j = 6 * K + m.j * (C + 1);
+  if (c < 6)
+    return 6 * m.i + c;
+  if (c < 12)
+    return 6 * m.j + (c - 6);
+  if (m.kind == 1)
+  {
+    if (c < 12 + C)
+      return cb_i + (c - 12);
+    if (c < 12 + 2 * C)
+      return cb_j + (c - 12 - C);
+    return c == 12 + 2 * C ? cb_i + C : cb_j + C;
+  }
+  if (c < 12 + C)
+    return cb_i + (c - 12);
+  return cb_i + C;
+}
+
+// H (fp64, dense n x n) += every factor's AtA scattered to the global variable order; g += Atb
+__global__ void assemble_kernel(const float *__restrict__ fbuf, const FactorMeta *__restrict__ metas, double *__restrict__ H,
+                                double *__restrict__ g, int n, int K, int C)
+{
+  const FactorMeta m = metas[blockIdx.x];
+  const float *A = fbuf + m.off;
+  const int D = m.D;
+  for (int e = threadIdx.x; e < D * D; e += blockDim.x)
+  {
+    const float v = A[e];
+    if (v != 0.f)
+      atomicAdd(&H[(size_t)var_index(m, e / D, K, C) * n + var_index(m, e % D, K, C)], (double)v);
+  }
+  for (int r = threadIdx.x; r < D; r += blockDim.x)
+    atomicAdd(&g[var_index(m, r, K, C)], (double)A[D * D + r]);
+}
+
+// priors: CodeFactor (AtA = w I, Atb = w (init - code), err = w mean((init-code)^2)) and ScaleFactor
+// (AtA = w/s^2, Atb = w/s (log s0 - log s), err = w (log s0 - log s)^2).  One block.
+__global__ void priors_kernel(const PriorSpec *pr, int np, const float *codes, const float *scales, double *H, double *g,
+                              double *prior_cost, int n, int K, int C, int add_to_system)
+{
+  __shared__ double red[256];
+  double cost = 0.0;
+  for (int q = 0; q < np; ++q)
+  {
+    const PriorSpec &p = pr[q];
+    const int cb = 6 * K + p.kf * (C + 1);
+    if (p.kind == 0)
+    {
+      for (int c = threadIdx.x; c < C; c += blockDim.x)
+      {
+        const double diff = (double)p.init_code[c] - (double)codes[p.kf * C + c];
+        cost += (double)p.weight * diff * diff / (double)C;
+        if (add_to_system)
+        {
+          H[(size_t)(cb + c) * n + cb + c] += (double)p.weight;
+          g[cb + c] += (double)p.weight * diff;
+        }
+      }
+    }
+    else if (threadIdx.x == 0)
+    {
+      const double s = (double)scales[p.kf];
+      const double d = log((double)p.init_scale) - log(s);
+      cost += (double)p.weight * d * d;
+      if (add_to_system)
+      {
+        H[(size_t)(cb + C) * n + cb + C] += (double)p.weight / (s * s);
+        g[cb + C] += (double)p.weight / s * d;
+      }
+    }
+    __syncthreads();
+  }
+  red[threadIdx.x] = cost;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1)
+  {
+    if (threadIdx.x < s)
+      red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *prior_cost = red[0];
+}
+
+// total = sum_f buf[pos_f] + prior   (fixed order, fp64)
+__global__ void total_cost_kernel(const float *buf, const int *pos, int nf, const double *prior, double *total)
+{
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int f = threadIdx.x; f < nf; f += blockDim.x)
+    s += (double)buf[pos[f]];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1)
+  {
+    if (threadIdx.x < k)
+      red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *total = red[0] + *prior;
+}
+
+// Hd = H with damped diagonal; fixed variables become identity rows/cols with zero gradient
+__global__ void damp_kernel(const double *H, const double *g, const unsigned char *fixed, double *Hd, double *gd, int n, double damp)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n * n)
+    return;
+  const int r = (int)(e / n), c = (int)(e % n);
+  double v = H[e];
+  if (fixed[r] || fixed[c])
+    v = (r == c) ? 1.0 : 0.0;
+  else if (r == c)
+  {
+    v = v + damp * v;
+    if (!(v > 0.0))
+      v = 1.0; // variable untouched by any factor: keep the system positive definite
+  }
+  Hd[e] = v;
+  if (c == 0)
+    gd[r] = fixed[r] ? 0.0 : g[r];
+}
+
+__device__ void se3_exp_dev(const float *w, const float *v, float *R, float *t)
+{
+  // se3_exp (core/mapping/mapping_utils.h:316-346), fp32
+  float theta = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  float nx = 1.f, ny = 0.f, nz = 0.f;
+  if (theta > 0.f)
+  {
+    nx = w[0] / theta;
+    ny = w[1] / theta;
+    nz = w[2] / theta;
+  }
+  theta = fmaxf(theta, 1.0e-14f);
+  const float s = sinf(theta), c = cosf(theta);
+  const float K[9] = {0.f, -nz, ny, nz, 0.f, -nx, -ny, nx, 0.f};
+  float K2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q)
+      K2[r * 3 + q] = K[r * 3 + 0] * K[0 * 3 + q] + K[r * 3 + 1] * K[1 * 3 + q] + K[r * 3 + 2] * K[2 * 3 + q];
+  const float a = (1.0f - c) / theta, b = (theta - s) / theta;
+  for (int r = 0; r < 3; ++r)
+  {
+    float tv = 0.f;
+    for (int q = 0; q < 3; ++q)
+    {
+      const float id = r == q ? 1.f : 0.f;
+      R[r * 3 + q] = id + s * K[r * 3 + q] + (1.0f - c) * K2[r * 3 + q];
+      tv += (id + a * K[r * 3 + q] + b * K2[r * 3 + q]) * v[q];
+    }
+    t[r] = tv;
+  }
+}
+
+// candidate = x (+) delta : pose <- exp([v, w]) * pose (left multiplication), code += dc, scale += ds
+__global__ void retract_kernel(const float *poses, const float *codes, const float *scales, const double *delta, float *poses_c,
+                               float *codes_c, float *scales_c, int K, int C)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K)
+    return;
+  float v[3], w[3], dR[9], dt[3];
+  for (int q = 0; q < 3; ++q)
+  {
+    v[q] = (float)delta[6 * k + q];
+    w[q] = (float)delta[6 * k + 3 + q];
+  }
+  se3_exp_dev(w, v, dR, dt);
+  const float *R = poses + k * 12, *t = R + 9;
+  float *Rc = poses_c + k * 12, *tc = Rc + 9;
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int q = 0; q < 3; ++q)
+      Rc[r * 3 + q] = dR[r * 3 + 0] * R[0 * 3 + q] + dR[r * 3 + 1] * R[1 * 3 + q] + dR[r * 3 + 2] * R[2 * 3 + q];
+    tc[r] = dR[r * 3 + 0] * t[0] + dR[r * 3 + 1] * t[1] + dR[r * 3 + 2] * t[2] + dt[r];
+  }
+  const int cb = 6 * K + k * (C + 1);
+  for (int c = 0; c < C; ++c)
+    codes_c[k * C + c] = codes[k * C + c] + (float)delta[cb + c];
+  scales_c[k] = scales[k] + (float)delta[cb + C];
+}
+
+} // namespace sage
+
+struct sage_ba_problem
+{
+  sage_ba_context *ctx = nullptr;
+  int K = 0, F = 0, C = 0, L = 0, H = 0, W = 0, N = 0;
+  std::vector<sage_ba_keyframe *> kfs;
+  float eps = 1e-4f;
+  int rank = 0, world = 1;
+  bool built = false;
+
+  // factor specs in order of addition (global index = position in `metas`)
+  std::vector<FactorMeta> metas;
+  std::vector<PhotoFactor> photo_h;
+  std::vector<GeoFactor> geo_h;
+  std::vector<ReprojFactor> reproj_h;
+  std::vector<int> photo_g, geo_g, reproj_g; // global factor index of each typed factor
+  std::vector<PriorSpec> priors;
+  std::vector<unsigned char> fixed_h;
+  std::vector<void *> owned; // device allocations owned by the problem (match arrays)
+  size_t fbuf_count = 0;
+  long residuals = 0;
+
+  // device
+  DevBuf<PhotoFactor> photo_d;
+  DevBuf<GeoFactor> geo_d;
+  DevBuf<ReprojFactor> reproj_d;
+  DevBuf<int2> photo_ij, geo_ij, reproj_ij, photo_off, geo_off, reproj_off;
+  int n_photo = 0, n_geo = 0, n_reproj = 0; // this shard
+  DevBuf<FactorMeta> metas_d;
+  DevBuf<PriorSpec> priors_d;
+  DevBuf<int> errpos_d, costpos_d;
+  DevBuf<KfMaps> maps_d;
+  DevBuf<float> state[2][3]; // [which][poses, codes, scales]
+  DevBuf<float> fbuf, cbuf, partH, partE;
+  DevBuf<double> Hm, gv, Hd, gd, delta, prior_cost, total_cost, work;
+  DevBuf<int> info;
+  DevBuf<unsigned char> fixed_d;
+  PinBuf<double> hcost;
+  PinBuf<int> hinfo;
+  int potrf_lwork = 0;
+  int slices_photo = 32, slices_geo = 32;
+
+  sage_ba_allreduce_fn allreduce = nullptr;
+  void *allreduce_user = nullptr;
+
+  int dim() const { return K * (7 + C); }
+};
+
+namespace sage
+{
+
+static void problem_build(sage_ba_problem *p)
+{
+  if (p->built)
+    return;
+  sage_ba_context *ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const int K = p->K, C = p->C;
+  // shard: factor with global index f belongs to rank f % world
+  std::vector<PhotoFactor> ph;
+  std::vector<GeoFactor> ge;
+  std::vector<ReprojFactor> re;
+  std::vector<int2> pij, gij, rij, poff, goff, roff;
+  for (size_t q = 0; q < p->photo_h.size(); ++q)
+  {
+    const FactorMeta &m = p->metas[p->photo_g[q]];
+    if (p->photo_g[q] % p->world != p->rank)
+      continue;
+    ph.push_back(p->photo_h[q]);
+    pij.push_back(make_int2(m.i, m.j));
+    poff.push_back(make_int2(m.off, m.cost_off));
+  }
+  for (size_t q = 0; q < p->geo_h.size(); ++q)
+  {
+    const FactorMeta &m = p->metas[p->geo_g[q]];
+    if (p->geo_g[q] % p->world != p->rank)
+      continue;
+    ge.push_back(p->geo_h[q]);
+    gij.push_back(make_int2(m.i, m.j));
+    goff.push_back(make_int2(m.off, m.cost_off));
+  }
+  for (size_t q = 0; q < p->reproj_h.size(); ++q)
+  {
+    const FactorMeta &m = p->metas[p->reproj_g[q]];
+    if (p->reproj_g[q] % p->world != p->rank)
+      continue;
+    re.push_back(p->reproj_h[q]);
+    rij.push_back(make_int2(m.i, m.j));
+    roff.push_back(make_int2(m.off, m.cost_off));
+  }
+  p->n_photo = (int)ph.size();
+  p->n_geo = (int)ge.size();
+  p->n_reproj = (int)re.size();
+  auto up = [&](auto &dev, const auto &host) {
+    using T = typename std::remove_reference<decltype(host[0])>::type;
+    if (host.empty())
+      return;
+    auto *d = dev.ensure(host.size());
+    SAGE_CUDA(cudaMemcpyAsync((void *)d, (const void *)host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  };
+  up(p->photo_d, ph);
+  up(p->geo_d, ge);
+  up(p->reproj_d, re);
+  up(p->photo_ij, pij);
+  up(p->geo_ij, gij);
+  up(p->reproj_ij, rij);
+  up(p->photo_off, poff);
+  up(p->geo_off, goff);
+  up(p->reproj_off, roff);
+  up(p->metas_d, p->metas);
+  up(p->priors_d, p->priors);
+  std::vector<int> errpos, costpos;
+  for (const FactorMeta &m : p->metas)
+  {
+    errpos.push_back(m.off + m.D * m.D + m.D);
+    costpos.push_back(m.cost_off);
+  }
+  up(p->errpos_d, errpos);
+  up(p->costpos_d, costpos);
+  std::vector<KfMaps> maps;
+  for (sage_ba_keyframe *kf : p->kfs)
+    maps.push_back(KfMaps{kf->bias, kf->basis, kf->mask, kf->dgm, kf->dscr});
+  up(p->maps_d, maps);
+  if (p->fixed_h.empty())
+    p->fixed_h.assign(p->dim(), 0);
+  up(p->fixed_d, p->fixed_h);
+
+  const int n = p->dim();
+  p->fbuf.ensure(std::max<size_t>(p->fbuf_count, 4));
+  p->cbuf.ensure(std::max<size_t>(p->metas.size() * 2, 4));
+  SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf.cap * sizeof(float), s));
+  SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->cbuf.cap * sizeof(float), s));
+  // slices: enough CTAs to fill the machine a few times over, but never more steps than samples
+  const int sps_p = (32 / (p->F / 4)) * (SAGE_CTA / 32), sps_g = (32 / (C / 4)) * (SAGE_CTA / 32);
+  const int target = 8 * ctx->num_sms;
+  p->slices_photo = std::max(1, std::min((p->N + sps_p - 1) / sps_p, std::max(4, target / std::max(1, p->n_photo))));
+  p->slices_geo = std::max(1, std::min((p->N + sps_g - 1) / sps_g, std::max(4, target / std::max(1, p->n_geo))));
+  p->slices_photo = std::min(p->slices_photo, 64);
+  p->slices_geo = std::min(p->slices_geo, 64);
+  const int WPp = 16 + C, WPg = 16 + 2 * C;
+  const size_t nh = std::max((size_t)p->n_photo * p->slices_photo * WPp * WPp, (size_t)p->n_geo * p->slices_geo * WPg * WPg);
+  p->partH.ensure(std::max<size_t>(nh, 4));
+  p->partE.ensure(std::max<size_t>(2 * std::max((size_t)p->n_photo * p->slices_photo, (size_t)p->n_geo * p->slices_geo), 4));
+  p->Hm.ensure((size_t)n * n);
+  p->Hd.ensure((size_t)n * n);
+  p->gv.ensure(n);
+  p->gd.ensure(n);
+  p->delta.ensure(n);
+  p->prior_cost.ensure(2);
+  p->total_cost.ensure(2);
+  p->info.ensure(4);
+  p->hcost.ensure(4);
+  p->hinfo.ensure(4);
+  int lw1 = 0, lw2 = 0;
+  const int np = 6 * K, nc = n - np;
+  SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, nc, p->Hd.p, n, &lw1) == CUSOLVER_STATUS_SUCCESS,
+             "potrf_bufferSize failed");
+  SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, np, p->Hd.p, n, &lw2) == CUSOLVER_STATUS_SUCCESS,
+             "potrf_bufferSize failed");
+  p->potrf_lwork = std::max(lw1, lw2);
+  p->work.ensure(std::max(p->potrf_lwork, 4));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  p->built = true;
+}
+
+static void refresh_factors(sage_ba_problem *p, int which, bool jac)
+{
+  sage_ba_context *ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const float *poses = p->state[which][0].p, *codes = p->state[which][1].p, *scales = p->state[which][2].p;
+  if (p->n_photo)
+  {
+    setup_photo_kernel<<<(p->n_photo + 127) / 128, 128, 0, s>>>(p->photo_d.p, p->photo_ij.p, p->photo_off.p, p->n_photo, poses, codes,
+                                                                scales, p->C, p->eps, jac);
+    ctx->launches++;
+  }
+  if (p->n_geo)
+  {
+    setup_geo_kernel<<<(p->n_geo + 127) / 128, 128, 0, s>>>(p->geo_d.p, p->geo_ij.p, p->geo_off.p, p->n_geo, poses, codes, scales, p->C,
+                                                            p->eps, jac);
+    const int HW = p->H * p->W;
+    dim3 grid((HW + 255) / 256, p->K);
+    depth_unscaled_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, codes, HW, p->C);
+    depth_pack_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, p->H, p->W);
+    ctx->launches += 3;
+  }
+  if (p->n_reproj)
+  {
+    setup_reproj_kernel<<<(p->n_reproj + 127) / 128, 128, 0, s>>>(p->reproj_d.p, p->reproj_ij.p, p->reproj_off.p, p->n_reproj, poses,
+                                                                  codes, scales, p->C, p->eps, jac);
+    ctx->launches++;
+  }
+}
+
+static void run_factors(sage_ba_problem *p, bool jac, float *out)
+{
+  sage_ba_context *ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const sage_ba_keyframe *k0 = p->kfs[0];
+  if (p->n_photo)
+  {
+    SAGE_CHECK(launch_photo(jac ? PH_MAP_JAC : PH_MAP_ERR, p->F, p->C, p->photo_d.p, p->n_photo, k0->pyr, p->slices_photo, p->partH.p,
+                            p->partE.p, out, 1, 13 + p->C, s) == 0,
+               "unsupported (feat_channels, code_size)");
+    ctx->launches += 2;
+  }
+  if (p->n_geo)
+  {
+    const sage_ba_camera &cam = k0->cams[0];
+    SAGE_CHECK(launch_geo(jac, p->C, p->geo_d.p, p->n_geo, p->W, p->H, cam.fx, cam.fy, cam.u0, cam.v0, p->slices_geo, p->partH.p,
+                          p->partE.p, out, 1, s) == 0,
+               "unsupported code_size");
+    ctx->launches += 2;
+  }
+  if (p->n_reproj)
+  {
+    SAGE_CHECK(launch_reproj(jac, false, p->C, p->reproj_d.p, p->n_reproj, out, 1, s) == 0, "unsupported code_size");
+    ctx->launches += 1;
+  }
+  SAGE_CUDA(cudaGetLastError());
+}
+
+} // namespace sage
+
+#define SAGE_PTRY(p_)                               \
+  sage_ba_problem *prob__ = (p_);                   \
+  if (!prob__)                                      \
+    return 1;                                       \
+  sage_ba_context *ctx__ = prob__->ctx;             \
+  try                                               \
+  {                                                 \
+    SAGE_CUDA(cudaSetDevice(ctx__->device));
+#define SAGE_PCATCH                \
+  }                                \
+  catch (const sage::Error &e)     \
+  {                                \
+    ctx__->err = e.msg;            \
+    return 1;                      \
+  }                                \
+  catch (const std::exception &e)  \
+  {                                \
+    ctx__->err = e.what();         \
+    return 1;                      \
+  }                                \
+  return 0;
+
+extern "C" {
+
+int sage_ba_problem_create(sage_ba_context *ctx, int num_keyframes, sage_ba_keyframe *const *kfs, sage_ba_problem **out)
+{
+  if (!ctx || !out)
+    return 1;
+  sage_ba_context *ctx__ = ctx;
+  try
+  {
+    SAGE_CHECK(num_keyframes >= 1 && kfs, "need at least one keyframe");
+    sage_ba_problem *p = new sage_ba_problem();
+    p->ctx = ctx;
+    p->K = num_keyframes;
+    for (int k = 0; k < num_keyframes; ++k)
+    {
+      SAGE_CHECK(kfs[k] && kfs[k]->bias && kfs[k]->loc1d, "keyframes of a problem need depth and sample data");
+      if (k)
+        SAGE_CHECK(kfs[k]->H == kfs[0]->H && kfs[k]->W == kfs[0]->W && kfs[k]->F == kfs[0]->F && kfs[k]->C == kfs[0]->C &&
+                       kfs[k]->L == kfs[0]->L,
+                   "keyframes have different shapes");
+      p->kfs.push_back(kfs[k]);
+    }
+    p->F = kfs[0]->F;
+    p->C = kfs[0]->C;
+    p->L = kfs[0]->L;
+    p->H = kfs[0]->H;
+    p->W = kfs[0]->W;
+    p->N = kfs[0]->N;
+    SAGE_CUDA(cudaSetDevice(ctx->device));
+    for (int w = 0; w < 2; ++w)
+    {
+      p->state[w][0].ensure((size_t)p->K * 12);
+      p->state[w][1].ensure((size_t)p->K * p->C);
+      p->state[w][2].ensure((size_t)p->K);
+    }
+    *out = p;
+    return 0;
+  }
+  catch (const sage::Error &e)
+  {
+    ctx__->err = e.msg;
+    return 1;
+  }
+}
+
+void sage_ba_problem_destroy(sage_ba_problem *p)
+{
+  if (!p)
+    return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  for (void *q : p->owned)
+    cudaFree(q);
+  delete p;
+}
+
+static int add_meta(sage_ba_problem *p, int kind, int i, int j, int D)
+{
+  FactorMeta m;
+  m.kind = kind;
+  m.i = i;
+  m.j = j;
+  m.D = D;
+  m.off = (int)p->fbuf_count;
+  m.cost_off = (int)p->metas.size() * 2;
+  p->fbuf_count += (size_t)D * D + D + 2;
+  p->metas.push_back(m);
+  return (int)p->metas.size() - 1;
+}
+
+int sage_ba_problem_add_photometric(sage_ba_problem *p, int i, int j, const float *weights)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
+  const sage_ba_keyframe *a = p->kfs[i], *b = p->kfs[j];
+  PhotoFactor f;
+  memset(&f, 0, sizeof(f));
+  f.fg0 = a->fg;
+  f.fg1 = b->fg;
+  f.mask1 = b->mask;
+  f.bias0 = a->bias;
+  f.basis0 = a->basis;
+  f.loc1d = a->loc1d;
+  f.homo = a->homo;
+  f.N = a->N;
+  memcpy(f.w, weights, sizeof(float) * p->L);
+  p->photo_h.push_back(f);
+  p->photo_g.push_back(add_meta(p, 0, i, j, 13 + p->C));
+  p->residuals += (long)p->L * a->N * p->F;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_add_geometric(sage_ba_problem *p, int i, int j, float loss_param, float weight)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
+  const sage_ba_keyframe *a = p->kfs[i], *b = p->kfs[j];
+  GeoFactor f;
+  memset(&f, 0, sizeof(f));
+  f.bias0 = a->bias;
+  f.basis0 = a->basis;
+  f.loc1d = a->loc1d;
+  f.homo = a->homo;
+  f.dgm1 = b->dgm;
+  f.basis1 = b->basis;
+  f.N = a->N;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  p->geo_h.push_back(f);
+  p->geo_g.push_back(add_meta(p, 1, i, j, 14 + 2 * p->C));
+  p->residuals += a->N;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_add_reprojection(sage_ba_problem *p, int i, int j, const int32_t *loc1d, const float *homo, const float *match2d,
+                                     int M, float loss_param, float weight)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
+  SAGE_CHECK(M > 0 && M <= 4096, "num_matches out of range");
+  const sage_ba_keyframe *a = p->kfs[i];
+  float *dm = nullptr;
+  SAGE_CUDA(cudaMalloc(&dm, sizeof(float) * 6 * M));
+  p->owned.push_back(dm);
+  std::vector<float> hm((size_t)6 * M);
+  memcpy(hm.data(), homo, sizeof(float) * 3 * M);
+  memcpy(hm.data() + 3 * M, match2d, sizeof(float) * 2 * M);
+  memcpy(hm.data() + 5 * M, loc1d, sizeof(int32_t) * M);
+  SAGE_CUDA(cudaMemcpy(dm, hm.data(), sizeof(float) * 6 * M, cudaMemcpyHostToDevice));
+  ReprojFactor f;
+  memset(&f, 0, sizeof(f));
+  f.bias0 = a->bias;
+  f.basis0 = a->basis;
+  f.homo = dm;
+  f.match2d = dm + 3 * M;
+  f.loc1d = reinterpret_cast<const int *>(dm + 5 * M);
+  f.M = M;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  f.fx = a->cams[0].fx;
+  f.fy = a->cams[0].fy;
+  f.cx = a->cams[0].u0;
+  f.cy = a->cams[0].v0;
+  p->reproj_h.push_back(f);
+  p->reproj_g.push_back(add_meta(p, 2, i, j, 13 + p->C));
+  p->residuals += 2L * M;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_add_code_prior(sage_ba_problem *p, int kf, const float *init_code, float weight)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(kf >= 0 && kf < p->K, "bad keyframe index");
+  PriorSpec s;
+  memset(&s, 0, sizeof(s));
+  s.kind = 0;
+  s.kf = kf;
+  s.weight = weight;
+  if (init_code)
+    memcpy(s.init_code, init_code, sizeof(float) * p->C);
+  p->priors.push_back(s);
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale, float weight)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(kf >= 0 && kf < p->K && init_scale > 0.f, "bad scale prior");
+  PriorSpec s;
+  memset(&s, 0, sizeof(s));
+  s.kind = 1;
+  s.kf = kf;
+  s.weight = weight;
+  s.init_scale = init_scale;
+  p->priors.push_back(s);
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(kf >= 0 && kf < p->K, "bad keyframe index");
+  if (p->fixed_h.empty())
+    p->fixed_h.assign(p->dim(), 0);
+  if (fix_pose)
+    for (int c = 0; c < 6; ++c)
+      p->fixed_h[6 * kf + c] = 1;
+  if (fix_scale)
+    p->fixed_h[6 * p->K + kf * (p->C + 1) + p->C] = 1;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(world >= 1 && rank >= 0 && rank < world, "bad shard");
+  p->rank = rank;
+  p->world = world;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses, const float *codes, const float *scales, float eps)
+{
+  SAGE_PTRY(p)
+  cudaStream_t s = ctx__->stream;
+  p->eps = eps;
+  SAGE_CUDA(cudaMemcpyAsync(p->state[0][0].p, poses, sizeof(float) * p->K * 12, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaMemcpyAsync(p->state[0][1].p, codes, sizeof(float) * p->K * p->C, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaMemcpyAsync(p->state[0][2].p, scales, sizeof(float) * p->K, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_get_state(sage_ba_problem *p, float *poses, float *codes, float *scales)
+{
+  SAGE_PTRY(p)
+  cudaStream_t s = ctx__->stream;
+  SAGE_CUDA(cudaMemcpyAsync(poses, p->state[0][0].p, sizeof(float) * p->K * 12, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaMemcpyAsync(codes, p->state[0][1].p, sizeof(float) * p->K * p->C, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaMemcpyAsync(scales, p->state[0][2].p, sizeof(float) * p->K, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_dim(const sage_ba_problem *p) { return p ? p->dim() : 0; }
+int sage_ba_problem_num_factors(const sage_ba_problem *p) { return p ? (int)(p->metas.size() + p->priors.size()) : 0; }
+long sage_ba_problem_num_residuals(const sage_ba_problem *p) { return p ? p->residuals : 0; }
+
+int sage_ba_problem_factor_buffer(sage_ba_problem *p, float **ptr, size_t *count)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  if (ptr)
+    *ptr = p->fbuf.p;
+  if (count)
+    *count = p->fbuf_count;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_cost_buffer(sage_ba_problem *p, float **ptr, size_t *count)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  if (ptr)
+    *ptr = p->cbuf.p;
+  if (count)
+    *count = p->metas.size() * 2;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_set_allreduce(sage_ba_problem *p, sage_ba_allreduce_fn fn, void *user)
+{
+  if (!p)
+    return 1;
+  p->allreduce = fn;
+  p->allreduce_user = user;
+  return 0;
+}
+
+int sage_ba_problem_linearize(sage_ba_problem *p)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  if (p->world > 1)
+    SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf_count * sizeof(float), s));
+  refresh_factors(p, 0, true);
+  run_factors(p, true, p->fbuf.p);
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_assemble(sage_ba_problem *p, double *H, double *g, double *cost)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  const int n = p->dim();
+  SAGE_CUDA(cudaMemsetAsync(p->Hm.p, 0, sizeof(double) * n * n, s));
+  SAGE_CUDA(cudaMemsetAsync(p->gv.p, 0, sizeof(double) * n, s));
+  if (!p->metas.empty())
+  {
+    assemble_kernel<<<(unsigned)p->metas.size(), 256, 0, s>>>(p->fbuf.p, p->metas_d.p, p->Hm.p, p->gv.p, n, p->K, p->C);
+    ctx__->launches++;
+  }
+  priors_kernel<<<1, 256, 0, s>>>(p->priors_d.p, (int)p->priors.size(), p->state[0][1].p, p->state[0][2].p, p->Hm.p, p->gv.p,
+                                  p->prior_cost.p, n, p->K, p->C, 1);
+  total_cost_kernel<<<1, 256, 0, s>>>(p->fbuf.p, p->errpos_d.p, (int)p->metas.size(), p->prior_cost.p, p->total_cost.p);
+  ctx__->launches += 2;
+  SAGE_CUDA(cudaGetLastError());
+  if (H || g || cost)
+  {
+    SAGE_CUDA(cudaMemcpyAsync(p->hcost.p, p->total_cost.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (H)
+      SAGE_CUDA(cudaMemcpyAsync(H, p->Hm.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, s));
+    if (g)
+      SAGE_CUDA(cudaMemcpyAsync(g, p->gv.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    SAGE_CUDA(cudaStreamSynchronize(s));
+    if (cost)
+      *cost = p->hcost.p[0];
+  }
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  const int n = p->dim(), np = 6 * p->K, nc = n - np;
+  damp_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, p->Hd.p, p->gd.p, n, damp);
+  ctx__->launches++;
+  double *Hd = p->Hd.p, *gd = p->gd.p, *dl = p->delta.p;
+  // H is symmetric, so the row-major buffer is also a valid column-major matrix (lda = n).
+  double *A = Hd;                        // pose block            [np x np]
+  double *Bt = Hd + np;                  // rows np.., cols 0..np  [nc x np]  (= H_cp)
+  double *Cc = Hd + (size_t)np * n + np; // code+scale block       [nc x nc]
+  const double one = 1.0, mone = -1.0;
+  cublasHandle_t cb = ctx__->cublas;
+  cusolverDnHandle_t cs = ctx__->cusolver;
+  SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
+  // 1. H_cc = L L^T
+  SAGE_CHECK(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, nc, Cc, n, p->work.p, p->potrf_lwork, p->info.p) == CUSOLVER_STATUS_SUCCESS,
+             "potrf(H_cc) failed to launch");
+  // 2. W = L^-1 H_cp  (in place)
+  SAGE_CHECK(cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nc, np, &one, Cc, n, Bt, n) ==
+                 CUBLAS_STATUS_SUCCESS,
+             "trsm failed");
+  // 3. S = H_pp - W^T W
+  SAGE_CHECK(cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, np, nc, &mone, Bt, n, &one, A, n) == CUBLAS_STATUS_SUCCESS, "syrk failed");
+  // 4. y = L^-1 g_c ; rhs_p = g_p - W^T y
+  SAGE_CUDA(cudaMemcpyAsync(dl, gd, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  SAGE_CHECK(cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nc, Cc, n, dl + np, 1) == CUBLAS_STATUS_SUCCESS,
+             "trsv failed");
+  SAGE_CHECK(cublasDgemv(cb, CUBLAS_OP_T, nc, np, &mone, Bt, n, dl + np, 1, &one, dl, 1) == CUBLAS_STATUS_SUCCESS, "gemv failed");
+  // 5. S dp = rhs_p
+  SAGE_CHECK(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, np, A, n, p->work.p, p->potrf_lwork, p->info.p + 1) == CUSOLVER_STATUS_SUCCESS,
+             "potrf(S) failed to launch");
+  SAGE_CHECK(cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, np, 1, A, n, dl, n, p->info.p + 2) == CUSOLVER_STATUS_SUCCESS, "potrs failed");
+  // 6. dc = L^-T (y - W dp)
+  SAGE_CHECK(cublasDgemv(cb, CUBLAS_OP_N, nc, np, &mone, Bt, n, dl, 1, &one, dl + np, 1) == CUBLAS_STATUS_SUCCESS, "gemv failed");
+  SAGE_CHECK(cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, nc, Cc, n, dl + np, 1) == CUBLAS_STATUS_SUCCESS,
+             "trsv failed");
+  retract_kernel<<<(p->K + 63) / 64, 64, 0, s>>>(p->state[0][0].p, p->state[0][1].p, p->state[0][2].p, dl, p->state[1][0].p,
+                                                 p->state[1][1].p, p->state[1][2].p, p->K, p->C);
+  ctx__->launches++;
+  SAGE_CUDA(cudaGetLastError());
+  if (delta)
+  {
+    SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    SAGE_CUDA(cudaMemcpyAsync(p->hinfo.p, p->info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+    SAGE_CUDA(cudaStreamSynchronize(s));
+    SAGE_CHECK(p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0, "normal equations are not positive definite");
+  }
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_evaluate(sage_ba_problem *p, int which)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  if (p->world > 1)
+    SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->metas.size() * 2 * sizeof(float), s));
+  refresh_factors(p, which ? 1 : 0, false);
+  run_factors(p, false, p->cbuf.p);
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_cost(sage_ba_problem *p, int which, double *cost)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  const int w = which ? 1 : 0;
+  priors_kernel<<<1, 256, 0, s>>>(p->priors_d.p, (int)p->priors.size(), p->state[w][1].p, p->state[w][2].p, nullptr, nullptr,
+                                  p->prior_cost.p + 1, p->dim(), p->K, p->C, 0);
+  total_cost_kernel<<<1, 256, 0, s>>>(p->cbuf.p, p->costpos_d.p, (int)p->metas.size(), p->prior_cost.p + 1, p->total_cost.p + 1);
+  ctx__->launches += 2;
+  SAGE_CUDA(cudaMemcpyAsync(p->hcost.p + 1, p->total_cost.p + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaMemcpyAsync(p->hinfo.p, p->info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  if (cost)
+    *cost = p->hcost.p[1];
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_accept(sage_ba_problem *p)
+{
+  SAGE_PTRY(p)
+  cudaStream_t s = ctx__->stream;
+  for (int q = 0; q < 3; ++q)
+  {
+    const size_t nfl = q == 0 ? (size_t)p->K * 12 : (q == 1 ? (size_t)p->K * p->C : (size_t)p->K);
+    SAGE_CUDA(cudaMemcpyAsync(p->state[0][q].p, p->state[1][q].p, sizeof(float) * nfl, cudaMemcpyDeviceToDevice, s));
+  }
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_ba_lm_report *rep)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(opt, "null options");
+  problem_build(p);
+  sage_ba_lm_report r;
+  memset(&r, 0, sizeof(r));
+  auto reduce = [&](float *buf, size_t count) {
+    if (p->allreduce && p->world > 1)
+      SAGE_CHECK(p->allreduce(buf, count, p->allreduce_user) == 0, "all-reduce callback failed");
+  };
+  auto clampd = [&](double d) { return std::min(std::max(opt->min_damp, d), opt->max_damp); };
+  double damp = opt->init_damp;
+  double cost = 0.0;
+  SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
+  reduce(p->fbuf.p, p->fbuf_count);
+  SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, &cost) == 0, ctx__->err);
+  r.linearizations = 1;
+  r.initial_cost = cost;
+  for (int it = 0; it < opt->max_iters; ++it)
+  {
+    r.iterations = it + 1;
+    bool improved = false;
+    double cand = cost;
+    int trials = 0;
+    while (true)
+    {
+      SAGE_CHECK(sage_ba_problem_solve(p, damp, nullptr) == 0, ctx__->err);
+      SAGE_CHECK(sage_ba_problem_evaluate(p, 1) == 0, ctx__->err);
+      reduce(p->cbuf.p, p->metas.size() * 2);
+      SAGE_CHECK(sage_ba_problem_cost(p, 1, &cand) == 0, ctx__->err);
+      r.evaluations++;
+      const bool solved = p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0;
+      if (solved && cand < cost)
+      {
+        improved = true;
+        break;
+      }
+      if (damp < opt->max_damp && trials < opt->max_trials)
+      {
+        damp = clampd(damp * opt->damp_inc_factor);
+        ++trials;
+      }
+      else
+        break;
+    }
+    if (!improved)
+      break;
+    SAGE_CHECK(sage_ba_problem_accept(p) == 0, ctx__->err);
+    r.accepted++;
+    const double prev = cost;
+    cost = cand;
+    damp = clampd(damp / opt->damp_dec_factor);
+    if (prev - cost < opt->min_rel_decrease * prev || it + 1 >= opt->max_iters)
+      break;
+    SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
+    reduce(p->fbuf.p, p->fbuf_count);
+    SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, nullptr) == 0, ctx__->err);
+    r.linearizations++;
+  }
+  r.final_cost = cost;
+  r.final_damp = damp;
+  if (rep)
+    *rep = r;
+  SAGE_PCATCH
+}
+
+} // extern "C"

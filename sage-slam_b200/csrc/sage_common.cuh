@@ -1,0 +1,239 @@
+// sage_common.cuh -- device-side building blocks shared by the factor kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SAGE_MAX_LEVELS 8
+#define SAGE_MAX_CODE 32
+#define SAGE_CTA 256
+
+// CameraPyramid<float> (common/camera_pyramid.h:18-32) passed by value to every kernel instead of the
+// reference's per-call thrust::device_vector fill (photometric_factor_kernels.cpp:1099-1106).
+struct CamPyr
+{
+  int L;
+  float fx[SAGE_MAX_LEVELS], fy[SAGE_MAX_LEVELS];
+  int w[SAGE_MAX_LEVELS], h[SAGE_MAX_LEVELS];
+  int off[SAGE_MAX_LEVELS];
+  float ofx, ofy, ocx, ocy; // level-0 intrinsics
+  int ow, oh;
+};
+
+// One photometric-type factor (mapping or tracker form).  State-dependent fields are filled on the
+// host (single-factor API) or by setup kernels (batched problem).
+struct PhotoFactor
+{
+  const float *fg0;    // KF0 channel-last [SP][3][F] (mapping form) or nullptr
+  const float *fg1;    // frame-1 channel-last [SP][3][F]
+  const float *mask1;  // [H][W]
+  const float *bias0;  // [HW]
+  const float *basis0; // [HW][C] pixel-major
+  const int *loc1d;    // [N]
+  const float4 *homo;  // [N] (hx, hy, hz, float(idx % W)... unused w)
+  const float *sfeat0; // tracker form: [L][N][F]
+  const float *dpts0;  // tracker form: [N]
+  int N;
+  float R10[9], t10[3], R0[9], t0[3], R1[9];
+  float code0[SAGE_MAX_CODE];
+  float scale0, eps;
+  float w[SAGE_MAX_LEVELS];
+  int out; // slot in the factor output buffers
+};
+
+struct GeoFactor
+{
+  const float *bias0, *basis0; // KF0
+  const int *loc1d;
+  const float4 *homo;
+  const float4 *dgm1;  // KF1 [HW] (depth, d/dx, d/dy, mask)  -- depth/gradient UNSCALED when dscale != 1
+  const float *basis1; // KF1 [HW][C]
+  int N;
+  float R10[9], t10[3], R0[9], t0[3], R1[9];
+  float code0[SAGE_MAX_CODE];
+  float scale0, scale1, dscale, eps, loss_param, weight;
+  int out;
+};
+
+struct ReprojFactor
+{
+  const float *bias0, *basis0; // KF0 (mapping form) or nullptr
+  const int *loc1d;            // [M]
+  const float *homo;           // [M][3]
+  const float *match2d;        // [M][2]
+  const float *dpts0;          // tracker form [M]
+  int M;
+  float R10[9], t10[3], R0[9], t0[3], R1[9];
+  float code0[SAGE_MAX_CODE];
+  float scale0, eps, loss_param, weight;
+  float fx, fy, cx, cy;
+  int out;
+};
+
+__device__ __forceinline__ bool within(int x, int y, int W, int H) { return x >= 0 && x < W && y >= 0 && y < H; }
+
+// bilinear tap set: floor / floor+1, weights from those integers (photometric_factor_kernels.cpp:146-156)
+struct Taps
+{
+  int x0, y0;
+  float nw, se, sw, ne;
+  bool bnw, bse, bsw, bne;
+};
+
+__device__ __forceinline__ Taps make_taps(float px, float py, int W, int H)
+{
+  Taps t;
+  const float fxf = floorf(px), fyf = floorf(py);
+  t.x0 = (int)fxf;
+  t.y0 = (int)fyf;
+  const float lx = (float)(t.x0 + 1) - px, ly = (float)(t.y0 + 1) - py;
+  const float ux = 1.0f - lx, uy = 1.0f - ly;
+  t.nw = lx * ly;
+  t.se = ux * uy;
+  t.sw = lx * uy;
+  t.ne = ux * ly;
+  t.bnw = within(t.x0, t.y0, W, H);
+  t.bse = within(t.x0 + 1, t.y0 + 1, W, H);
+  t.bsw = within(t.x0, t.y0 + 1, W, H);
+  t.bne = within(t.x0 + 1, t.y0, W, H);
+  return t;
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// acc = nw*a + se*b + sw*c + ne*d in the reference's tap order (nw + se + sw + ne), per component
+__device__ __forceinline__ float4 tap_combine(const Taps &t, float4 a, float4 b, float4 c, float4 d)
+{
+  float4 r;
+  r.x = a.x * t.nw + b.x * t.se + c.x * t.sw + d.x * t.ne;
+  r.y = a.y * t.nw + b.y * t.se + c.y * t.sw + d.y * t.ne;
+  r.z = a.z * t.nw + b.z * t.se + c.z * t.sw + d.z * t.ne;
+  r.w = a.w * t.nw + b.w * t.se + c.w * t.sw + d.w * t.ne;
+  return r;
+}
+
+// reduce over the lanes of a sub-warp group of LPG lanes (power of two), result in every lane
+template <int LPG>
+__device__ __forceinline__ float group_sum(float v)
+{
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+// block-wide sum of one float per thread; result valid in thread 0. red: >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float *red)
+{
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0)
+    red[wid] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (wid == 0)
+  {
+    r = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cooperative symmetric rank-k accumulator: H += Y^T Y for rows Y[r][0..WP) staged in shared memory.
+// The WP x WP result is kept as upper-triangular 4x4 register tiles, one tile per thread, with the
+// rows split round-robin over KS thread groups (K-split) so that KS * NT threads are busy.
+//   NB = WP/4 tile rows, NT = NB*(NB+1)/2 tiles.
+// ------------------------------------------------------------------------------------------------
+template <int WP>
+struct Syrk
+{
+  static constexpr int NB = WP / 4;
+  static constexpr int NT = NB * (NB + 1) / 2;
+  static constexpr int KS_ = (SAGE_CTA / NT) < 1 ? 1 : (SAGE_CTA / NT);
+  static constexpr int KS = KS_ > 8 ? 8 : KS_;
+  float acc[16];
+  int bi, bj, ks;
+  bool active;
+
+  __device__ __forceinline__ void init()
+  {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      acc[i] = 0.f;
+    const int t = threadIdx.x;
+    ks = t / NT;
+    active = ks < KS;
+    int tile = t - ks * NT;
+    // tile -> (bi <= bj), row-major over the upper triangle
+    int b = 0;
+    int rem = tile;
+    while (rem >= NB - b)
+    {
+      rem -= NB - b;
+      ++b;
+    }
+    bi = b;
+    bj = b + rem;
+  }
+
+  // rows [0, nrows) of Y (row stride WP floats, 16-byte aligned)
+  __device__ __forceinline__ void accumulate(const float *Y, int nrows)
+  {
+    if (!active)
+      return;
+    for (int r = ks; r < nrows; r += KS)
+    {
+      const float4 a = *reinterpret_cast<const float4 *>(Y + r * WP + bi * 4);
+      const float4 b = *reinterpret_cast<const float4 *>(Y + r * WP + bj * 4);
+      acc[0] = fmaf(a.x, b.x, acc[0]); acc[1] = fmaf(a.x, b.y, acc[1]); acc[2] = fmaf(a.x, b.z, acc[2]); acc[3] = fmaf(a.x, b.w, acc[3]);
+      acc[4] = fmaf(a.y, b.x, acc[4]); acc[5] = fmaf(a.y, b.y, acc[5]); acc[6] = fmaf(a.y, b.z, acc[6]); acc[7] = fmaf(a.y, b.w, acc[7]);
+      acc[8] = fmaf(a.z, b.x, acc[8]); acc[9] = fmaf(a.z, b.y, acc[9]); acc[10] = fmaf(a.z, b.z, acc[10]); acc[11] = fmaf(a.z, b.w, acc[11]);
+      acc[12] = fmaf(a.w, b.x, acc[12]); acc[13] = fmaf(a.w, b.y, acc[13]); acc[14] = fmaf(a.w, b.z, acc[14]); acc[15] = fmaf(a.w, b.w, acc[15]);
+    }
+  }
+
+  // Sum the K-split groups through shared memory (scratch: NT*16 floats) and add the CTA's result to
+  // the full WP x WP (row-major, both triangles of off-diagonal tiles mirrored) partial in global
+  // memory.  dst is this CTA's private slice, so plain stores suffice.
+  __device__ __forceinline__ void store(float *scratch, float *dst)
+  {
+    __syncthreads();
+    for (int g = KS - 1; g >= 1; --g)
+    {
+      if (active && ks == g)
+      {
+        const int tile = threadIdx.x - ks * NT;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          scratch[tile * 16 + i] = acc[i];
+      }
+      __syncthreads();
+      if (active && ks == 0)
+      {
+        const int tile = threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          acc[i] += scratch[tile * 16 + i];
+      }
+      __syncthreads();
+    }
+    if (active && ks == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+          const int r = bi * 4 + i, c = bj * 4 + j;
+          dst[r * WP + c] = acc[i * 4 + j];
+          if (bi != bj)
+            dst[c * WP + r] = acc[i * 4 + j];
+        }
+    }
+  }
+};

@@ -1,0 +1,126 @@
+// sage_internal.h -- host-side objects behind the opaque handles of include/sage_ba.h.
+#pragma once
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/sage_ba.h"
+#include "sage_kernels.h"
+
+namespace sage
+{
+
+struct Error
+{
+  std::string msg;
+};
+
+#define SAGE_CUDA(call)                                                                                   \
+  do                                                                                                      \
+  {                                                                                                       \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+      throw sage::Error{std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +   \
+                        std::to_string(__LINE__) + ")"};                                                  \
+  } while (0)
+
+#define SAGE_CHECK(cond, text)                \
+  do                                          \
+  {                                           \
+    if (!(cond))                              \
+      throw sage::Error{std::string(text)};   \
+  } while (0)
+
+template <typename T>
+struct DevBuf
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  T *ensure(size_t n)
+  {
+    if (n > cap)
+    {
+      release();
+      SAGE_CUDA(cudaMalloc(&p, n * sizeof(T)));
+      cap = n;
+    }
+    return p;
+  }
+};
+
+template <typename T>
+struct PinBuf
+{
+  T *p = nullptr;
+  size_t cap = 0;
+  ~PinBuf()
+  {
+    if (p)
+      cudaFreeHost(p);
+  }
+  T *ensure(size_t n)
+  {
+    if (n > cap)
+    {
+      if (p)
+        cudaFreeHost(p);
+      p = nullptr;
+      SAGE_CUDA(cudaMallocHost(&p, n * sizeof(T)));
+      cap = n;
+    }
+    return p;
+  }
+};
+
+} // namespace sage
+
+struct sage_ba_context
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  std::string err;
+  long launches = 0;
+  int num_sms = 148;
+  // workspaces of the single-factor entry points
+  sage::DevBuf<float> partH, partE, out, scratch;
+  sage::DevBuf<unsigned char> factor; // one factor struct
+  sage::PinBuf<float> hout;
+  sage::PinBuf<unsigned char> hfactor;
+  sage::DevBuf<float> tmp_code;
+  // tracker scratch
+  sage::DevBuf<float> trk_dpts, trk_homo, trk_feats, trk_m_dpts, trk_m_homo, trk_m_2d;
+};
+
+struct sage_ba_keyframe
+{
+  int H = 0, W = 0, L = 0, F = 0, C = 0, N = 0;
+  long SP = 0;
+  sage_ba_camera cams[SAGE_BA_MAX_LEVELS];
+  CamPyr pyr;
+  float *fg = nullptr;    // [SP][3][F]
+  float *bias = nullptr;  // [HW]
+  float *basis = nullptr; // [HW][C]
+  float *mask = nullptr;  // [H][W]
+  int *loc1d = nullptr;   // [N]
+  float4 *homo = nullptr; // [N]
+  float4 *dgm = nullptr;  // [HW] (D, dx, dy, mask) for the geometric factor, state dependent
+  float *dscr = nullptr;  // [HW] scratch
+};

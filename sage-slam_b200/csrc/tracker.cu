@@ -1,0 +1,276 @@
+// tracker.cu -- CameraTracker::TrackNewFrame's damped Gauss-Newton loop on the 6-DoF relative pose
+// (core/system/camera_tracker.cpp:1034-1310; loop :1156-1279, UpdateVariables :491-512,
+// LMConvergence :552-573).  Same control flow and constants as the reference; the Jacobian / error
+// evaluations are the fused kernels of photometric.cu / reprojection.cu and the keyframe features are
+// pre-sampled once on the device (:1104-1123).  Host C++ above the C ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "sage_internal.h"
+
+using namespace sage;
+
+namespace
+{
+
+// solve A x = b (n <= 8) by Gaussian elimination with partial pivoting in double; the reference uses
+// Eigen colPivHouseholderQr on the same 6x6 float system (:1182-1183)
+bool solve_small(const float *A, const float *b, int n, float *x)
+{
+  double M[8][9];
+  for (int r = 0; r < n; ++r)
+  {
+    for (int c = 0; c < n; ++c)
+      M[r][c] = A[r * n + c];
+    M[r][n] = b[r];
+  }
+  for (int c = 0; c < n; ++c)
+  {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (std::fabs(M[r][c]) > std::fabs(M[piv][c]))
+        piv = r;
+    if (M[piv][c] == 0.0)
+      return false;
+    if (piv != c)
+      for (int k = 0; k <= n; ++k)
+        std::swap(M[piv][k], M[c][k]);
+    for (int r = c + 1; r < n; ++r)
+    {
+      const double f = M[r][c] / M[c][c];
+      for (int k = c; k <= n; ++k)
+        M[r][k] -= f * M[c][k];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r)
+  {
+    double s = M[r][n];
+    for (int k = r + 1; k < n; ++k)
+      s -= M[r][k] * x[k];
+    x[r] = (float)(s / M[r][r]);
+  }
+  return true;
+}
+
+void se3_exp_host(const float *w, const float *v, float *R, float *t)
+{
+  // se3_exp<float> (core/mapping/mapping_utils.h:316-346)
+  float theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  float n[3] = {1.f, 0.f, 0.f};
+  if (theta > 0.f)
+    for (int i = 0; i < 3; ++i)
+      n[i] = w[i] / theta;
+  theta = std::max(theta, 1.0e-14f);
+  const float s = std::sin(theta), c = std::cos(theta);
+  const float K[9] = {0.f, -n[2], n[1], n[2], 0.f, -n[0], -n[1], n[0], 0.f};
+  float K2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 3; ++q)
+      K2[r * 3 + q] = K[r * 3] * K[q] + K[r * 3 + 1] * K[3 + q] + K[r * 3 + 2] * K[6 + q];
+  const float a = (1.0f - c) / theta, b = (theta - s) / theta;
+  for (int r = 0; r < 3; ++r)
+  {
+    float tv = 0.f;
+    for (int q = 0; q < 3; ++q)
+    {
+      const float id = r == q ? 1.f : 0.f;
+      R[r * 3 + q] = id + s * K[r * 3 + q] + (1.0f - c) * K2[r * 3 + q];
+      tv += (id + a * K[r * 3 + q] + b * K2[r * 3 + q]) * v[q];
+    }
+    t[r] = tv;
+  }
+}
+
+// RotationToAngleAxis (core/mapping/mapping_utils.h:145-214), including its normalisation quirk
+void rotation_to_angle_axis(const float *R, float eps, float *out)
+{
+  // m = R^T
+  auto m = [&](int r, int c) { return R[c * 3 + r]; };
+  const bool d2 = m(2, 2) < eps;
+  const bool d0_d1 = m(0, 0) > m(1, 1);
+  const bool d0_nd1 = m(0, 0) < -m(1, 1);
+  const float t0 = 1.f + m(0, 0) - m(1, 1) - m(2, 2);
+  const float q0[4] = {m(1, 2) - m(2, 1), t0, m(0, 1) + m(1, 0), m(2, 0) + m(0, 2)};
+  const float t1 = 1.f - m(0, 0) + m(1, 1) - m(2, 2);
+  const float q1[4] = {m(2, 0) - m(0, 2), m(0, 1) + m(1, 0), t1, m(1, 2) + m(2, 1)};
+  const float t2 = 1.f - m(0, 0) - m(1, 1) + m(2, 2);
+  const float q2[4] = {m(0, 1) - m(1, 0), m(2, 0) + m(0, 2), m(1, 2) + m(2, 1), t2};
+  const float t3 = 1.f + m(0, 0) + m(1, 1) + m(2, 2);
+  const float q3[4] = {t3, m(1, 2) - m(2, 1), m(2, 0) - m(0, 2), m(0, 1) - m(1, 0)};
+  const float c0 = d2 && d0_d1, c1 = d2 && !d0_d1, c2 = !d2 && d0_nd1, c3 = !d2 && !d0_nd1;
+  const float den = std::sqrt(t0 * c1 + t1 * c1 + t2 * c2 + t3 * c3); // reference: t0 * mask_c1 (:187)
+  float q[4];
+  for (int i = 0; i < 4; ++i)
+    q[i] = 0.5f * (q0[i] * c0 + q1[i] * c1 + q2[i] * c2 + q3[i] * c3) / den;
+  const float s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const float sn = std::sqrt(s2);
+  const float two_theta = q[0] < 0.f ? std::atan2(-sn, -q[0]) : std::atan2(sn, q[0]);
+  const float k = s2 > 0.f ? two_theta / sn : 2.0f;
+  for (int i = 0; i < 3; ++i)
+    out[i] = k * q[1 + i];
+}
+
+} // namespace
+
+extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *frame1,
+                                       const float *code0, float scale0, const sage_ba_tracker_config *cfg, float *R, float *t,
+                                       const float *match_dpts, const float *match_homo, const float *match2d, int num_matches,
+                                       sage_ba_tracker_report *report)
+{
+  if (!ctx)
+    return 1;
+  try
+  {
+    SAGE_CHECK(kf0 && frame1 && cfg && R && t, "null argument");
+    SAGE_CUDA(cudaSetDevice(ctx->device));
+    const int N = kf0->N, L = kf0->L, F = kf0->F;
+    const bool use_photo = cfg->use_photo != 0, use_reproj = cfg->use_reproj != 0 && num_matches > 0;
+    SAGE_CHECK(use_photo || use_reproj, "no factor enabled");
+    if (cfg->use_reproj && num_matches <= 3)
+      throw Error{"not enough feature matches (camera_tracker.cpp:1141-1146)"};
+    float *d_dpts = ctx->trk_dpts.ensure(std::max(N, 1));
+    float *d_homo = ctx->trk_homo.ensure((size_t)std::max(N, 1) * 3);
+    float *d_feats = ctx->trk_feats.ensure((size_t)L * std::max(N, 1) * F);
+    if (use_photo)
+      SAGE_CHECK(sage_ba_tracker_presample(ctx, kf0, code0, scale0, d_dpts, d_homo, d_feats) == 0, ctx->err);
+    const sage_ba_camera cam = frame1->cams[0];
+
+    sage_ba_tracker_report rep;
+    memset(&rep, 0, sizeof(rep));
+    auto jac_fn = [&](const float *Rg, const float *tg, float *AtA, float *Atb, float *err) {
+      for (int i = 0; i < 36; ++i)
+        AtA[i] = 0.f;
+      for (int i = 0; i < 6; ++i)
+        Atb[i] = 0.f;
+      float e_photo = 0.f, e_rep = 0.f, A[36], b[6];
+      if (use_photo)
+      {
+        SAGE_CHECK(sage_ba_tracker_photo_jac_error(ctx, frame1, Rg, tg, d_dpts, d_homo, d_feats, N, 0, 1.f, cfg->dpt_eps,
+                                                   cfg->photo_weights, A, b, &e_photo, nullptr) == 0,
+                   ctx->err);
+        for (int i = 0; i < 36; ++i)
+          AtA[i] += A[i];
+        for (int i = 0; i < 6; ++i)
+          Atb[i] += b[i];
+      }
+      if (use_reproj)
+      {
+        SAGE_CHECK(sage_ba_tracker_reproj_jac_error(ctx, &cam, Rg, tg, match_dpts, match_homo, match2d, num_matches, cfg->dpt_eps,
+                                                    cfg->reproj_loss_param, cfg->reproj_weight, A, b, &e_rep, nullptr) == 0,
+                   ctx->err);
+        for (int i = 0; i < 36; ++i)
+          AtA[i] += A[i];
+        for (int i = 0; i < 6; ++i)
+          Atb[i] += b[i];
+      }
+      *err = e_photo + e_rep;
+      rep.jacobian_evals++;
+    };
+    auto err_fn = [&](const float *Rg, const float *tg) -> float {
+      float e_photo = 0.f, e_rep = 0.f;
+      if (use_photo)
+        SAGE_CHECK(sage_ba_tracker_photo_error(ctx, frame1, Rg, tg, d_dpts, d_homo, d_feats, N, cfg->dpt_eps, cfg->photo_weights,
+                                               &e_photo, nullptr) == 0,
+                   ctx->err);
+      if (use_reproj)
+        SAGE_CHECK(sage_ba_tracker_reproj_error(ctx, &cam, Rg, tg, match_dpts, match_homo, match2d, num_matches, cfg->dpt_eps,
+                                                cfg->reproj_loss_param, cfg->reproj_weight, &e_rep, nullptr) == 0,
+                   ctx->err);
+      rep.error_evals++;
+      return e_photo + e_rep;
+    };
+    auto clampd = [&](float d) { return std::min(std::max(cfg->min_damp, d), cfg->max_damp); };
+
+    float Rg[9], tg[3], Rc[9], tc[3];
+    memcpy(Rg, R, sizeof(Rg));
+    memcpy(tg, t, sizeof(tg));
+    float AtA[36], Atb[6], damped[36], sol[6];
+    float prev_error = 0.f, curr_error = 1.f, cand_error = 1.f; // :1056-1057
+    float damp = cfg->init_damp;
+    long iter = 0;
+    bool update_jac = true;
+    while (true)
+    {
+      // recompute the Jacobian only when the relative error change is large enough (:1159)
+      if (std::fabs(curr_error - prev_error) / prev_error > cfg->jac_update_err_inc_threshold)
+      {
+        float e = 0.f;
+        jac_fn(Rg, tg, AtA, Atb, &e);
+        if (iter == 0)
+          curr_error = e; // update_error only on the first iteration (:1167)
+        update_jac = true;
+      }
+      else
+        update_jac = false;
+      iter += 1;
+      auto solve = [&]() {
+        for (int i = 0; i < 36; ++i)
+          damped[i] = AtA[i];
+        for (int i = 0; i < 6; ++i)
+          damped[i * 6 + i] = AtA[i * 6 + i] + damp * AtA[i * 6 + i];
+        if (!solve_small(damped, Atb, 6, sol))
+          for (int i = 0; i < 6; ++i)
+            sol[i] = 0.f;
+      };
+      solve();
+      // LMConvergence (:552-573): max |Atb| and the SIGNED max of delta / (|x| + 1e-8)
+      float rotvec[3];
+      rotation_to_angle_axis(Rg, 1.0e-6f, rotvec);
+      float max_grad = 0.f, max_inc = -INFINITY;
+      for (int i = 0; i < 6; ++i)
+      {
+        max_grad = std::max(max_grad, std::fabs(Atb[i]));
+        const float x = i < 3 ? tg[i] : rotvec[i - 3];
+        max_inc = std::max(max_inc, sol[i] / (std::fabs(x) + 1.0e-8f));
+      }
+      if (max_grad < cfg->min_grad_thresh || max_inc < cfg->min_param_inc_thresh)
+        break;
+      while (true)
+      {
+        // UpdateVariables (:491-512): T <- exp([v, w]) * T
+        float dR[9], dt[3];
+        se3_exp_host(sol + 3, sol, dR, dt);
+        for (int r = 0; r < 3; ++r)
+        {
+          for (int c = 0; c < 3; ++c)
+            Rc[r * 3 + c] = dR[r * 3] * Rg[c] + dR[r * 3 + 1] * Rg[3 + c] + dR[r * 3 + 2] * Rg[6 + c];
+          tc[r] = dR[r * 3] * tg[0] + dR[r * 3 + 1] * tg[1] + dR[r * 3 + 2] * tg[2] + dt[r];
+        }
+        cand_error = err_fn(Rc, tc);
+        if (cand_error < curr_error)
+          break;
+        else if (damp < cfg->max_damp)
+        {
+          damp = clampd(damp * cfg->damp_inc_factor);
+          solve();
+        }
+        else
+          break;
+      }
+      if (cand_error >= curr_error && damp >= cfg->max_damp)
+        break;
+      memcpy(Rg, Rc, sizeof(Rg));
+      memcpy(tg, tc, sizeof(tg));
+      if (update_jac)
+        prev_error = curr_error;
+      curr_error = cand_error;
+      damp = clampd(damp / cfg->damp_dec_factor);
+      if (iter >= cfg->max_num_iters)
+        break;
+    }
+    memcpy(R, Rg, sizeof(Rg));
+    memcpy(t, tg, sizeof(tg));
+    rep.iterations = (int)iter;
+    rep.final_error = curr_error;
+    rep.final_damp = damp;
+    if (report)
+      *report = rep;
+    return 0;
+  }
+  catch (const sage::Error &e)
+  {
+    ctx->err = e.msg;
+    return 1;
+  }
+}

@@ -1,0 +1,249 @@
+"""Batched local bundle adjustment over the C ABI's problem object, plus the multi-GPU plumbing.
+
+One process per GPU.  Factors (ordered keyframe pairs) are sharded round-robin by global factor index
+(`shard_factors`); every rank linearises its shard into the packed per-factor buffer
+[AtA | Atb | error | inliers]*, the buffer is all-reduced (sum; a factor's slot is non-zero on exactly
+one rank, so the reduced bits do not depend on the world size), and every rank assembles and solves the
+same normal equations redundantly (the Schur complement needs the fully summed
+code block).  The collective is torch.distributed (NCCL on GPUs, gloo in the CPU tests); the LM loop is
+the C++ one (sage_ba_problem_lm) calling back into `_allreduce` on the context's stream.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .ops import Context, DeviceKeyframe, SageError, _f, _p
+
+F32 = np.float32
+
+
+def shard_factors(num_factors, rank, world):
+    """Global factor indices owned by `rank`: f % world == rank (same rule as sage_ba_problem_set_shard)."""
+    return [f for f in range(num_factors) if f % world == rank]
+
+
+def factor_layout(kinds, C_code):
+    """Offsets of each factor's [AtA D*D | Atb D | error | inliers] block in the packed buffer.
+    kinds: sequence of 'photo' | 'geo' | 'reproj'.  Returns (offsets, dims, total)."""
+    offs, dims, off = [], [], 0
+    for k in kinds:
+        D = 14 + 2 * C_code if k == "geo" else 13 + C_code
+        offs.append(off)
+        dims.append(D)
+        off += D * D + D + 2
+    return offs, dims, off
+
+
+def pack_factor(buf, off, D, AtA, Atb, error, inliers):
+    buf[off:off + D * D] = np.asarray(AtA, buf.dtype).reshape(-1)
+    buf[off + D * D:off + D * D + D] = np.asarray(Atb, buf.dtype).reshape(-1)
+    buf[off + D * D + D] = error
+    buf[off + D * D + D + 1] = inliers
+
+
+def variable_index(kind, i, j, c, K, C_code):
+    """Global variable index of column c of a factor between keyframes i -> j.
+    Global order: [pose_0..pose_{K-1} (6 each) | (code_k (C), scale_k) ...]."""
+    cb_i, cb_j = 6 * K + i * (C_code + 1), 6 * K + j * (C_code + 1)
+    if c < 6:
+        return 6 * i + c
+    if c < 12:
+        return 6 * j + (c - 6)
+    if kind == "geo":
+        if c < 12 + C_code:
+            return cb_i + (c - 12)
+        if c < 12 + 2 * C_code:
+            return cb_j + (c - 12 - C_code)
+        return cb_i + C_code if c == 12 + 2 * C_code else cb_j + C_code
+    if c < 12 + C_code:
+        return cb_i + (c - 12)
+    return cb_i + C_code
+
+
+def assemble_dense(buf, factors, K, C_code):
+    """Host restatement of the device assembly: dense fp64 (H, g, cost) from a packed factor buffer.
+    factors: list of (kind, i, j).  Used by the gloo tests and as documentation of the layout."""
+    n = K * (7 + C_code)
+    H, g, cost = np.zeros((n, n)), np.zeros(n), 0.0
+    offs, dims, _ = factor_layout([f[0] for f in factors], C_code)
+    for (kind, i, j), off, D in zip(factors, offs, dims):
+        idx = np.array([variable_index(kind, i, j, c, K, C_code) for c in range(D)])
+        A = np.asarray(buf[off:off + D * D], np.float64).reshape(D, D)
+        b = np.asarray(buf[off + D * D:off + D * D + D], np.float64)
+        H[np.ix_(idx, idx)] += A
+        np.add.at(g, idx, b)
+        cost += float(buf[off + D * D + D])
+    return H, g, cost
+
+
+def allreduce_sum(tensor):
+    """Sum-all-reduce through torch.distributed if a process group is up (NCCL or gloo); no-op otherwise."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+class _DevPtr:
+    """Zero-copy torch view of a device buffer owned by libsage_ba (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class LocalBA:
+    """Batched LM over K keyframes and a list of factors; Mapper::MappingStep's role (mapper.cpp:469-612)
+    without ISAM2.  State = (pose_wk [K] as (R,t), code [K,C], dpt_scale [K])."""
+
+    def __init__(self, ctx: Context, keyframes, rank=0, world=1):
+        self.ctx = ctx
+        self.kfs = list(keyframes)
+        self.K = len(self.kfs)
+        self.C = self.kfs[0].C
+        self.L = self.kfs[0].L
+        arr = (C.c_void_p * self.K)(*[k.h for k in self.kfs])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sage_ba_problem_create(ctx.h, self.K, arr, C.byref(h)))
+        self.h = h
+        self.rank, self.world = rank, world
+        ctx.check(ctx.lib.sage_ba_problem_set_shard(self.h, rank, world))
+        self.factors = []
+        self._cb = None
+        self._views = {}
+
+    # -- factor graph ------------------------------------------------------------------------------
+    def add_photometric(self, i, j, weights):
+        w = _f(weights)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_add_photometric(self.h, i, j, _p(w)))
+        self.factors.append(("photo", i, j))
+
+    def add_geometric(self, i, j, loss_param, weight):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_add_geometric(self.h, i, j, float(loss_param), float(weight)))
+        self.factors.append(("geo", i, j))
+
+    def add_reprojection(self, i, j, loc1d, homo, match2d, loss_param, weight):
+        loc, hm, m2 = np.ascontiguousarray(loc1d, np.int32), _f(homo), _f(match2d)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_add_reprojection(self.h, i, j, _p(loc), _p(hm), _p(m2), len(loc),
+                                                                     float(loss_param), float(weight)))
+        self.factors.append(("reproj", i, j))
+
+    def add_code_prior(self, k, weight, init_code=None):
+        c = _f(init_code) if init_code is not None else np.zeros(self.C, F32)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_add_code_prior(self.h, k, _p(c), float(weight)))
+
+    def add_scale_prior(self, k, init_scale, weight):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_add_scale_prior(self.h, k, float(init_scale), float(weight)))
+
+    def fix(self, k, pose=True, scale=True):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_fix(self.h, k, int(pose), int(scale)))
+
+    # -- state ---------------------------------------------------------------------------------------
+    def set_state(self, poses, codes, scales, eps=1e-4):
+        P = np.stack([np.concatenate([_f(R).reshape(-1), _f(t).reshape(-1)]) for R, t in poses]).astype(F32)
+        c, s = _f(codes), _f(scales)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_set_state(self.h, _p(P), _p(c), _p(s), float(eps)))
+
+    def get_state(self):
+        P = np.zeros((self.K, 12), F32)
+        c = np.zeros((self.K, self.C), F32)
+        s = np.zeros((self.K,), F32)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_get_state(self.h, _p(P), _p(c), _p(s)))
+        return [(P[k, :9].reshape(3, 3).copy(), P[k, 9:].copy()) for k in range(self.K)], c, s
+
+    @property
+    def dim(self):
+        return int(self.ctx.lib.sage_ba_problem_dim(self.h))
+
+    @property
+    def num_residuals(self):
+        return int(self.ctx.lib.sage_ba_problem_num_residuals(self.h))
+
+    # -- multi-GPU -----------------------------------------------------------------------------------
+    def _buffer_view(self, which):
+        import torch
+
+        if which not in self._views:
+            ptr, cnt = C.c_void_p(), C.c_size_t()
+            fn = self.ctx.lib.sage_ba_problem_factor_buffer if which == "factor" else self.ctx.lib.sage_ba_problem_cost_buffer
+            self.ctx.check(fn(self.h, C.byref(ptr), C.byref(cnt)))
+            self._views[which] = (ptr.value, cnt.value,
+                                  torch.as_tensor(_DevPtr(ptr.value, cnt.value), device=torch.device("cuda", self.ctx.device)))
+        return self._views[which]
+
+    def enable_allreduce(self):
+        """Install the all-reduce callback the C++ LM loop calls once per linearisation and once per trial."""
+        views = {self._buffer_view(w)[0]: self._buffer_view(w)[2] for w in ("factor", "cost")}
+
+        def cb(ptr, count, user):
+            try:
+                allreduce_sum(views[ptr][:count])
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("all-reduce callback failed:", e)
+                return 1
+
+        self._cb = capi.ALLREDUCE_FN(cb)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_set_allreduce(self.h, self._cb, None))
+
+    # -- stages (sage_ba_problem_*) --------------------------------------------------------------------
+    def linearize(self, reduce=True):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_linearize(self.h))
+        if reduce and self.world > 1:
+            allreduce_sum(self._buffer_view("factor")[2])
+
+    def assemble(self, want_matrix=False):
+        cost = C.c_double(0)
+        if want_matrix:
+            n = self.dim
+            H, g = np.zeros((n, n)), np.zeros(n)
+            self.ctx.check(self.ctx.lib.sage_ba_problem_assemble(self.h, _p(H), _p(g), C.byref(cost)))
+            return H, g, cost.value
+        self.ctx.check(self.ctx.lib.sage_ba_problem_assemble(self.h, None, None, C.byref(cost)))
+        return cost.value
+
+    def solve(self, damp, want_delta=False):
+        if want_delta:
+            d = np.zeros(self.dim)
+            self.ctx.check(self.ctx.lib.sage_ba_problem_solve(self.h, float(damp), _p(d)))
+            return d
+        self.ctx.check(self.ctx.lib.sage_ba_problem_solve(self.h, float(damp), None))
+
+    def evaluate(self, candidate=True, reduce=True):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_evaluate(self.h, int(candidate)))
+        if reduce and self.world > 1:
+            allreduce_sum(self._buffer_view("cost")[2])
+        cost = C.c_double(0)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_cost(self.h, int(candidate), C.byref(cost)))
+        return cost.value
+
+    def accept(self):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_accept(self.h))
+
+    def factor_buffer(self):
+        """Host copy of the packed per-factor outputs (after linearize)."""
+        self.ctx.synchronize()
+        return self._buffer_view("factor")[2].cpu().numpy()
+
+    def lm(self, max_iters=10, init_damp=1e-4, min_damp=1e-6, max_damp=1e2, damp_dec_factor=10.0, damp_inc_factor=10.0,
+           min_rel_decrease=1e-6, max_trials=8):
+        opt = capi.LMOptions(max_iters, init_damp, min_damp, max_damp, damp_dec_factor, damp_inc_factor, min_rel_decrease,
+                             max_trials)
+        rep = capi.LMReport()
+        if self.world > 1 and self._cb is None:
+            self.enable_allreduce()
+        self.ctx.check(self.ctx.lib.sage_ba_problem_lm(self.h, C.byref(opt), C.byref(rep)))
+        return {k: getattr(rep, k) for k, _ in capi.LMReport._fields_}
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.sage_ba_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

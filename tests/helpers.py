@@ -1,0 +1,110 @@
+"""Shared construction of parity-test cases (used by tests/, oracle/make_golden.py, bench.py's baselines).
+
+A *case* is a seeded synthetic two-keyframe scene plus a perturbed state; `case_args` flattens it into the
+reference-layout arrays every implementation (reference CUDA kernels, CPU oracle, sm_100a kernels) consumes.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import sage_slam_b200 as sage  # noqa: E402
+
+F32 = np.float32
+
+# name -> scene parameters.  (C, F) pairs match the compiled reference modules (8,16) (16,16) (32,32).
+CASES = {
+    "small_c8_f16": dict(W=64, H=48, L=3, F=16, C=8, num_samples=None, mask="full", seed=11),
+    "native_c16_f16": dict(W=80, H=64, L=4, F=16, C=16, num_samples=3072, mask="ellipse", seed=12),
+    "small_c32_f32": dict(W=64, H=48, L=4, F=32, C=32, num_samples=None, mask="full", seed=13),
+}
+PHOTO_WEIGHTS = [10.0, 9.0, 8.0, 7.0]
+EPS = 1e-4
+
+
+def build_case(name, far=False):
+    """Two keyframes + state.  far=True moves KF1 so that nothing overlaps (zero-inlier fallback)."""
+    prm = CASES[name]
+    kfs = sage.synthetic.make_scene(num_kf=2, **prm)
+    rng = np.random.default_rng(prm["seed"] + 100)
+    C = prm["C"]
+    for k in kfs:
+        k.code = (0.3 * rng.standard_normal(C)).astype(F32)
+        k.dpt_scale = float(F32(1.0 + 0.1 * rng.standard_normal()))
+    if far:
+        R, t = kfs[1].pose_wk
+        kfs[1].pose_wk = (R, (t + np.array([50.0, 0, 0])).astype(F32))
+    return kfs
+
+
+def rel_pose_f32(p0, p1):
+    R0, t0 = p0
+    R1, t1 = p1
+    R10 = (R1.T.astype(F32) @ R0.astype(F32)).astype(F32)
+    t10 = (R1.T.astype(F32) @ (t0 - t1).astype(F32)).astype(F32)
+    return R10, t10
+
+
+def case_args(kfs, i=0, j=1):
+    """Reference-layout argument dict for the ordered pair i -> j."""
+    a, b = kfs[i], kfs[j]
+    R10, t10 = rel_pose_f32(a.pose_wk, b.pose_wk)
+    cams = a.camera_pyramid
+    L = len(cams)
+    H, W = a.video_mask.shape
+    C = a.dpt_jac_code.shape[1]
+    D1u = (b.dpt_map_bias + b.dpt_jac_code @ b.code).reshape(H, W).astype(F32)  # unscaled depth of KF1
+    gx, gy = sage.frames.spatial_grad(D1u[None])
+    s1 = F32(b.dpt_scale)
+    return dict(
+        R10=R10, t10=t10, R0=a.pose_wk[0], t0=a.pose_wk[1], R1=b.pose_wk[0], t1=b.pose_wk[1],
+        bias0=a.dpt_map_bias, jac0=a.dpt_jac_code, code0=a.code, code1=b.code, scale0=float(a.dpt_scale),
+        scale1=float(b.dpt_scale), mask1=b.video_mask, loc1d=a.sampled_locations_1d, homo=a.sampled_locations_homo,
+        feat0=a.feat_map_pyramid, feat1=b.feat_map_pyramid, grad1=b.feat_map_grad_pyramid,
+        level_offsets=a.level_offsets, cams=cams, eps=EPS, weights=np.array(PHOTO_WEIGHTS[:L], F32),
+        # what GeometricFactor::ComputeJacobianAndError hands over (geometric_factor.cpp:317-320,340-342)
+        dpt1=(s1 * D1u).astype(F32), dgrad1=(s1 * np.stack([gx[0], gy[0]])).astype(F32),
+        basis1=np.ascontiguousarray(b.dpt_jac_code.reshape(H, W, C)), cam=cams[0],
+        geo_loss=float(0.03 * np.mean(a.dpt_map_bias.astype(np.float64) ** 2)), geo_weight=0.1,
+        rep_loss=float(0.03 * W * W), rep_weight=0.1, H=H, W=W, C=C, L=L, F=a.feat_map_pyramid.shape[0])
+
+
+def tracker_args(kfs, args):
+    """The tracker's pre-sampled tensors (camera_tracker.cpp:1086-1123) via torch grid_sample on the CPU."""
+    import torch
+    import torch.nn.functional as Fn
+
+    a = kfs[0]
+    H, W, L = args["H"], args["W"], args["L"]
+    loc = torch.from_numpy(a.sampled_locations_1d)
+    x = torch.fmod(loc.to(torch.float32), W)
+    y = torch.floor(loc.to(torch.float32) / W)
+    grid = torch.stack([(x + 0.5) * (2.0 / W) - 1.0, (y + 0.5) * (2.0 / H) - 1.0], 1).reshape(1, 1, -1, 2)
+    feats = []
+    pyr = torch.from_numpy(a.feat_map_pyramid)
+    Fc = pyr.shape[0]
+    for l in range(L):
+        w, h = int(args["cams"][l][4]), int(args["cams"][l][5])
+        off = int(a.level_offsets[l])
+        m = pyr[:, off:off + w * h].reshape(1, Fc, h, w)
+        s = Fn.grid_sample(m, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        feats.append(s.reshape(Fc, -1).permute(1, 0))
+    sfeat0 = torch.stack(feats, 0).contiguous().numpy()
+    dpts0 = a.dpt_map.reshape(-1)[a.sampled_locations_1d].astype(F32)
+    return dict(sfeat0=sfeat0, dpts0=dpts0)
+
+
+def match_args(kfs, M=200):
+    loc, homo, uv = sage.synthetic.make_matches(kfs[0], kfs[1], M=M)
+    dpts = kfs[0].dpt_map.reshape(-1)[loc].astype(F32)
+    return dict(mloc=loc, mhomo=homo, m2d=uv, mdpts=dpts)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
