@@ -254,6 +254,26 @@ int sage_ba_problem_cost(sage_ba_problem *p, int which, double *cost);
 /* stage 6: make the candidate the current state */
 int sage_ba_problem_accept(sage_ba_problem *p);
 
+/* CUDA-event timing of the launches inside linearize / evaluate / assemble / solve, per kind (ms summed and
+ * launch counts since the last reset).  Used by bench.py for the roofline line; off by default. */
+enum
+{
+  SAGE_BA_PROF_PHOTO_JAC = 0,
+  SAGE_BA_PROF_GEO_JAC = 1,
+  SAGE_BA_PROF_REPROJ_JAC = 2,
+  SAGE_BA_PROF_PHOTO_ERR = 3,
+  SAGE_BA_PROF_GEO_ERR = 4,
+  SAGE_BA_PROF_REPROJ_ERR = 5,
+  SAGE_BA_PROF_DEPTH_PREP = 6,
+  SAGE_BA_PROF_ASSEMBLE = 7,
+  SAGE_BA_PROF_SOLVE = 8,
+  SAGE_BA_PROF_KINDS = 9
+};
+int sage_ba_problem_profile(sage_ba_problem *p, int enable);
+int sage_ba_problem_profile_read(sage_ba_problem *p, double *ms /* [KINDS] */, long *counts /* [KINDS] */, int reset);
+/* factors of each kind this process's shard owns (valid after the first linearize / buffer query) */
+int sage_ba_problem_shard_counts(const sage_ba_problem *p, int *n_photo, int *n_geo, int *n_reproj);
+
 typedef int (*sage_ba_allreduce_fn)(void *device_buffer, size_t count, void *user); /* fp32 sum, on ctx stream */
 int sage_ba_problem_set_allreduce(sage_ba_problem *p, sage_ba_allreduce_fn fn, void *user);
 

@@ -6,6 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsage_ba.so")
 MAX_LEVELS = 8
+PROF_KINDS = ["photo_jac", "geo_jac", "reproj_jac", "photo_err", "geo_err", "reproj_err", "depth_prep", "assemble", "solve"]
 HOST, DEVICE = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
@@ -101,6 +102,9 @@ SIGNATURES = {
     "sage_ba_problem_cost": (C.c_int, [vp, C.c_int, c_double_p]),
     "sage_ba_problem_accept": (C.c_int, [vp]),
     "sage_ba_problem_set_allreduce": (C.c_int, [vp, ALLREDUCE_FN, vp]),
+    "sage_ba_problem_profile": (C.c_int, [vp, C.c_int]),
+    "sage_ba_problem_profile_read": (C.c_int, [vp, c_double_p, C.POINTER(C.c_long), C.c_int]),
+    "sage_ba_problem_shard_counts": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
     "sage_ba_problem_lm": (C.c_int, [vp, C.POINTER(LMOptions), C.POINTER(LMReport)]),
 }
 

@@ -397,11 +397,54 @@ struct sage_ba_problem
   sage_ba_allreduce_fn allreduce = nullptr;
   void *allreduce_user = nullptr;
 
+  // optional CUDA-event profiling of the launches (bench.py's roofline leg)
+  bool profiling = false;
+  struct ProfSpan
+  {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[SAGE_BA_PROF_KINDS] = {0};
+  long prof_n[SAGE_BA_PROF_KINDS] = {0};
+
   int dim() const { return K * (7 + C); }
 };
 
 namespace sage
 {
+
+struct ProfScope
+{
+  sage_ba_problem *p;
+  cudaEvent_t b = nullptr;
+  ProfScope(sage_ba_problem *p_, int kind) : p(p_)
+  {
+    if (!p->profiling)
+      return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!p->event_pool.empty())
+      {
+        e = p->event_pool.back();
+        p->event_pool.pop_back();
+      }
+      else
+        cudaEventCreate(&e);
+      return e;
+    };
+    cudaEvent_t a = get();
+    b = get();
+    cudaEventRecord(a, p->ctx->stream);
+    p->spans.push_back({kind, a, b});
+  }
+  ~ProfScope()
+  {
+    if (b)
+      cudaEventRecord(b, p->ctx->stream);
+  }
+};
 
 static void problem_build(sage_ba_problem *p)
 {
@@ -534,6 +577,7 @@ static void refresh_factors(sage_ba_problem *p, int which, bool jac)
                                                             p->eps, jac);
     const int HW = p->H * p->W;
     dim3 grid((HW + 255) / 256, p->K);
+    ProfScope ps(p, SAGE_BA_PROF_DEPTH_PREP);
     depth_unscaled_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, codes, HW, p->C);
     depth_pack_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, p->H, p->W);
     ctx->launches += 3;
@@ -553,6 +597,7 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
   const sage_ba_keyframe *k0 = p->kfs[0];
   if (p->n_photo)
   {
+    ProfScope ps(p, jac ? SAGE_BA_PROF_PHOTO_JAC : SAGE_BA_PROF_PHOTO_ERR);
     SAGE_CHECK(launch_photo(jac ? PH_MAP_JAC : PH_MAP_ERR, p->F, p->C, p->photo_d.p, p->n_photo, k0->pyr, p->slices_photo, p->partH.p,
                             p->partE.p, out, 1, 13 + p->C, s) == 0,
                "unsupported (feat_channels, code_size)");
@@ -561,6 +606,7 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
   if (p->n_geo)
   {
     const sage_ba_camera &cam = k0->cams[0];
+    ProfScope ps(p, jac ? SAGE_BA_PROF_GEO_JAC : SAGE_BA_PROF_GEO_ERR);
     SAGE_CHECK(launch_geo(jac, p->C, p->geo_d.p, p->n_geo, p->W, p->H, cam.fx, cam.fy, cam.u0, cam.v0, p->slices_geo, p->partH.p,
                           p->partE.p, out, 1, s) == 0,
                "unsupported code_size");
@@ -568,6 +614,7 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
   }
   if (p->n_reproj)
   {
+    ProfScope ps(p, jac ? SAGE_BA_PROF_REPROJ_JAC : SAGE_BA_PROF_REPROJ_ERR);
     SAGE_CHECK(launch_reproj(jac, false, p->C, p->reproj_d.p, p->n_reproj, out, 1, s) == 0, "unsupported code_size");
     ctx->launches += 1;
   }
@@ -882,6 +929,7 @@ int sage_ba_problem_assemble(sage_ba_problem *p, double *H, double *g, double *c
   problem_build(p);
   cudaStream_t s = ctx__->stream;
   const int n = p->dim();
+  ProfScope ps(p, SAGE_BA_PROF_ASSEMBLE);
   SAGE_CUDA(cudaMemsetAsync(p->Hm.p, 0, sizeof(double) * n * n, s));
   SAGE_CUDA(cudaMemsetAsync(p->gv.p, 0, sizeof(double) * n, s));
   if (!p->metas.empty())
@@ -894,6 +942,11 @@ int sage_ba_problem_assemble(sage_ba_problem *p, double *H, double *g, double *c
   total_cost_kernel<<<1, 256, 0, s>>>(p->fbuf.p, p->errpos_d.p, (int)p->metas.size(), p->prior_cost.p, p->total_cost.p);
   ctx__->launches += 2;
   SAGE_CUDA(cudaGetLastError());
+  if (ps.b)
+  {
+    cudaEventRecord(ps.b, s);
+    ps.b = nullptr;
+  }
   if (H || g || cost)
   {
     SAGE_CUDA(cudaMemcpyAsync(p->hcost.p, p->total_cost.p, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -914,6 +967,7 @@ int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta)
   problem_build(p);
   cudaStream_t s = ctx__->stream;
   const int n = p->dim(), np = 6 * p->K, nc = n - np;
+  ProfScope ps(p, SAGE_BA_PROF_SOLVE);
   damp_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, p->Hd.p, p->gd.p, n, damp);
   ctx__->launches++;
   double *Hd = p->Hd.p, *gd = p->gd.p, *dl = p->delta.p;
@@ -951,6 +1005,11 @@ int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta)
                                                  p->state[1][1].p, p->state[1][2].p, p->K, p->C);
   ctx__->launches++;
   SAGE_CUDA(cudaGetLastError());
+  if (ps.b)
+  {
+    cudaEventRecord(ps.b, s);
+    ps.b = nullptr;
+  }
   if (delta)
   {
     SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -1001,6 +1060,58 @@ int sage_ba_problem_accept(sage_ba_problem *p)
     SAGE_CUDA(cudaMemcpyAsync(p->state[0][q].p, p->state[1][q].p, sizeof(float) * nfl, cudaMemcpyDeviceToDevice, s));
   }
   SAGE_PCATCH
+}
+
+int sage_ba_problem_profile(sage_ba_problem *p, int enable)
+{
+  if (!p)
+    return 1;
+  p->profiling = enable != 0;
+  return 0;
+}
+
+int sage_ba_problem_profile_read(sage_ba_problem *p, double *ms, long *counts, int reset)
+{
+  SAGE_PTRY(p)
+  SAGE_CUDA(cudaStreamSynchronize(ctx__->stream));
+  for (auto &sp : p->spans)
+  {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess)
+    {
+      p->prof_ms[sp.kind] += t;
+      p->prof_n[sp.kind] += 1;
+    }
+    p->event_pool.push_back(sp.a);
+    p->event_pool.push_back(sp.b);
+  }
+  p->spans.clear();
+  for (int k = 0; k < SAGE_BA_PROF_KINDS; ++k)
+  {
+    if (ms)
+      ms[k] = p->prof_ms[k];
+    if (counts)
+      counts[k] = p->prof_n[k];
+    if (reset)
+    {
+      p->prof_ms[k] = 0;
+      p->prof_n[k] = 0;
+    }
+  }
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_shard_counts(const sage_ba_problem *p, int *n_photo, int *n_geo, int *n_reproj)
+{
+  if (!p || !p->built)
+    return 1;
+  if (n_photo)
+    *n_photo = p->n_photo;
+  if (n_geo)
+    *n_geo = p->n_geo;
+  if (n_reproj)
+    *n_reproj = p->n_reproj;
+  return 0;
 }
 
 int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_ba_lm_report *rep)

@@ -237,6 +237,21 @@ class LocalBA:
         self.ctx.check(self.ctx.lib.sage_ba_problem_lm(self.h, C.byref(opt), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in capi.LMReport._fields_}
 
+    def profile(self, enable=True):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_profile(self.h, int(enable)))
+
+    def profile_read(self, reset=True):
+        """{kind: (total_ms, launches)} measured with CUDA events on the context's stream."""
+        n = len(capi.PROF_KINDS)
+        ms, cnt = (C.c_double * n)(), (C.c_long * n)()
+        self.ctx.check(self.ctx.lib.sage_ba_problem_profile_read(self.h, ms, cnt, int(reset)))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(capi.PROF_KINDS)}
+
+    def shard_counts(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.ctx.lib.sage_ba_problem_shard_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"photo": a.value, "geo": b.value, "reproj": c.value}
+
     def close(self):
         if self.h:
             self.ctx.lib.sage_ba_problem_destroy(self.h)

@@ -1,0 +1,122 @@
+"""CPU: host-side pieces of the path -- camera pyramid, Gaussian pyramid + gradients, retraction, NearestPsd,
+the tracker LM restatement, factor packing / dense assembly -- against independent restatements."""
+import numpy as np
+import torch
+
+import helpers
+import oracle as O
+import sage_slam_b200 as sage
+from sage_slam_b200 import local_ba
+
+
+def test_camera_pyramid_matches_oracle_and_halves():
+    cam = [256.0, 250.0, 159.5, 127.5, 320, 256]
+    a, b = sage.frames.camera_pyramid(cam, 4), O.camera_pyramid(cam, 4)
+    np.testing.assert_array_equal(a, b)
+    assert list(a[:, 4]) == [320, 160, 80, 40] and list(a[:, 5]) == [256, 128, 64, 32]
+    np.testing.assert_allclose(a[1, :4], [128, 125, 79.75, 63.75])
+
+
+def test_gaussian_pyramid_numpy_vs_torch_restatement():
+    rng = np.random.default_rng(0)
+    feat = rng.standard_normal((5, 48, 64)).astype(np.float32)
+    yy, xx = np.mgrid[0:48, 0:64]
+    mask = ((xx - 32) ** 2 / 900 + (yy - 24) ** 2 / 500 <= 1).astype(np.float32)
+    masks = sage.frames.mask_pyramid(mask, 4)
+    pyr, grad = sage.frames.gaussian_pyramid_with_grad(feat, masks)
+    tm = O.mask_pyramid(torch.from_numpy(mask)[None, None], 4)
+    for a, b in zip(masks, tm):
+        np.testing.assert_array_equal(a, b[0, 0].numpy())
+    tp, tg = O.gaussian_pyramid_with_grad(torch.from_numpy(feat)[None], tm)
+    np.testing.assert_allclose(pyr, tp.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(grad, tg.numpy(), rtol=1e-5, atol=1e-6)
+    assert pyr.shape == (5, 64 * 48 + 32 * 24 + 16 * 12 + 8 * 6)
+
+
+def test_valid_locations():
+    cam = np.array([50.0, 50.0, 31.5, 23.5, 64, 48], np.float32)
+    m = np.zeros((48, 64), np.float32)
+    m[10, 20] = 1
+    loc, homo = sage.frames.valid_locations(m, cam)
+    assert list(loc) == [10 * 64 + 20]
+    np.testing.assert_allclose(homo[0], [(20 - 31.5) / 50, (10 - 23.5) / 50, 1.0])
+    l2, h2 = O.valid_locations(m, cam)
+    np.testing.assert_array_equal(loc, l2)
+    np.testing.assert_array_equal(homo, h2)
+
+
+def test_se3_exp_is_left_multiplicative_and_orthonormal():
+    w, v = np.array([0.02, -0.01, 0.03]), np.array([0.1, 0.2, -0.05])
+    R, t = O.se3_exp(w, v)
+    np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-12)
+    from scipy.linalg import expm
+
+    X = np.zeros((4, 4))
+    X[:3, :3] = O.so3_hat(w)
+    X[:3, 3] = v
+    E = expm(X)
+    np.testing.assert_allclose(R, E[:3, :3], atol=1e-12)
+    np.testing.assert_allclose(t, E[:3, 3], atol=1e-12)
+    R0, t0 = O.se3_exp(np.array([0.3, 0.1, -0.2]), np.array([1.0, 2.0, 3.0]))
+    R1, t1 = O.retract(R0, t0, np.concatenate([v, w]))
+    np.testing.assert_allclose(R1, R @ R0, atol=1e-12)
+    np.testing.assert_allclose(t1, R @ t0 + t, atol=1e-12)
+
+
+def test_nearest_psd_reference_quirk():
+    """the reference forms V^T S V, which is NOT the identity map on PSD input."""
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((8, 8))
+    B = A @ A.T
+    np.testing.assert_allclose(O.nearest_psd(B, reference_faithful=False), B, rtol=1e-9, atol=1e-9)
+    Q = O.nearest_psd(B, reference_faithful=True)
+    assert np.linalg.norm(Q - B) / np.linalg.norm(B) > 1e-2
+    assert np.linalg.eigvalsh(Q).min() > -1e-9
+
+
+def test_tracker_lm_restatement_converges_on_a_quadratic():
+    """camera_tracker.cpp:1156-1279 bookkeeping on a synthetic 6-DoF quadratic bowl."""
+    rng = np.random.default_rng(5)
+    J = rng.standard_normal((40, 6))
+    target = np.array([0.02, -0.01, 0.03, 0.01, -0.02, 0.015])
+
+    def params(R, t):
+        return np.concatenate([t, O.rotation_to_angle_axis(R)])
+
+    def jac(R, t):
+        r = J @ (target - params(R, t))
+        return J.T @ J, J.T @ r, float(r @ r)
+
+    def err(R, t):
+        r = J @ (target - params(R, t))
+        return float(r @ r)
+
+    R, t, e, trace = O.tracker_lm(jac, err, np.eye(3, dtype=np.float32), np.zeros(3, np.float32), max_iters=30)
+    assert e < 1e-6 * err(np.eye(3), np.zeros(3)) and all(a for _, _, a, _ in trace[:-1])
+
+
+def test_factor_packing_and_dense_assembly_layout():
+    K, C = 3, 8
+    factors = [("photo", 0, 1), ("geo", 1, 2), ("reproj", 2, 0)]
+    offs, dims, total = local_ba.factor_layout([f[0] for f in factors], C)
+    assert dims == [21, 30, 21] and offs == [0, 21 * 21 + 23, 21 * 21 + 23 + 30 * 30 + 32]
+    buf = np.zeros(total, np.float32)
+    rng = np.random.default_rng(1)
+    mats = []
+    for (kind, i, j), off, D in zip(factors, offs, dims):
+        A = rng.standard_normal((D, D)).astype(np.float32)
+        A = A @ A.T
+        b = rng.standard_normal(D).astype(np.float32)
+        local_ba.pack_factor(buf, off, D, A, b, 1.5, 10)
+        mats.append((A, b))
+    H, g, cost = local_ba.assemble_dense(buf, factors, K, C)
+    assert cost == 4.5 and H.shape == (K * (7 + C),) * 2
+    np.testing.assert_allclose(H, H.T)
+    # photometric 0->1: pose0 block lands on pose 0, scale column on the scale slot of keyframe 0
+    np.testing.assert_allclose(H[0:6, 0:6], mats[0][0][0:6, 0:6] + mats[2][0][6:12, 6:12], rtol=1e-6)
+    s0 = 6 * K + 0 * (C + 1) + C
+    np.testing.assert_allclose(g[s0], mats[0][1][12 + C], rtol=1e-6)
+    # geometric 1->2 couples code_1 with code_2
+    c1, c2 = 6 * K + 1 * (C + 1), 6 * K + 2 * (C + 1)
+    np.testing.assert_allclose(H[c1:c1 + C, c2:c2 + C], mats[1][0][12:12 + C, 12 + C:12 + 2 * C], rtol=1e-6)
+    assert local_ba.shard_factors(7, 1, 3) == [1, 4]
