@@ -73,7 +73,7 @@ CamPyr make_campyr(const sage_ba_camera &cam, int levels, sage_ba_camera *cams_o
 static int pick_slices(const sage_ba_context *ctx, int N, int samples_per_step)
 {
   const int steps = (N + samples_per_step - 1) / samples_per_step;
-  return std::max(1, std::min(steps, 2 * ctx->num_sms));
+  return std::max(1, std::min(steps, 3 * ctx->num_sms));
 }
 
 // run one photometric-type factor and bring [AtA | Atb | error | inliers] to the host
@@ -82,8 +82,8 @@ static void run_photo_single(sage_ba_context *ctx, int mode, int F, int C, const
 {
   const bool jac = (mode == PH_MAP_JAC || mode == PH_TRK_JAC);
   const int WP = photo_row_width(mode, C);
-  const int sps = (32 / (F / 4)) * (SAGE_CTA / 32);
-  const int slices = pick_slices(ctx, f.N, sps);
+  // every warp of a CTA should see a few 32-sample batches so the end-of-CTA reduction is amortised
+  const int slices = pick_slices(ctx, f.N, 4 * photo_samples_per_cta());
   const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
   float *partH = ctx->partH.ensure(jac ? (size_t)slices * WP * WP : 4);
   float *partE = ctx->partE.ensure((size_t)slices * 2);

@@ -7,44 +7,157 @@
 //   tracker_photo_error_calculate_kernel     :875-988                                    (PH_TRK_ERR)
 // plus the ATen reductions that follow them (:1139-1161, :1220-1242, :1301-1322, :1049-1057).
 //
-// Work decomposition: a sub-warp group of F/4 lanes owns one sample point; each lane owns 4 feature
-// channels and fetches them as one float4 per bilinear tap from the channel-last pyramid
-// [SP][3][F] (feature | d/dx | d/dy), i.e. every tap of every map is one fully used 128-byte line
-// per group for F = 32.  Per sample the F x L residual rows J = g~^T P^ (g~: level-scaled sampled
-// gradient, P^: 2 x D level-independent projection Jacobian) collapse to the 2x2 Gram matrix
-// G = sum w_l g~ g~^T and b = sum w_l g~ r; a Cholesky factor of G turns them into two "virtual
-// rows" of width D+1 that are staged in shared memory and accumulated into J^T J | J^T r by a
-// cooperative register-tiled rank-k update (Syrk<>).  Each CTA writes one private partial; a
-// second tiny kernel reduces partials in a fixed order (deterministic) and applies the
-// inlier normalisation / zero-overlap fallback.
+// Design (one warp = one independent worker, no block barriers in the main loop):
+//  * A warp takes batches of 32 sample points.  Warp geometry, mask lookup and the bilinear tap sets of
+//    every level are computed once per sample with lane == sample.
+//  * The gathers run with lane == channel quad: a group of F/4 lanes fetches one sample's taps as float4
+//    from the channel-last pyramid [SP][3][F] (feature | d/dx | d/dy), so every tap of every map is one
+//    fully used 128-byte line for F = 32.  The owner lane broadcasts the packed tap descriptor and the
+//    four (zero-padded) weights with 5 shuffles per map set; out-of-bounds taps have weight 0 and a
+//    clamped address, so the loads need no predicates.
+//  * The F x L residual rows of a sample collapse to the 2x2 Gram matrix G = sum_l w_l sum_ch g~ g~^T and
+//    b = sum g~ r (g~ = level-scaled sampled gradient): J_row = g~^T P^ with P^ (2 x D) independent of
+//    channel and level.  The six partial sums are reduce-scattered inside the group (7 shuffles) and
+//    accumulated over levels; a Cholesky factor of G turns them into two "virtual rows" P^T L of width
+//    8 + C ([pose0 6 | scale | rhs | code C]; the pose1 block is exactly -pose0 and is expanded at the end).
+//  * J^T J | J^T r of the staged rows is accumulated per warp on the tensor cores: mma.sync m16n8k8 TF32 with
+//    the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulate), upper-triangular tiles only, operand
+//    fragments shared between the A and B roles because both are the same staged rows.
+//  * Each CTA writes one private partial; a tiny second kernel reduces partials in a fixed order
+//    (deterministic) and applies the inlier normalisation / zero-overlap fallback of the reference.
 #include "sage_common.cuh"
 #include "sage_kernels.h"
 
 namespace sage
 {
 
+constexpr int PH_WARPS = 4;
+constexpr int PH_CTA = PH_WARPS * 32;
+
 template <int F, int C, int MODE>
 struct PhotoTraits
 {
   static constexpr bool kJac = (MODE == PH_MAP_JAC || MODE == PH_TRK_JAC);
   static constexpr bool kMap = (MODE == PH_MAP_JAC || MODE == PH_MAP_ERR);
-  static constexpr int LPG = F / 4;           // lanes per sample
-  static constexpr int GPW = 32 / LPG;        // samples per warp
-  static constexpr int SPS = GPW * (SAGE_CTA / 32); // samples per CTA step
-  // staged row: [pose0 6 | pose1 6 | scale | rhs | pad 2 | code C]   (mapping)   /   [pose 6 | scale | rhs] (tracker)
-  static constexpr int WP = kMap ? 16 + C : 8;
+  static constexpr int LPG = F / 4;     // lanes per sample group (8 for F = 32, 4 for F = 16)
+  static constexpr int NG = 32 / LPG;   // groups per warp
+  static constexpr int VPL = 8 / LPG;   // reduced values each lane ends up owning
+  static constexpr int WP = kMap ? 8 + C : 8; // staged row: [pose 6 | scale | rhs | code C]
+  static constexpr int ST = MmaSyrk<WP>::ST;
+  static constexpr int CCH = (C / 4 + LPG - 1) / LPG; // code chunks (float4) per lane
 };
 
+struct TapSet
+{
+  int pk;      // (offset << 2) | (dx << 1) | dy : clamped base pixel and whether the +1 taps move
+  float w[4];  // nw, se, sw, ne ; 0 for out-of-bounds taps (zero padding)
+};
+
+__device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H)
+{
+  TapSet t;
+  const int x0 = (int)floorf(px), y0 = (int)floorf(py);
+  const float lx = (float)(x0 + 1) - px, ly = (float)(y0 + 1) - py;
+  const float ux = 1.0f - lx, uy = 1.0f - ly;
+  const int x1 = x0 < 0x7fffffff ? x0 + 1 : x0, y1 = y0 < 0x7fffffff ? y0 + 1 : y0; // cvt saturates; avoid wrap-around
+  const bool bx0 = x0 >= 0 && x0 < W, bx1 = x1 >= 0 && x1 < W;
+  const bool by0 = y0 >= 0 && y0 < H, by1 = y1 >= 0 && y1 < H;
+  t.w[0] = (bx0 && by0) ? lx * ly : 0.f; // nw
+  t.w[1] = (bx1 && by1) ? ux * uy : 0.f; // se
+  t.w[2] = (bx0 && by1) ? lx * uy : 0.f; // sw
+  t.w[3] = (bx1 && by0) ? ux * ly : 0.f; // ne
+  const int xa = min(max(x0, 0), W - 1), xb = min(max(x1, 0), W - 1);
+  const int ya = min(max(y0, 0), H - 1), yb = min(max(y1, 0), H - 1);
+  t.pk = ((ya * W + xa) << 2) | ((xb != xa) ? 2 : 0) | ((yb != ya) ? 1 : 0);
+  return t;
+}
+
+__device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
+{
+  TapSet r;
+  r.pk = __shfl_sync(0xffffffffu, t.pk, src);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    r.w[k] = __shfl_sync(0xffffffffu, t.w[k], src);
+  return r;
+}
+
+// 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
+__device__ __forceinline__ float4 gather4(const float *base, int onw, int ose, int osw, int one, const float *w)
+{
+  const float4 a = ldg4(base + onw), b = ldg4(base + ose), c = ldg4(base + osw), d = ldg4(base + one);
+  float4 r;
+  r.x = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3];
+  r.y = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];
+  r.z = a.z * w[0] + b.z * w[1] + c.z * w[2] + d.z * w[3];
+  r.w = a.w * w[0] + b.w * w[1] + c.w * w[2] + d.w * w[3];
+  return r;
+}
+
+// reduce-scatter of 8 values over a group of LPG lanes: lane gl ends with VPL = 8/LPG totals, value index gl*VPL+k
+template <int LPG>
+__device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&out)[8 / LPG])
+{
+  static_assert(LPG == 8 || LPG == 4, "LPG must be 4 or 8");
+  if constexpr (LPG == 8)
+  {
+    float a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      const bool hi = gl & 4;
+      const float send = hi ? v[k] : v[k + 4];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      a[k] = (hi ? v[k + 4] : v[k]) + recv;
+    }
+    float b[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+      const bool hi = gl & 2;
+      const float send = hi ? a[k] : a[k + 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      b[k] = (hi ? a[k + 2] : a[k]) + recv;
+    }
+    const bool hi = gl & 1;
+    const float send = hi ? b[0] : b[1];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    out[0] = (hi ? b[1] : b[0]) + recv;
+  }
+  else
+  {
+    float a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+      const bool hi = gl & 2;
+      const float send = hi ? v[k] : v[k + 4];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      a[k] = (hi ? v[k + 4] : v[k]) + recv;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+      const bool hi = gl & 1;
+      const float send = hi ? a[k] : a[k + 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+      out[k] = (hi ? a[k + 2] : a[k]) + recv;
+    }
+  }
+}
+
 template <int F, int C, int MODE>
-__global__ void __launch_bounds__(SAGE_CTA, 2)
+__global__ void __launch_bounds__(PH_CTA, 3)
 photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ CamPyr cam, float *__restrict__ partH,
              float *__restrict__ partE)
 {
   using T = PhotoTraits<F, C, MODE>;
-  constexpr int LPG = T::LPG, SPS = T::SPS, WP = T::WP;
-  constexpr int STAGE = T::kJac ? 2 * SPS * WP : 4;
-  constexpr int SCR = T::kJac ? Syrk<WP>::NT * 16 : 4;
-  __shared__ __align__(16) float Y[STAGE > SCR ? STAGE : SCR];
+  constexpr int LPG = T::LPG, NG = T::NG, VPL = T::VPL, WP = T::WP, ST = T::ST, CCH = T::CCH;
+  constexpr int ROWS = 64; // two virtual rows per sample, 32 samples per warp batch
+  constexpr int STAGE = T::kJac ? PH_WARPS * ROWS * ST : 4;
+  constexpr int HS = T::kJac ? WP * WP : 4;
+  __shared__ __align__(16) float Y[STAGE > HS ? STAGE : HS];
+  __shared__ __align__(16) float XP[PH_WARPS][32 * 8];
   __shared__ PhotoFactor fs;
   __shared__ float red[32];
 
@@ -56,165 +169,195 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPG;                              // lane inside the sample group
-  const int grp = (threadIdx.x >> 5) * T::GPW + lane / LPG; // sample slot inside the CTA step
-  const int N = fs.N;
-  const int L = cam.L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPG, q = lane / LPG; // lane inside its group, group inside the warp
+  const int N = fs.N, L = cam.L;
+  float *Yw = Y + (size_t)warp * ROWS * ST;
+  float *xp = XP[warp];
 
-  Syrk<WP> syrk;
+  MmaSyrk<WP> syrk;
   if constexpr (T::kJac)
     syrk.init();
   float err_acc = 0.f, inl_acc = 0.f;
 
-  for (int base = blockIdx.x * SPS; base < N; base += gridDim.x * SPS)
+  // per-level scale of the value(s) this lane accumulates: [Gxx Gxy Gyy bx by e - -] -> w_l * {fx fx, fx fy, fy fy, fx, fy, 1}
+  int selA[VPL], selB[VPL]; // 0: 1, 1: fx_l, 2: fy_l
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
   {
-    const int n = base + grp;
-    const bool live = n < N;
-    float Gxx = 0.f, Gxy = 0.f, Gyy = 0.f, bx = 0.f, by = 0.f, esum = 0.f;
-    float valid = 0.f;
-    float px0 = 0.f, py0 = 0.f, pz0 = 1.f, rx = 0.f, ry = 0.f, rz = 0.f, d0 = 0.f;
-    float hx = 0.f, hy = 0.f, hz = 0.f;
-    int idx = 0;
-    float4 cb[(C / 4 + LPG - 1) / LPG]; // this lane's chunks of the KF0 depth-basis row
-#pragma unroll
-    for (int j = 0; j < (C / 4 + LPG - 1) / LPG; ++j)
-      cb[j] = f4zero();
+    const int vi = gl * VPL + k;
+    selA[k] = (vi == 0 || vi == 1 || vi == 3) ? 1 : ((vi == 2 || vi == 4) ? 2 : 0);
+    selB[k] = vi == 0 ? 1 : ((vi == 1 || vi == 2) ? 2 : 0);
+  }
 
-    float dot = 0.f;
-    if (live)
+  const int nbatch = (N + 31) / 32;
+  for (int batch = blockIdx.x * PH_WARPS + warp; batch < nbatch; batch += gridDim.x * PH_WARPS)
+  {
+    // ------------------------------------------------------------------ lane == sample: geometry
+    const int n = batch * 32 + lane;
+    const bool live = n < N;
+    const int nc = live ? n : N - 1; // clamped index: dead lanes read valid memory and are masked out below
+    const float4 hm = __ldg(fs.homo + nc);
+    const float hx = hm.x, hy = hm.y, hz = hm.z;
+    int idx = 0;
+    float d0;
+    if constexpr (T::kMap)
     {
-      const float4 hm = __ldg(fs.homo + n);
-      hx = hm.x; hy = hm.y; hz = hm.z;
-      if constexpr (T::kMap)
-      {
-        idx = __ldg(fs.loc1d + n);
+      idx = __ldg(fs.loc1d + nc);
+      // sampled_dpts_0 = scale_0 * (bias[idx] + jac[idx,:] . code)   (:1094-1095); the dot runs lane == channel quad
+      float mydot = 0.f;
 #pragma unroll
-        for (int j = 0; j < (C / 4 + LPG - 1) / LPG; ++j)
+      for (int i = 0; i < LPG; ++i)
+      {
+        const int sidx = __shfl_sync(0xffffffffu, idx, q * LPG + i);
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < CCH; ++k)
         {
-          const int ch = gl + j * LPG;
+          const int ch = gl + k * LPG;
           if (ch < C / 4)
           {
-            cb[j] = ldg4(fs.basis0 + (size_t)idx * C + ch * 4);
-            dot += cb[j].x * fs.code0[ch * 4 + 0] + cb[j].y * fs.code0[ch * 4 + 1] + cb[j].z * fs.code0[ch * 4 + 2] +
-                   cb[j].w * fs.code0[ch * 4 + 3];
+            const float4 cb = ldg4(fs.basis0 + (size_t)sidx * C + ch * 4);
+            dot += cb.x * fs.code0[ch * 4 + 0] + cb.y * fs.code0[ch * 4 + 1] + cb.z * fs.code0[ch * 4 + 2] + cb.w * fs.code0[ch * 4 + 3];
           }
         }
+        dot = group_sum<LPG>(dot);
+        if (gl == i)
+          mydot = dot;
       }
+      d0 = fs.scale0 * (__ldg(fs.bias0 + idx) + mydot);
     }
-    if constexpr (T::kMap)
-      dot = group_sum<LPG>(dot); // outside the divergent region: every lane of the warp takes part
-    if (live)
+    else
+      d0 = __ldg(fs.dpts0 + nc);
+    const float rx = fs.R10[0] * hx + fs.R10[1] * hy + fs.R10[2] * hz;
+    const float ry = fs.R10[3] * hx + fs.R10[4] * hy + fs.R10[5] * hz;
+    const float rz = fs.R10[6] * hx + fs.R10[7] * hy + fs.R10[8] * hz;
+    const float px0 = d0 * rx + fs.t10[0], py0 = d0 * ry + fs.t10[1], pz0 = d0 * rz + fs.t10[2];
+    const bool pos = pz0 > fs.eps;
+    float ux = (px0 / pz0) * cam.ofx + cam.ocx;
+    float uy = (py0 / pz0) * cam.ofy + cam.ocy;
+    // nearest lookup in the full-resolution mask (:158-166); CUDA round() == roundf()
+    const int mx = (int)roundf(ux), my = (int)roundf(uy);
+    const float wm = (live && pos && within(mx, my, cam.ow, cam.oh)) ? __ldg(fs.mask1 + my * cam.ow + mx) : 0.f;
+    const float valid = wm;
+    if (valid == 0.f)
     {
-      // sampled_dpts_0 = scale_0 * (bias[idx] + jac[idx,:] . code)   (:1094-1095)
+      ux = 0.f; // keep every later quantity finite: the sample is multiplied by valid == 0 at the end
+      uy = 0.f;
+    }
+    // KF pixel at level 0: a1 re-derives it from the ray (:101-103), a2 from the integer index (:423-424)
+    float kx = 0.f, ky = 0.f;
+    if constexpr (MODE == PH_MAP_JAC)
+    {
+      kx = hx * cam.ofx + cam.ocx;
+      ky = hy * cam.ofy + cam.ocy;
+    }
+    else if constexpr (MODE == PH_MAP_ERR)
+    {
+      const float fidx = (float)idx;
+      kx = fmodf(fidx, (float)cam.ow);
+      ky = floorf(fidx / (float)cam.ow);
+    }
+
+    // JAC: value (gl*VPL+k) of sample (q*LPG+i) is accumulated over levels in xp[sample][value] by this lane only
+    float eacc = 0.f; // ERR: error of my own sample
+    if constexpr (T::kJac)
+    {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        xp[lane * 8 + k] = 0.f;
+      __syncwarp();
+    }
+
+    for (int l = 0; l < L; ++l)
+    {
+      const int W = cam.w[l], H = cam.h[l];
+      // pixel at level l = (pixel_0 + 0.5) * f_l / f_0 - 0.5   (:142-144)
+      const TapSet t1 = make_tapset((ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H);
+      TapSet t0;
       if constexpr (T::kMap)
-        d0 = fs.scale0 * (__ldg(fs.bias0 + idx) + dot);
-      else
-        d0 = __ldg(fs.dpts0 + n);
-      rx = fs.R10[0] * hx + fs.R10[1] * hy + fs.R10[2] * hz;
-      ry = fs.R10[3] * hx + fs.R10[4] * hy + fs.R10[5] * hz;
-      rz = fs.R10[6] * hx + fs.R10[7] * hy + fs.R10[8] * hz;
-      px0 = d0 * rx + fs.t10[0];
-      py0 = d0 * ry + fs.t10[1];
-      pz0 = d0 * rz + fs.t10[2];
-      const bool pos = pz0 > fs.eps;
-      const float ux = (px0 / pz0) * cam.ofx + cam.ocx;
-      const float uy = (py0 / pz0) * cam.ofy + cam.ocy;
-      // nearest lookup in the full-resolution mask (:158-166); CUDA round() == roundf()
-      const int mx = (int)roundf(ux), my = (int)roundf(uy);
-      const float wm = within(mx, my, cam.ow, cam.oh) ? __ldg(fs.mask1 + my * cam.ow + mx) : 0.f;
-      valid = pos ? wm : 0.f;
+        t0 = make_tapset((kx + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (ky + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H);
+      const float *fg1 = fs.fg1 + (size_t)cam.off[l] * (3 * F) + gl * 4;
+      const float *fg0 = T::kMap ? fs.fg0 + (size_t)cam.off[l] * (3 * F) + gl * 4 : nullptr;
+      const int rowo = W * (3 * F);
+      float lsc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        lsc[k] = fs.w[l] * (selA[k] == 1 ? cam.fx[l] : selA[k] == 2 ? cam.fy[l] : 1.f) *
+                 (selB[k] == 1 ? cam.fx[l] : selB[k] == 2 ? cam.fy[l] : 1.f);
 
-      if (valid != 0.f)
+      // -------------------------------------------------------------- lane == channel quad: gathers
+#pragma unroll 2
+      for (int i = 0; i < LPG; ++i)
       {
-        // KF pixel at level 0: a1 re-derives it from the ray (:101-103), a2 from the integer index (:423-424)
-        float kx, ky;
-        if constexpr (MODE == PH_MAP_JAC)
+        const int src = q * LPG + i;
+        const TapSet s1 = shfl_tapset(t1, src);
+        const int o = (s1.pk >> 2) * (3 * F), dxo = (s1.pk & 2) ? 3 * F : 0, dyo = (s1.pk & 1) ? rowo : 0;
+        const float4 f1 = gather4(fg1, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
+        float4 f0;
+        if constexpr (T::kMap)
         {
-          kx = hx * cam.ofx + cam.ocx;
-          ky = hy * cam.ofy + cam.ocy;
+          const TapSet s0 = shfl_tapset(t0, src);
+          const int o0 = (s0.pk >> 2) * (3 * F), dx0 = (s0.pk & 2) ? 3 * F : 0, dy0 = (s0.pk & 1) ? rowo : 0;
+          f0 = gather4(fg0, o0, o0 + dx0 + dy0, o0 + dy0, o0 + dx0, s0.w);
         }
-        else if constexpr (MODE == PH_MAP_ERR)
+        else
         {
-          const float fidx = (float)idx;
-          kx = fmodf(fidx, (float)cam.ow);
-          ky = floorf(fidx / (float)cam.ow);
+          const int ns = min(batch * 32 + src, N - 1);
+          f0 = ldg4(fs.sfeat0 + ((size_t)l * N + ns) * F + gl * 4);
         }
-        for (int l = 0; l < L; ++l)
+        const float dfx = f0.x - f1.x, dfy = f0.y - f1.y, dfz = f0.z - f1.z, dfw = f0.w - f1.w;
+        const float e = dfx * dfx + dfy * dfy + dfz * dfz + dfw * dfw;
+        if constexpr (T::kJac)
         {
-          const int W = cam.w[l], H = cam.h[l];
-          const float fxl = cam.fx[l], fyl = cam.fy[l];
-          const float *fg1 = fs.fg1 + (size_t)cam.off[l] * (3 * F) + gl * 4;
-          float4 f0;
-          if constexpr (T::kMap)
+          const float4 gx = gather4(fg1 + F, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
+          const float4 gy = gather4(fg1 + 2 * F, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
+          float v[8];
+          v[0] = gx.x * gx.x + gx.y * gx.y + gx.z * gx.z + gx.w * gx.w;
+          v[1] = gx.x * gy.x + gx.y * gy.y + gx.z * gy.z + gx.w * gy.w;
+          v[2] = gy.x * gy.x + gy.y * gy.y + gy.z * gy.z + gy.w * gy.w;
+          v[3] = gx.x * dfx + gx.y * dfy + gx.z * dfz + gx.w * dfw;
+          v[4] = gy.x * dfx + gy.y * dfy + gy.z * dfz + gy.w * dfw;
+          v[5] = e;
+          v[6] = 0.f;
+          v[7] = 0.f;
+          float r[VPL];
+          reduce_scatter8<LPG>(v, gl, r);
+#pragma unroll
+          for (int k = 0; k < VPL; ++k)
           {
-            const float sx = (kx + 0.5f) * fxl / cam.ofx - 0.5f;
-            const float sy = (ky + 0.5f) * fyl / cam.ofy - 0.5f;
-            const Taps ta = make_taps(sx, sy, W, H);
-            const float *fg0 = fs.fg0 + (size_t)cam.off[l] * (3 * F) + gl * 4;
-            const int o = (ta.y0 * W + ta.x0) * (3 * F);
-            const float4 a = ta.bnw ? ldg4(fg0 + o) : f4zero();
-            const float4 b = ta.bse ? ldg4(fg0 + o + (W + 1) * (3 * F)) : f4zero();
-            const float4 c = ta.bsw ? ldg4(fg0 + o + W * (3 * F)) : f4zero();
-            const float4 d = ta.bne ? ldg4(fg0 + o + (3 * F)) : f4zero();
-            f0 = tap_combine(ta, a, b, c, d);
+            float *dstv = xp + src * 8 + gl * VPL + k;
+            *dstv = fmaf(lsc[k], r[k], *dstv);
           }
-          else
-          {
-            f0 = ldg4(fs.sfeat0 + ((size_t)l * N + n) * F + gl * 4);
-          }
-          const float qx = (ux + 0.5f) * fxl / cam.ofx - 0.5f;
-          const float qy = (uy + 0.5f) * fyl / cam.ofy - 0.5f;
-          const Taps tb = make_taps(qx, qy, W, H);
-          const int o = (tb.y0 * W + tb.x0) * (3 * F);
-          const float *pnw = fg1 + o, *pse = fg1 + o + (W + 1) * (3 * F), *psw = fg1 + o + W * (3 * F),
-                      *pne = fg1 + o + (3 * F);
-          const float4 f1 = tap_combine(tb, tb.bnw ? ldg4(pnw) : f4zero(), tb.bse ? ldg4(pse) : f4zero(),
-                                        tb.bsw ? ldg4(psw) : f4zero(), tb.bne ? ldg4(pne) : f4zero());
-          float4 df;
-          if constexpr (MODE == PH_MAP_ERR)
-            df = make_float4(f1.x - f0.x, f1.y - f0.y, f1.z - f0.z, f1.w - f0.w);
-          else
-            df = make_float4(f0.x - f1.x, f0.y - f1.y, f0.z - f1.z, f0.w - f1.w);
-          const float wl = fs.w[l];
-          esum += wl * (wm * (df.x * df.x) + wm * (df.y * df.y) + wm * (df.z * df.z) + wm * (df.w * df.w));
-          if constexpr (T::kJac)
-          {
-            const float4 gx = tap_combine(tb, tb.bnw ? ldg4(pnw + F) : f4zero(), tb.bse ? ldg4(pse + F) : f4zero(),
-                                          tb.bsw ? ldg4(psw + F) : f4zero(), tb.bne ? ldg4(pne + F) : f4zero());
-            const float4 gy = tap_combine(tb, tb.bnw ? ldg4(pnw + 2 * F) : f4zero(), tb.bse ? ldg4(pse + 2 * F) : f4zero(),
-                                          tb.bsw ? ldg4(psw + 2 * F) : f4zero(), tb.bne ? ldg4(pne + 2 * F) : f4zero());
-            // g~ = within_mask * sampled gradient, scaled by the level focal lengths; r = within_mask * diff
-            const float sxl = wm * fxl, syl = wm * fyl;
-            const float ax = gx.x * sxl, ay = gy.x * syl, bxv = gx.y * sxl, byv = gy.y * syl;
-            const float cx = gx.z * sxl, cy = gy.z * syl, dx = gx.w * sxl, dy = gy.w * syl;
-            const float r0 = wm * df.x, r1 = wm * df.y, r2 = wm * df.z, r3 = wm * df.w;
-            Gxx += wl * (ax * ax + bxv * bxv + cx * cx + dx * dx);
-            Gxy += wl * (ax * ay + bxv * byv + cx * cy + dx * dy);
-            Gyy += wl * (ay * ay + byv * byv + cy * cy + dy * dy);
-            bx += wl * (ax * r0 + bxv * r1 + cx * r2 + dx * r3);
-            by += wl * (ay * r0 + byv * r1 + cy * r2 + dy * r3);
-          }
+        }
+        else
+        {
+          const float es = group_sum<LPG>(e);
+          if (gl == i)
+            eacc = fmaf(fs.w[l], es, eacc);
         }
       }
     }
 
-    esum = group_sum<LPG>(esum);
-    if (gl == 0)
+    // ------------------------------------------------------------------ back to lane == sample
+    float Gxx = 0.f, Gxy = 0.f, Gyy = 0.f, bx = 0.f, by = 0.f, esum = eacc;
+    if constexpr (T::kJac)
     {
-      err_acc += esum;
-      inl_acc += valid;
+      __syncwarp();
+      const float4 g0 = *reinterpret_cast<const float4 *>(xp + lane * 8);
+      const float4 g1 = *reinterpret_cast<const float4 *>(xp + lane * 8 + 4);
+      const float m2 = wm * wm; // g~ and r both carry within_mask (:200, :234)
+      Gxx = g0.x * m2; Gxy = g0.y * m2; Gyy = g0.z * m2; bx = g0.w * m2; by = g1.x * m2;
+      esum = g1.y;
     }
+    err_acc += wm * esum; // feat_error = within_mask * diff^2 (:228)
+    inl_acc += valid;
 
     if constexpr (T::kJac)
     {
-      Gxx = group_sum<LPG>(Gxx);
-      Gxy = group_sum<LPG>(Gxy);
-      Gyy = group_sum<LPG>(Gyy);
-      bx = group_sum<LPG>(bx);
-      by = group_sum<LPG>(by);
-
       // Cholesky G = L L^T and L rho = b  -> virtual rows y1 = l11 P0 + l21 P1, y2 = l22 P1
+      const bool on = valid != 0.f;
       const float l11 = sqrtf(Gxx);
       const float il11 = l11 > 0.f ? 1.0f / l11 : 0.f;
       const float l21 = Gxy * il11;
@@ -222,19 +365,16 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       const float il22 = l22 > 0.f ? 1.0f / l22 : 0.f;
       const float rho1 = bx * il11;
       const float rho2 = (by - l21 * rho1) * il22;
-
-      // level-independent projection Jacobian P^ = A^ dp1/dx with A^ = [[1/z,0,-x/z^2],[0,1/z,-y/z^2]]
-      const bool on = valid != 0.f;
-      const float iz = on ? 1.0f / pz0 : 0.f; // invalid samples contribute exact zeros (never 0 * inf)
+      // level-independent projection Jacobian P^ = A^ dp1/dx, A^ = [[1/z,0,-x/z^2],[0,1/z,-y/z^2]] (:241-245 without f)
+      const float iz = on ? 1.0f / pz0 : 0.f;
       const float xz = px0 * iz, yz = py0 * iz;
-      float P0[14], P1[14]; // [pose0 6 | pose1 6 | scale | rhs] (mapping) ; [pose 6 | scale | rhs] uses first 8
+      float P0[7], P1[7];
       if constexpr (T::kMap)
       {
-        // p_w = d0 R0 x~ + t0 ; dp1/dd0 = R1^T [I | -[p_w]x],  dp1/dd1 = [-R1^T | R1^T [p_w]x]   (:247-297)
+        // p_w = d0 R0 x~ + t0 ; dp1/d(pose0) = R1^T [I | -[p_w]x] and dp1/d(pose1) = -dp1/d(pose0)   (:247-297)
         const float wx = d0 * (fs.R0[0] * hx + fs.R0[1] * hy + fs.R0[2] * hz) + fs.t0[0];
         const float wy = d0 * (fs.R0[3] * hx + fs.R0[4] * hy + fs.R0[5] * hz) + fs.t0[1];
         const float wz = d0 * (fs.R0[6] * hx + fs.R0[7] * hy + fs.R0[8] * hz) + fs.t0[2];
-        // rows of A^ R1^T: a0 = (R1^T row0)/z - xz/z (R1^T row2) ...  with R1^T[i][k] = R1[k][i]
         float a0[3], a1[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
@@ -242,7 +382,6 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
           a0[k] = iz * fs.R1[k * 3 + 0] - xz * iz * fs.R1[k * 3 + 2];
           a1[k] = iz * fs.R1[k * 3 + 1] - yz * iz * fs.R1[k * 3 + 2];
         }
-        // pose0 columns: [a | a x-product with p_w]: (A^ R1^T)[I | -[pw]x]; -[pw]x = [[0,wz,-wy],[-wz,0,wx],[wy,-wx,0]]
         P0[0] = a0[0]; P0[1] = a0[1]; P0[2] = a0[2];
         P0[3] = -a0[1] * wz + a0[2] * wy;
         P0[4] = a0[0] * wz - a0[2] * wx;
@@ -251,12 +390,6 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
         P1[3] = -a1[1] * wz + a1[2] * wy;
         P1[4] = a1[0] * wz - a1[2] * wx;
         P1[5] = -a1[0] * wy + a1[1] * wx;
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-        {
-          P0[6 + k] = -P0[k];
-          P1[6 + k] = -P1[k];
-        }
       }
       else
       {
@@ -264,78 +397,66 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
         P0[0] = iz; P0[1] = 0.f; P0[2] = -xz * iz; P0[3] = -xz * yz; P0[4] = 1.0f + xz * xz; P0[5] = -yz;
         P1[0] = 0.f; P1[1] = iz; P1[2] = -yz * iz; P1[3] = -(1.0f + yz * yz); P1[4] = xz * yz; P1[5] = xz;
       }
-      // d pi / d depth (:324-325) without the focal length, and the scale column (:335)
+      // d pi / d depth (:324-325) without the focal length, and the scale column (:335); scale0 == 0 marks the 6-DoF tracker
       const float jdx = rx * iz - px0 * rz * iz * iz;
       const float jdy = ry * iz - py0 * rz * iz * iz;
-      constexpr int SC = T::kMap ? 12 : 6;
-      P0[SC] = jdx * d0 / fs.scale0;
-      P1[SC] = jdy * d0 / fs.scale0;
-      if constexpr (MODE == PH_TRK_JAC)
+      const bool has_scale = T::kMap || fs.scale0 != 0.f;
+      P0[6] = has_scale ? jdx * d0 / fs.scale0 : 0.f;
+      P1[6] = has_scale ? jdy * d0 / fs.scale0 : 0.f;
+      const float c11 = on ? l11 : 0.f, c21 = on ? l21 : 0.f, c22 = on ? l22 : 0.f;
+      float *row = Yw + (size_t)(2 * lane) * ST;
       {
-        if (fs.scale0 == 0.f) // 6-DoF tracker form: no scale column
+        float v[8], u[8];
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
         {
-          P0[SC] = 0.f;
-          P1[SC] = 0.f;
+          v[k] = c11 * P0[k] + c21 * P1[k];
+          u[k] = c22 * P1[k];
         }
-      }
-
-      float *row = Y + (size_t)(2 * grp) * WP;
-      {
-        // lane 0 -> virtual row 1, lane 1 -> virtual row 2 (same arithmetic, different coefficients)
-        const float ca = on ? (gl == 0 ? l11 : 0.f) : 0.f;
-        const float cbv = on ? (gl == 0 ? l21 : l22) : 0.f;
-        const float rr = on ? (gl == 0 ? rho1 : rho2) : 0.f;
-        if (gl < 2)
-        {
-          float *dst = row + gl * WP;
-          if constexpr (T::kMap)
-          {
-            float v[16];
-#pragma unroll
-            for (int k = 0; k < 13; ++k)
-              v[k] = ca * P0[k] + cbv * P1[k];
-            v[13] = rr; v[14] = 0.f; v[15] = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-          else
-          {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 7; ++k)
-              v[k] = ca * P0[k] + cbv * P1[k];
-            v[7] = rr;
-            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        }
+        v[7] = on ? rho1 : 0.f;
+        u[7] = on ? rho2 : 0.f;
+        *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<float4 *>(row + ST) = make_float4(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<float4 *>(row + ST + 4) = make_float4(u[4], u[5], u[6], u[7]);
       }
       if constexpr (T::kMap)
       {
-        // code columns: P[:, code_i] = jd * scale0 * basis_i  (:331-332)  -> y1 = k1 c, y2 = k2 c
-        const float k1 = on ? (l11 * jdx + l21 * jdy) * fs.scale0 : 0.f;
-        const float k2 = on ? (l22 * jdy) * fs.scale0 : 0.f;
+        // code columns: P[:, code_i] = jd * scale0 * basis_i (:331-332)  ->  y1 = k1 c, y2 = k2 c   (lane == channel quad)
+        const float k1 = (c11 * jdx + c21 * jdy) * fs.scale0;
+        const float k2 = (c22 * jdy) * fs.scale0;
 #pragma unroll
-        for (int j = 0; j < (C / 4 + LPG - 1) / LPG; ++j)
+        for (int i = 0; i < LPG; ++i)
         {
-          const int ch = gl + j * LPG;
-          if (ch < C / 4)
+          const int src = q * LPG + i;
+          const float s1 = __shfl_sync(0xffffffffu, k1, src), s2 = __shfl_sync(0xffffffffu, k2, src);
+          const int sidx = __shfl_sync(0xffffffffu, idx, src);
+          float *r0 = Yw + (size_t)(2 * src) * ST + 8;
+#pragma unroll
+          for (int k = 0; k < CCH; ++k)
           {
-            *reinterpret_cast<float4 *>(row + 16 + ch * 4) = make_float4(k1 * cb[j].x, k1 * cb[j].y, k1 * cb[j].z, k1 * cb[j].w);
-            *reinterpret_cast<float4 *>(row + WP + 16 + ch * 4) = make_float4(k2 * cb[j].x, k2 * cb[j].y, k2 * cb[j].z, k2 * cb[j].w);
+            const int ch = gl + k * LPG;
+            if (ch < C / 4)
+            {
+              const float4 cb = ldg4(fs.basis0 + (size_t)sidx * C + ch * 4);
+              *reinterpret_cast<float4 *>(r0 + ch * 4) = make_float4(s1 * cb.x, s1 * cb.y, s1 * cb.z, s1 * cb.w);
+              *reinterpret_cast<float4 *>(r0 + ST + ch * 4) = make_float4(s2 * cb.x, s2 * cb.y, s2 * cb.z, s2 * cb.w);
+            }
           }
         }
       }
-      __syncthreads();
-      syrk.accumulate(Y, 2 * SPS);
-      __syncthreads();
+      __syncwarp();
+      syrk.accumulate(Yw, ROWS, lane);
+      __syncwarp();
     }
   }
 
   const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x; // partials are indexed by launch-local factor
   if constexpr (T::kJac)
-    syrk.store(Y, partH + slot * (WP * WP));
+  {
+    __syncthreads();
+    syrk.store_cta(Y, partH + slot * (WP * WP), warp, lane, PH_WARPS);
+  }
   const float e = block_sum(err_acc, red);
   const float c = block_sum(inl_acc, red);
   if (threadIdx.x == 0)
@@ -345,16 +466,17 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   }
 }
 
-// Reduce the per-CTA partials of one factor in a fixed order and emit the reference outputs:
+// Reduce the per-CTA partials of one factor in a fixed order and emit the reference outputs
 //   [AtA D*D | Atb D | error | inliers]  with AtA = (1/n) sum, error = sum/n, or the zero-overlap fallback
-//   (error = 10 * sum w_l, zeros)   photometric_factor_kernels.cpp:1139-1161
+//   (error = 10 * sum w_l, zeros)   photometric_factor_kernels.cpp:1139-1161.
+// Internal row layout [pose0 6 | scale | rhs | code C]; the pose1 block of the reference is -pose0.
 template <int C, int MODE>
 __global__ void photo_finalize_kernel(const PhotoFactor *__restrict__ factors, int nlevels, int slices, const float *__restrict__ partH,
                                       const float *__restrict__ partE, float *__restrict__ out, int out_stride, int D)
 {
   constexpr bool kJac = (MODE == PH_MAP_JAC || MODE == PH_TRK_JAC);
   constexpr bool kMap = (MODE == PH_MAP_JAC || MODE == PH_MAP_ERR);
-  constexpr int WP = kMap ? 16 + C : 8;
+  constexpr int WP = kMap ? 8 + C : 8;
   const PhotoFactor &f = factors[blockIdx.x];
   const int slot = blockIdx.x; // launch-local index into the partials
   float *o = out + (size_t)f.out * out_stride;
@@ -384,31 +506,42 @@ __global__ void photo_finalize_kernel(const PhotoFactor *__restrict__ factors, i
   if constexpr (kJac)
   {
     const float inv = n > 0.f ? 1.0f / n : 0.f;
-    // internal column of reference column c
-    auto icol = [&](int c) -> int {
+    // reference column c -> internal column and sign
+    auto icol = [&](int c, float &sg) -> int {
+      sg = 1.f;
       if constexpr (kMap)
-        return c < 12 ? c : (c < 12 + C ? 16 + (c - 12) : 12);
+      {
+        if (c < 6)
+          return c;
+        if (c < 12)
+        {
+          sg = -1.f;
+          return c - 6;
+        }
+        return c < 12 + C ? 8 + (c - 12) : 6;
+      }
       else
         return c;
     };
-    constexpr int RHS = kMap ? 13 : 7;
     for (int e = threadIdx.x; e < D * D + D; e += blockDim.x)
     {
+      float sr, sc = 1.f;
       int r, c;
       if (e < D * D)
       {
-        r = icol(e / D);
-        c = icol(e % D);
+        r = icol(e / D, sr);
+        c = icol(e % D, sc);
       }
       else
       {
-        r = icol(e - D * D);
-        c = RHS;
+        r = icol(e - D * D, sr);
+        c = 7;
       }
+      const int lo = r < c ? r : c, hi = r < c ? c : r; // only the upper triangle of the partial is written
       float v = 0.f;
       for (int s = 0; s < slices; ++s)
-        v += partH[((size_t)slot * slices + s) * (WP * WP) + r * WP + c];
-      o[e] = v * inv;
+        v += partH[((size_t)slot * slices + s) * (WP * WP) + lo * WP + hi];
+      o[e] = sr * sc * v * inv;
     }
   }
 }
@@ -418,7 +551,7 @@ static void launch_photo_t(const PhotoFactor *factors, int nfactors, const CamPy
                            float *out, int out_stride, int D, cudaStream_t stream)
 {
   dim3 grid(slices, nfactors);
-  photo_kernel<F, C, MODE><<<grid, SAGE_CTA, 0, stream>>>(factors, cam, partH, partE);
+  photo_kernel<F, C, MODE><<<grid, PH_CTA, 0, stream>>>(factors, cam, partH, partE);
   photo_finalize_kernel<C, MODE><<<nfactors, 256, 0, stream>>>(factors, cam.L, slices, partH, partE, out, out_stride, D);
 }
 
@@ -435,7 +568,8 @@ static void launch_photo_fc(int mode, const PhotoFactor *factors, int nfactors, 
   }
 }
 
-int photo_row_width(int mode, int C) { return (mode == PH_MAP_JAC || mode == PH_MAP_ERR) ? 16 + C : 8; }
+int photo_row_width(int mode, int C) { return (mode == PH_MAP_JAC || mode == PH_MAP_ERR) ? 8 + C : 8; }
+int photo_samples_per_cta() { return PH_WARPS * 32; }
 
 // returns 0 on success, -1 for an unsupported (F, C)
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,

@@ -528,13 +528,14 @@ static void problem_build(sage_ba_problem *p)
   SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf.cap * sizeof(float), s));
   SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->cbuf.cap * sizeof(float), s));
   // slices: enough CTAs to fill the machine a few times over, but never more steps than samples
-  const int sps_p = (32 / (p->F / 4)) * (SAGE_CTA / 32), sps_g = (32 / (C / 4)) * (SAGE_CTA / 32);
-  const int target = 8 * ctx->num_sms;
-  p->slices_photo = std::max(1, std::min((p->N + sps_p - 1) / sps_p, std::max(4, target / std::max(1, p->n_photo))));
-  p->slices_geo = std::max(1, std::min((p->N + sps_g - 1) / sps_g, std::max(4, target / std::max(1, p->n_geo))));
-  p->slices_photo = std::min(p->slices_photo, 64);
+  const int sps_p = 4 * photo_samples_per_cta(), sps_g = (32 / (C / 4)) * (SAGE_CTA / 32);
+  // photometric: 3 CTAs of 4 warps per SM; aim for ~6 waves so the tail is small.  geometric: 2 CTAs of 8 warps per SM.
+  const int target_p = 18 * ctx->num_sms, target_g = 8 * ctx->num_sms;
+  p->slices_photo = std::max(1, std::min((p->N + sps_p - 1) / sps_p, std::max(4, target_p / std::max(1, p->n_photo))));
+  p->slices_geo = std::max(1, std::min((p->N + sps_g - 1) / sps_g, std::max(4, target_g / std::max(1, p->n_geo))));
+  p->slices_photo = std::min(p->slices_photo, 128);
   p->slices_geo = std::min(p->slices_geo, 64);
-  const int WPp = 16 + C, WPg = 16 + 2 * C;
+  const int WPp = 8 + C, WPg = 16 + 2 * C;
   const size_t nh = std::max((size_t)p->n_photo * p->slices_photo * WPp * WPp, (size_t)p->n_geo * p->slices_geo * WPg * WPg);
   p->partH.ensure(std::max<size_t>(nh, 4));
   p->partE.ensure(std::max<size_t>(2 * std::max((size_t)p->n_photo * p->slices_photo, (size_t)p->n_geo * p->slices_geo), 4));

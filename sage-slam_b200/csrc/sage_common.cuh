@@ -237,3 +237,124 @@ struct Syrk
     }
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core symmetric rank-k accumulator (per warp): H += Y^T Y for rows Y[r][0..WP) staged in shared
+// memory with row stride ST.  mma.sync.m16n8k8 TF32 with the 3xTF32 split (lo*hi + hi*lo + hi*hi, fp32
+// accumulate) keeps fp32-level accuracy; only tiles touching the upper triangle are computed, and because
+// A = Y^T and B = Y are the same staged rows the B fragments double as A fragments.
+//   A (16x8, row): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B (8x8, col): b0 (t, g) b1 (t+4, g)
+//   C (16x8): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)       with g = lane >> 2, t = lane & 3
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float rest = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int WP>
+struct MmaSyrk
+{
+  static_assert(WP % 8 == 0, "row width must be a multiple of 8");
+  static constexpr int NT8 = WP / 8;        // 8-wide column tiles
+  static constexpr int MT = (NT8 + 1) / 2;  // 16-tall row tiles
+  static constexpr int ST = (WP % 32 == 8 || WP % 32 == 24) ? WP : WP + 8; // conflict-free fragment loads
+  static constexpr int count_tiles()
+  {
+    int n = 0;
+    for (int mi = 0; mi < MT; ++mi)
+      n += NT8 - 2 * mi;
+    return n;
+  }
+  static constexpr int NTILES = count_tiles();
+  float acc[NTILES][4];
+
+  __device__ __forceinline__ void init()
+  {
+#pragma unroll
+    for (int i = 0; i < NTILES; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        acc[i][k] = 0.f;
+  }
+
+  // rows must be a multiple of 8; every lane of the warp calls this
+  __device__ __forceinline__ void accumulate(const float *Y, int rows, int lane)
+  {
+    const int g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < rows; k0 += 8)
+    {
+      uint32_t bh[NT8][2], bl[NT8][2];
+      const float *r0 = Y + (size_t)(k0 + t) * ST + g, *r1 = r0 + 4 * ST;
+#pragma unroll
+      for (int nj = 0; nj < NT8; ++nj)
+      {
+        split_tf32(r0[8 * nj], bh[nj][0], bl[nj][0]);
+        split_tf32(r1[8 * nj], bh[nj][1], bl[nj][1]);
+      }
+      int ti = 0;
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi)
+      {
+        const bool full = 2 * mi + 1 < NT8;
+        const uint32_t ah0 = bh[2 * mi][0], ah2 = bh[2 * mi][1], al0 = bl[2 * mi][0], al2 = bl[2 * mi][1];
+        const uint32_t ah1 = full ? bh[full ? 2 * mi + 1 : 0][0] : 0u, ah3 = full ? bh[full ? 2 * mi + 1 : 0][1] : 0u;
+        const uint32_t al1 = full ? bl[full ? 2 * mi + 1 : 0][0] : 0u, al3 = full ? bl[full ? 2 * mi + 1 : 0][1] : 0u;
+#pragma unroll
+        for (int nj = 2 * mi; nj < NT8; ++nj)
+        {
+          mma_tf32(acc[ti], al0, al1, al2, al3, bh[nj][0], bh[nj][1]);
+          mma_tf32(acc[ti], ah0, ah1, ah2, ah3, bl[nj][0], bl[nj][1]);
+          mma_tf32(acc[ti], ah0, ah1, ah2, ah3, bh[nj][0], bh[nj][1]);
+          ++ti;
+        }
+      }
+    }
+  }
+
+  // Sum the warps' accumulators in shared memory (Hs: WP*WP floats, may alias the staging buffer once every warp is
+  // done with it) and write the CTA's WP x WP partial (upper triangle valid) to dst.  Called by all threads.
+  __device__ __forceinline__ void store_cta(float *Hs, float *dst, int warp, int lane, int nwarps)
+  {
+    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
+      Hs[i] = 0.f;
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    for (int w = 0; w < nwarps; ++w)
+    {
+      if (warp == w)
+      {
+        int ti = 0;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+          for (int nj = 2 * mi; nj < NT8; ++nj)
+          {
+            const int r = 16 * mi + g, c = 8 * nj + 2 * t;
+            if (r < WP)
+            {
+              Hs[r * WP + c] += acc[ti][0];
+              Hs[r * WP + c + 1] += acc[ti][1];
+            }
+            if (r + 8 < WP)
+            {
+              Hs[(r + 8) * WP + c] += acc[ti][2];
+              Hs[(r + 8) * WP + c + 1] += acc[ti][3];
+            }
+            ++ti;
+          }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
+      dst[i] = Hs[i];
+  }
+};

@@ -9,6 +9,7 @@ enum { PH_MAP_JAC = 0, PH_MAP_ERR = 1, PH_TRK_JAC = 2, PH_TRK_ERR = 3 };
 
 // photometric.cu
 int photo_row_width(int mode, int C);
+int photo_samples_per_cta();
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
                  float *partE, float *out, int out_stride, int D, cudaStream_t stream);
 
