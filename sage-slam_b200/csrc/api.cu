@@ -273,6 +273,10 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
         const int64_t *l64 = (const int64_t *)stage(d->sampled_locations_1d, sizeof(int64_t) * N);
         launch_convert_loc(l64, kf->loc1d, N, s);
         ctx->launches += 1;
+        // features of this keyframe at its own sample points, every level: what the mapping kernels read as "feat_0"
+        SAGE_CUDA(cudaMalloc(&kf->sfeat, sizeof(float) * (size_t)kf->L * N * F));
+        launch_presample(kf->fg, nullptr, nullptr, kf->loc1d, kf->homo, nullptr, 1.f, kf->pyr, F, C, N, nullptr, nullptr, kf->sfeat, s);
+        ctx->launches += 1;
       }
     }
     SAGE_CUDA(cudaGetLastError());
@@ -303,6 +307,7 @@ void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf)
   cudaFree(kf->mask);
   cudaFree(kf->loc1d);
   cudaFree(kf->homo);
+  cudaFree(kf->sfeat);
   cudaFree(kf->dgm);
   cudaFree(kf->dscr);
   delete kf;
@@ -330,10 +335,11 @@ static PhotoFactor photo_map_factor(const sage_ba_keyframe *kf0, const sage_ba_k
                                     const float *weights)
 {
   check_pair(kf0, kf1);
-  SAGE_CHECK(kf0->bias && kf0->basis && kf0->loc1d && kf0->homo, "kf0 lacks depth / sample data");
+  SAGE_CHECK(kf0->bias && kf0->basis && kf0->loc1d && kf0->homo && kf0->sfeat, "kf0 lacks depth / sample data");
   PhotoFactor f;
   memset(&f, 0, sizeof(f));
   f.fg0 = kf0->fg;
+  f.sfeat0 = kf0->sfeat;
   f.fg1 = kf1->fg;
   f.mask1 = kf1->mask;
   f.bias0 = kf0->bias;

@@ -49,11 +49,12 @@ struct PhotoTraits
 
 struct TapSet
 {
-  int pk;      // (offset << 2) | (dx << 1) | dy : clamped base pixel and whether the +1 taps move
+  int pk;      // pixel_offset * stride | (dx << 1) | dy : clamped base element and whether the +1 taps move
   float w[4];  // nw, se, sw, ne ; 0 for out-of-bounds taps (zero padding)
 };
 
-__device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H)
+// stride = floats per pixel of the map (a multiple of 4, so the two low bits are free for the flags)
+__device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H, int stride)
 {
   TapSet t;
   const int x0 = (int)floorf(px), y0 = (int)floorf(py);
@@ -68,7 +69,7 @@ __device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H)
   t.w[3] = (bx1 && by0) ? ux * ly : 0.f; // ne
   const int xa = min(max(x0, 0), W - 1), xb = min(max(x1, 0), W - 1);
   const int ya = min(max(y0, 0), H - 1), yb = min(max(y1, 0), H - 1);
-  t.pk = ((ya * W + xa) << 2) | ((xb != xa) ? 2 : 0) | ((yb != ya) ? 1 : 0);
+  t.pk = ((ya * W + xa) * stride) | ((xb != xa) ? 2 : 0) | ((yb != ya) ? 1 : 0);
   return t;
 }
 
@@ -83,9 +84,9 @@ __device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
 }
 
 // 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
-__device__ __forceinline__ float4 gather4(const float *base, int onw, int ose, int osw, int one, const float *w)
+__device__ __forceinline__ float4 gather4(const float *pnw, const float *pse, const float *psw, const float *pne, const float *w)
 {
-  const float4 a = ldg4(base + onw), b = ldg4(base + ose), c = ldg4(base + osw), d = ldg4(base + one);
+  const float4 a = ldg4(pnw), b = ldg4(pse), c = ldg4(psw), d = ldg4(pne);
   float4 r;
   r.x = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3];
   r.y = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];
@@ -157,7 +158,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   constexpr int STAGE = T::kJac ? PH_WARPS * ROWS * ST : 4;
   constexpr int HS = T::kJac ? WP * WP : 4;
   __shared__ __align__(16) float Y[STAGE > HS ? STAGE : HS];
-  __shared__ __align__(16) float XP[PH_WARPS][32 * 8];
+  __shared__ __align__(16) float XP[PH_WARPS][32 * 9 + 3];
   __shared__ PhotoFactor fs;
   __shared__ float red[32];
 
@@ -245,20 +246,6 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       ux = 0.f; // keep every later quantity finite: the sample is multiplied by valid == 0 at the end
       uy = 0.f;
     }
-    // KF pixel at level 0: a1 re-derives it from the ray (:101-103), a2 from the integer index (:423-424)
-    float kx = 0.f, ky = 0.f;
-    if constexpr (MODE == PH_MAP_JAC)
-    {
-      kx = hx * cam.ofx + cam.ocx;
-      ky = hy * cam.ofy + cam.ocy;
-    }
-    else if constexpr (MODE == PH_MAP_ERR)
-    {
-      const float fidx = (float)idx;
-      kx = fmodf(fidx, (float)cam.ow);
-      ky = floorf(fidx / (float)cam.ow);
-    }
-
     // JAC: value (gl*VPL+k) of sample (q*LPG+i) is accumulated over levels in xp[sample][value] by this lane only
     float eacc = 0.f; // ERR: error of my own sample
     if constexpr (T::kJac)
@@ -266,7 +253,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        xp[lane * 8 + k] = 0.f;
+        xp[lane * 9 + k] = 0.f;
       __syncwarp();
     }
 
@@ -274,12 +261,9 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
     {
       const int W = cam.w[l], H = cam.h[l];
       // pixel at level l = (pixel_0 + 0.5) * f_l / f_0 - 0.5   (:142-144)
-      const TapSet t1 = make_tapset((ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H);
-      TapSet t0;
-      if constexpr (T::kMap)
-        t0 = make_tapset((kx + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (ky + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H);
+      const TapSet t1 = make_tapset((ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H, 3 * F);
       const float *fg1 = fs.fg1 + (size_t)cam.off[l] * (3 * F) + gl * 4;
-      const float *fg0 = T::kMap ? fs.fg0 + (size_t)cam.off[l] * (3 * F) + gl * 4 : nullptr;
+      const float *sf0 = fs.sfeat0 + (size_t)l * N * F + gl * 4; // KF0 features pre-sampled at its own sample points
       const int rowo = W * (3 * F);
       float lsc[VPL];
 #pragma unroll
@@ -293,26 +277,19 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       {
         const int src = q * LPG + i;
         const TapSet s1 = shfl_tapset(t1, src);
-        const int o = (s1.pk >> 2) * (3 * F), dxo = (s1.pk & 2) ? 3 * F : 0, dyo = (s1.pk & 1) ? rowo : 0;
-        const float4 f1 = gather4(fg1, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
-        float4 f0;
-        if constexpr (T::kMap)
-        {
-          const TapSet s0 = shfl_tapset(t0, src);
-          const int o0 = (s0.pk >> 2) * (3 * F), dx0 = (s0.pk & 2) ? 3 * F : 0, dy0 = (s0.pk & 1) ? rowo : 0;
-          f0 = gather4(fg0, o0, o0 + dx0 + dy0, o0 + dy0, o0 + dx0, s0.w);
-        }
-        else
-        {
-          const int ns = min(batch * 32 + src, N - 1);
-          f0 = ldg4(fs.sfeat0 + ((size_t)l * N + ns) * F + gl * 4);
-        }
+        const float *pnw = fg1 + (s1.pk & ~3);
+        const float *pne = pnw + ((s1.pk & 2) ? 3 * F : 0);
+        const float *psw = pnw + ((s1.pk & 1) ? rowo : 0);
+        const float *pse = psw + ((s1.pk & 2) ? 3 * F : 0);
+        const float4 f1 = gather4(pnw, pse, psw, pne, s1.w);
+        const int ns = min(batch * 32 + src, N - 1);
+        const float4 f0 = ldg4(sf0 + (size_t)ns * F);
         const float dfx = f0.x - f1.x, dfy = f0.y - f1.y, dfz = f0.z - f1.z, dfw = f0.w - f1.w;
         const float e = dfx * dfx + dfy * dfy + dfz * dfz + dfw * dfw;
         if constexpr (T::kJac)
         {
-          const float4 gx = gather4(fg1 + F, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
-          const float4 gy = gather4(fg1 + 2 * F, o, o + dxo + dyo, o + dyo, o + dxo, s1.w);
+          const float4 gx = gather4(pnw + F, pse + F, psw + F, pne + F, s1.w);
+          const float4 gy = gather4(pnw + 2 * F, pse + 2 * F, psw + 2 * F, pne + 2 * F, s1.w);
           float v[8];
           v[0] = gx.x * gx.x + gx.y * gx.y + gx.z * gx.z + gx.w * gx.w;
           v[1] = gx.x * gy.x + gx.y * gy.y + gx.z * gy.z + gx.w * gy.w;
@@ -327,7 +304,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
 #pragma unroll
           for (int k = 0; k < VPL; ++k)
           {
-            float *dstv = xp + src * 8 + gl * VPL + k;
+            float *dstv = xp + src * 9 + gl * VPL + k;
             *dstv = fmaf(lsc[k], r[k], *dstv);
           }
         }
@@ -345,8 +322,9 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
     if constexpr (T::kJac)
     {
       __syncwarp();
-      const float4 g0 = *reinterpret_cast<const float4 *>(xp + lane * 8);
-      const float4 g1 = *reinterpret_cast<const float4 *>(xp + lane * 8 + 4);
+      const float *xo = xp + lane * 9;
+      const float4 g0 = make_float4(xo[0], xo[1], xo[2], xo[3]);
+      const float4 g1 = make_float4(xo[4], xo[5], 0.f, 0.f);
       const float m2 = wm * wm; // g~ and r both carry within_mask (:200, :234)
       Gxx = g0.x * m2; Gxy = g0.y * m2; Gyy = g0.z * m2; bx = g0.w * m2; by = g1.x * m2;
       esum = g1.y;

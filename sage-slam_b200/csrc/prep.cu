@@ -161,7 +161,7 @@ __global__ void presample_kernel(const float *__restrict__ fg0, const float *__r
   if (n >= N)
     return;
   const int idx = loc1d[n];
-  if (gl == 0)
+  if (gl == 0 && out_dpts != nullptr)
   {
     float acc = 0.f;
     for (int j = 0; j < C; ++j)

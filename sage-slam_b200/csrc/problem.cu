@@ -725,6 +725,7 @@ int sage_ba_problem_add_photometric(sage_ba_problem *p, int i, int j, const floa
   PhotoFactor f;
   memset(&f, 0, sizeof(f));
   f.fg0 = a->fg;
+  f.sfeat0 = a->sfeat;
   f.fg1 = b->fg;
   f.mask1 = b->mask;
   f.bias0 = a->bias;

@@ -121,6 +121,7 @@ struct sage_ba_keyframe
   float *mask = nullptr;  // [H][W]
   int *loc1d = nullptr;   // [N]
   float4 *homo = nullptr; // [N]
+  float *sfeat = nullptr; // [L][N][F] features pre-sampled at the keyframe's own sample points (camera_tracker.cpp:1104-1123)
   float4 *dgm = nullptr;  // [HW] (D, dx, dy, mask) for the geometric factor, state dependent
   float *dscr = nullptr;  // [HW] scratch
 };
