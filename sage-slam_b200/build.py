@@ -22,9 +22,11 @@ def _newer(a, b):
     return not os.path.exists(b) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib=None, objdir=None):
+    """extra_flags / lib / objdir let tuning scripts build kernel variants side by side (e.g. -DPH_MINB=4)."""
+    lib = lib or LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "sage_ba.h"))
@@ -35,7 +37,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src[:-3] + ".o")
         objs.append(o)
         if force or _newer(s, o) or os.path.getmtime(o) < hdr_time:
-            jobs.append(["nvcc"] + NVCC_FLAGS + ["-c", s, "-o", o])
+            jobs.append(["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -47,9 +49,9 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(run, jobs))
-    if jobs or not os.path.exists(LIB):
-        run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcublas", "-lcusolver", "-lcudart"])
-    return LIB
+    if jobs or not os.path.exists(lib):
+        run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcublas", "-lcusolver", "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":

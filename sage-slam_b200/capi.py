@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsage_ba.so")
+LIB_PATH = os.environ.get("SAGE_BA_LIB", os.path.join(HERE, "lib", "libsage_ba.so"))
 MAX_LEVELS = 8
 PROF_KINDS = ["photo_jac", "geo_jac", "reproj_jac", "photo_err", "geo_err", "reproj_err", "depth_prep", "assemble", "solve"]
 HOST, DEVICE = 0, 1

@@ -3,12 +3,16 @@
 // Replaces geometric_jac_error_calculate_kernel (cuda/geometric_factor_kernels.cpp:472-720),
 // geometric_error_calculate_kernel (:127-218) and the ATen reductions after them (:931-947, :870-879).
 //
-// A sub-warp group of C/4 lanes owns one sample: lane j holds 4 entries of the KF0 basis row and of
-// the bilinearly sampled KF1 basis (one float4 per tap from the pixel-major [HW][C] layout); the
-// depth map of KF1 with its gradient and mask comes as one float4 per tap (prep.cu).  The single
-// Cauchy-weighted Jacobian row (width 14+2C, plus the residual as an extra column) is staged in shared
-// memory and folded into J^T J | J^T r by the cooperative Syrk<> update; nothing is written to HBM
-// except one partial per CTA.
+// A CTA is a pair of warps; each warp takes batches of 32 samples.
+//  * lane == sample: depth of the sample, warp into KF1, nearest mask lookup, the bilinear taps of KF1's
+//    (depth, d/dx, d/dy, mask) float4 map, Cauchy weight and the 9 "small" columns of the Jacobian row
+//    ([pose0 6 | scale0 | scale1 | rhs]; the pose1 block is exactly -pose0 and is expanded at the end).
+//  * lane == channel quad: a group of C/4 lanes fetches the KF0 basis row and the four taps of KF1's
+//    pixel-major basis [HW][C] as float4 (one fully used 128-byte line per tap for C = 32) and writes the
+//    2C code columns of the row.
+//  * The staged rows (width 16 + 2C, one per sample) of both warps are folded into J^T J | J^T r on the
+//    tensor cores (mma.sync m16n8k8, 3xTF32, fp32 accumulate), the upper-triangular tiles split between
+//    the two warps.  Nothing is written to HBM except one partial per CTA.
 #include "sage_common.cuh"
 #include "sage_kernels.h"
 
@@ -21,25 +25,30 @@ struct GeoCam
   int W, H;
 };
 
-// staged row: [pose0 6 | pose1 6 | scale0 | scale1 | rhs | pad | code0 C | code1 C]
+constexpr int GEO_WARPS = 2;
+constexpr int GEO_CTA = GEO_WARPS * 32;
+
+// staged row: [pose0 6 | scale0 | scale1 | rhs | 0 x7 | code0 C | code1 C]
 template <int C>
 struct GeoTraits
 {
   static constexpr int LPG = C / 4;
-  static constexpr int GPW = 32 / LPG;
-  static constexpr int SPS = GPW * (SAGE_CTA / 32);
+  static constexpr int NG = 32 / LPG;
   static constexpr int WP = 16 + 2 * C;
+  using Syrk = MmaSyrk<WP, GEO_WARPS>;
+  static constexpr int ST = Syrk::ST;
 };
 
 template <int C, bool JAC>
-__global__ void __launch_bounds__(SAGE_CTA, 2)
+__global__ void __launch_bounds__(GEO_CTA, 6)
 geo_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__restrict__ partH, float *__restrict__ partE)
 {
   using T = GeoTraits<C>;
-  constexpr int LPG = T::LPG, SPS = T::SPS, WP = T::WP;
-  constexpr int STAGE = JAC ? SPS * WP : 4;
-  constexpr int SCR = JAC ? Syrk<WP>::NT * 16 : 4;
-  __shared__ __align__(16) float Y[STAGE > SCR ? STAGE : SCR];
+  constexpr int LPG = T::LPG, WP = T::WP, ST = T::ST;
+  constexpr int ROWS = GEO_WARPS * 32;
+  constexpr int STAGE = JAC ? ROWS * ST : 4;
+  constexpr int HS = JAC ? WP * WP : 4;
+  __shared__ __align__(16) float Y[STAGE > HS ? STAGE : HS];
   __shared__ GeoFactor fs;
   __shared__ float red[32];
   {
@@ -50,129 +59,149 @@ geo_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__res
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPG;
-  const int grp = (threadIdx.x >> 5) * T::GPW + lane / LPG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPG, q = lane / LPG;
   const int N = fs.N;
   const int W = cam.W, H = cam.H;
+  float *Yw = Y + (size_t)warp * 32 * ST;
 
-  Syrk<WP> syrk;
+  typename T::Syrk syrk;
   if constexpr (JAC)
     syrk.init();
   float err_acc = 0.f, inl_acc = 0.f;
 
-  for (int base = blockIdx.x * SPS; base < N; base += gridDim.x * SPS)
+  const int nbatch = (N + 31) / 32;
+  const int nround = (nbatch + GEO_WARPS - 1) / GEO_WARPS; // both warps run the same number of rounds (block barriers inside)
+  for (int round = blockIdx.x; round < nround; round += gridDim.x)
   {
-    const int n = base + grp;
+    const int batch = round * GEO_WARPS + warp;
+    // ------------------------------------------------------------------ lane == sample
+    const int n = batch * 32 + lane;
     const bool live = n < N;
-    float hx = 0.f, hy = 0.f, hz = 0.f, dot = 0.f;
-    int idx = 0;
-    float4 c0 = f4zero();
-    if (live)
-    {
-      const float4 hm = __ldg(fs.homo + n);
-      hx = hm.x; hy = hm.y; hz = hm.z;
-      idx = __ldg(fs.loc1d + n);
-      c0 = ldg4(fs.basis0 + (size_t)idx * C + gl * 4);
-      dot = c0.x * fs.code0[gl * 4 + 0] + c0.y * fs.code0[gl * 4 + 1] + c0.z * fs.code0[gl * 4 + 2] + c0.w * fs.code0[gl * 4 + 3];
-    }
-    dot = group_sum<LPG>(dot);
-
-    float sw = 0.f, diff = 0.f, e = 0.f, valid = 0.f;
-    float pose[6], js0 = 0.f, js1 = 0.f, kc0 = 0.f;
-    float4 c1 = f4zero();
+    const int nc = min(n, N - 1);
+    const float4 hm = __ldg(fs.homo + nc);
+    const float hx = hm.x, hy = hm.y, hz = hm.z;
+    const int idx = __ldg(fs.loc1d + nc);
+    // dpt_0 = (bias + jac . code) * scale_0   (:515-521); the dot product runs lane == channel quad
+    float mydot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 6; ++k)
-      pose[k] = 0.f;
-
-    if (live)
+    for (int i = 0; i < LPG; ++i)
     {
-      // dpt_0 = (bias + jac . code) * scale_0     (:515-521)
-      const float d0 = (__ldg(fs.bias0 + idx) + dot) * fs.scale0;
-      const float rx = fs.R10[0] * hx + fs.R10[1] * hy + fs.R10[2] * hz;
-      const float ry = fs.R10[3] * hx + fs.R10[4] * hy + fs.R10[5] * hz;
-      const float rz = fs.R10[6] * hx + fs.R10[7] * hy + fs.R10[8] * hz;
-      const float px = d0 * rx + fs.t10[0], py = d0 * ry + fs.t10[1], pz = d0 * rz + fs.t10[2];
-      const bool pos = pz > fs.eps;
-      const float ux = (px / pz) * cam.fx + cam.cx;
-      const float uy = (py / pz) * cam.fy + cam.cy;
-      const int mx = (int)roundf(ux), my = (int)roundf(uy);
-      const float wm = within(mx, my, W, H) ? __ldg(&fs.dgm1[my * W + mx].w) : 0.f;
-      valid = pos ? wm : 0.f;
-      if (valid != 0.f)
-      {
-        const Taps tb = make_taps(ux, uy, W, H);
-        const int o = tb.y0 * W + tb.x0;
-        const float4 *dg = fs.dgm1 + o;
-        const float4 z4 = f4zero();
-        const float4 dgv = tap_combine(tb, tb.bnw ? __ldg(dg) : z4, tb.bse ? __ldg(dg + W + 1) : z4, tb.bsw ? __ldg(dg + W) : z4,
-                                       tb.bne ? __ldg(dg + 1) : z4);
-        const float D1 = fs.dscale * dgv.x; // sampled (scaled) depth of KF1
-        const float gx = fs.dscale * dgv.y, gy = fs.dscale * dgv.z;
-        diff = D1 - pz;
-        const float md = wm * diff;
-        e = logf(1.0f + (md * md) / fs.loss_param); // :600
-        if constexpr (JAC)
-        {
-          const float *b1 = fs.basis1 + (size_t)o * C + gl * 4;
-          c1 = tap_combine(tb, tb.bnw ? ldg4(b1) : z4, tb.bse ? ldg4(b1 + (size_t)(W + 1) * C) : z4,
-                           tb.bsw ? ldg4(b1 + (size_t)W * C) : z4, tb.bne ? ldg4(b1 + C) : z4);
-          sw = wm * sqrtf(1.0f / (diff * diff + fs.loss_param)); // :690
-          const float iz = 1.0f / pz;
-          const float xz = px * iz, yz = py * iz;
-          const float wx = d0 * (fs.R0[0] * hx + fs.R0[1] * hy + fs.R0[2] * hz) + fs.t0[0];
-          const float wy = d0 * (fs.R0[3] * hx + fs.R0[4] * hy + fs.R0[5] * hz) + fs.t0[1];
-          const float wz = d0 * (fs.R0[6] * hx + fs.R0[7] * hy + fs.R0[8] * hz) + fs.t0[2];
-          // v = (R1^T)[2,:] - gx * (A R1^T)[0,:] - gy * (A R1^T)[1,:]  with A the 2x3 projection Jacobian (:607-608)
-          float v[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-          {
-            const float a0 = cam.fx * iz * fs.R1[k * 3 + 0] - cam.fx * xz * iz * fs.R1[k * 3 + 2];
-            const float a1 = cam.fy * iz * fs.R1[k * 3 + 1] - cam.fy * yz * iz * fs.R1[k * 3 + 2];
-            v[k] = fs.R1[k * 3 + 2] - (gx * a0 + gy * a1);
-          }
-          pose[0] = v[0]; pose[1] = v[1]; pose[2] = v[2];
-          pose[3] = -v[1] * wz + v[2] * wy;
-          pose[4] = v[0] * wz - v[2] * wx;
-          pose[5] = -v[0] * wy + v[1] * wx;
-          const float jdx = cam.fx * (rx * iz - px * rz * iz * iz);
-          const float jdy = cam.fy * (ry * iz - py * rz * iz * iz);
-          const float d1_jac_d0 = gx * jdx + gy * jdy;
-          kc0 = (rz - d1_jac_d0) * fs.scale0;          // :685
-          js0 = (rz - d1_jac_d0) * d0 / fs.scale0;     // :687
-          js1 = -D1 / fs.scale1;                       // :688
-        }
-      }
+      const int sidx = __shfl_sync(0xffffffffu, idx, q * LPG + i);
+      const float4 cb = ldg4(fs.basis0 + (size_t)sidx * C + gl * 4);
+      float dot = cb.x * fs.code0[gl * 4 + 0] + cb.y * fs.code0[gl * 4 + 1] + cb.z * fs.code0[gl * 4 + 2] + cb.w * fs.code0[gl * 4 + 3];
+      dot = group_sum<LPG>(dot);
+      if (gl == i)
+        mydot = dot;
     }
-    if (gl == 0)
+    const float d0 = (__ldg(fs.bias0 + idx) + mydot) * fs.scale0;
+    const float rx = fs.R10[0] * hx + fs.R10[1] * hy + fs.R10[2] * hz;
+    const float ry = fs.R10[3] * hx + fs.R10[4] * hy + fs.R10[5] * hz;
+    const float rz = fs.R10[6] * hx + fs.R10[7] * hy + fs.R10[8] * hz;
+    const float px = d0 * rx + fs.t10[0], py = d0 * ry + fs.t10[1], pz = d0 * rz + fs.t10[2];
+    const bool pos = pz > fs.eps;
+    float ux = (px / pz) * cam.fx + cam.cx;
+    float uy = (py / pz) * cam.fy + cam.cy;
+    const int mx = (int)roundf(ux), my = (int)roundf(uy);
+    const float wm = (live && pos && within(mx, my, W, H)) ? __ldg(&fs.dgm1[my * W + mx].w) : 0.f;
+    const float valid = wm;
+    if (valid == 0.f)
     {
-      err_acc += e;
-      inl_acc += valid;
+      ux = 0.f; // keep everything finite; the row is multiplied by the zero weight below
+      uy = 0.f;
     }
+    const TapSet tp = make_tapset(ux, uy, W, H, 4); // pk & ~3 = pixel * 4 (float offset into the float4 map)
+    float D1, gx, gy;
+    {
+      const float *pnw = reinterpret_cast<const float *>(fs.dgm1) + (tp.pk & ~3);
+      const float *pne = pnw + ((tp.pk & 2) ? 4 : 0);
+      const float *psw = pnw + ((tp.pk & 1) ? 4 * W : 0);
+      const float *pse = psw + ((tp.pk & 2) ? 4 : 0);
+      const float4 dgv = gather4(pnw, pse, psw, pne, tp.w);
+      D1 = fs.dscale * dgv.x; // sampled (scaled) depth of KF1 and its gradient
+      gx = fs.dscale * dgv.y;
+      gy = fs.dscale * dgv.z;
+    }
+    const float diff = D1 - pz;
+    const float md = wm * diff;
+    const float e = valid != 0.f ? logf(1.0f + (md * md) / fs.loss_param) : 0.f; // :600
+    err_acc += e;
+    inl_acc += valid;
 
     if constexpr (JAC)
     {
-      float *row = Y + (size_t)grp * WP;
-      if (gl == 0)
+      const bool on = valid != 0.f;
+      const float sw = on ? wm * sqrtf(1.0f / (diff * diff + fs.loss_param)) : 0.f; // :690
+      const float iz = on ? 1.0f / pz : 0.f;
+      const float xz = px * iz, yz = py * iz;
+      const float wx = d0 * (fs.R0[0] * hx + fs.R0[1] * hy + fs.R0[2] * hz) + fs.t0[0];
+      const float wy = d0 * (fs.R0[3] * hx + fs.R0[4] * hy + fs.R0[5] * hz) + fs.t0[1];
+      const float wz = d0 * (fs.R0[6] * hx + fs.R0[7] * hy + fs.R0[8] * hz) + fs.t0[2];
+      // v = (R1^T)[2,:] - gx * (A R1^T)[0,:] - gy * (A R1^T)[1,:]  with A the 2x3 projection Jacobian (:607-608, :671-679)
+      float v[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
       {
-        *reinterpret_cast<float4 *>(row + 0) = make_float4(sw * pose[0], sw * pose[1], sw * pose[2], sw * pose[3]);
-        *reinterpret_cast<float4 *>(row + 4) = make_float4(sw * pose[4], sw * pose[5], -(sw * pose[0]), -(sw * pose[1]));
-        *reinterpret_cast<float4 *>(row + 8) = make_float4(-(sw * pose[2]), -(sw * pose[3]), -(sw * pose[4]), -(sw * pose[5]));
-        *reinterpret_cast<float4 *>(row + 12) = make_float4(sw * js0, sw * js1, sw * diff, 0.f);
+        const float a0 = cam.fx * iz * fs.R1[k * 3 + 0] - cam.fx * xz * iz * fs.R1[k * 3 + 2];
+        const float a1 = cam.fy * iz * fs.R1[k * 3 + 1] - cam.fy * yz * iz * fs.R1[k * 3 + 2];
+        v[k] = fs.R1[k * 3 + 2] - (gx * a0 + gy * a1);
       }
-      const float k0 = sw * kc0, k1 = -(sw * fs.scale1);
-      *reinterpret_cast<float4 *>(row + 16 + gl * 4) = make_float4(k0 * c0.x, k0 * c0.y, k0 * c0.z, k0 * c0.w);
-      *reinterpret_cast<float4 *>(row + 16 + C + gl * 4) = make_float4(k1 * c1.x, k1 * c1.y, k1 * c1.z, k1 * c1.w);
+      const float p3 = -v[1] * wz + v[2] * wy, p4 = v[0] * wz - v[2] * wx, p5 = -v[0] * wy + v[1] * wx;
+      const float jdx = cam.fx * (rx * iz - px * rz * iz * iz);
+      const float jdy = cam.fy * (ry * iz - py * rz * iz * iz);
+      const float d1_jac_d0 = gx * jdx + gy * jdy;
+      const float kc0 = (rz - d1_jac_d0) * fs.scale0;      // :685
+      const float js0 = (rz - d1_jac_d0) * d0 / fs.scale0; // :687
+      const float js1 = -D1 / fs.scale1;                   // :688
+      float *row = Yw + (size_t)lane * ST;
+      *reinterpret_cast<float4 *>(row + 0) = make_float4(sw * v[0], sw * v[1], sw * v[2], sw * p3);
+      *reinterpret_cast<float4 *>(row + 4) = make_float4(sw * p4, sw * p5, sw * js0, sw * js1);
+      *reinterpret_cast<float4 *>(row + 8) = make_float4(sw * diff, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4 *>(row + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---------------------------------------------------------------- lane == channel quad: code columns
+      const float k0 = sw * kc0, k1 = -(sw * fs.scale1); // :695-696
+#pragma unroll 2
+      for (int i = 0; i < LPG; ++i)
+      {
+        const int src = q * LPG + i;
+        const float s0 = __shfl_sync(0xffffffffu, k0, src), s1 = __shfl_sync(0xffffffffu, k1, src);
+        const int sidx = __shfl_sync(0xffffffffu, idx, src);
+        const TapSet ts = shfl_tapset(tp, src);
+        const float4 c0 = ldg4(fs.basis0 + (size_t)sidx * C + gl * 4);
+        const float *pnw = fs.basis1 + (size_t)(ts.pk >> 2) * C + gl * 4;
+        const float *pne = pnw + ((ts.pk & 2) ? C : 0);
+        const float *psw = pnw + ((ts.pk & 1) ? W * C : 0);
+        const float *pse = psw + ((ts.pk & 2) ? C : 0);
+        const float4 c1 = gather4(pnw, pse, psw, pne, ts.w);
+        float *r = Yw + (size_t)src * ST + 16 + gl * 4;
+        *reinterpret_cast<float4 *>(r) = make_float4(s0 * c0.x, s0 * c0.y, s0 * c0.z, s0 * c0.w);
+        *reinterpret_cast<float4 *>(r + C) = make_float4(s1 * c1.x, s1 * c1.y, s1 * c1.z, s1 * c1.w);
+      }
       __syncthreads();
-      syrk.accumulate(Y, SPS);
+      if (warp == 0)
+        syrk.template accumulate<0>(Y, ROWS, lane);
+      else
+        syrk.template accumulate<1>(Y, ROWS, lane);
       __syncthreads();
     }
   }
 
   const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   if constexpr (JAC)
-    syrk.store(Y, partH + slot * (WP * WP));
+  {
+    __syncthreads();
+    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
+      Y[i] = 0.f;
+    __syncthreads();
+    if (warp == 0)
+      syrk.template add_to<0>(Y, lane);
+    else
+      syrk.template add_to<1>(Y, lane); // disjoint tiles: no race between the two warps
+    __syncthreads();
+    float *dst = partH + slot * (WP * WP);
+    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
+      dst[i] = Y[i];
+  }
   const float es = block_sum(err_acc, red);
   const float cs = block_sum(inl_acc, red);
   if (threadIdx.x == 0)
@@ -215,30 +244,43 @@ __global__ void geo_finalize_kernel(const GeoFactor *__restrict__ factors, int s
   if constexpr (JAC)
   {
     const float sc = n > 0.f ? f.weight / n : 0.f;
-    // reference order [pose0 6 | pose1 6 | code0 C | code1 C | scale0 | scale1] -> internal column
-    auto icol = [](int c) -> int { return c < 12 ? c : (c < 12 + 2 * C ? 16 + (c - 12) : 12 + (c - 12 - 2 * C)); };
+    // reference order [pose0 6 | pose1 6 | code0 C | code1 C | scale0 | scale1] -> internal column and sign
+    auto icol = [](int c, float &sg) -> int {
+      sg = 1.f;
+      if (c < 6)
+        return c;
+      if (c < 12)
+      {
+        sg = -1.f;
+        return c - 6;
+      }
+      return c < 12 + 2 * C ? 16 + (c - 12) : 6 + (c - 12 - 2 * C);
+    };
     for (int e = threadIdx.x; e < D * D + D; e += blockDim.x)
     {
+      float sr, scn = 1.f;
       int r, c;
       if (e < D * D)
       {
-        r = icol(e / D);
-        c = icol(e % D);
+        r = icol(e / D, sr);
+        c = icol(e % D, scn);
       }
       else
       {
-        r = icol(e - D * D);
-        c = 14;
+        r = icol(e - D * D, sr);
+        c = 8;
       }
+      const int lo = r < c ? r : c, hi = r < c ? c : r;
       float v = 0.f;
       for (int s = 0; s < slices; ++s)
-        v += partH[((size_t)slot * slices + s) * (WP * WP) + r * WP + c];
-      o[e] = v * sc;
+        v += partH[((size_t)slot * slices + s) * (WP * WP) + lo * WP + hi];
+      o[e] = sr * scn * v * sc;
     }
   }
 }
 
 int geo_row_width(int C) { return 16 + 2 * C; }
+int geo_samples_per_cta() { return GEO_WARPS * 32; }
 
 template <int C>
 static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const GeoCam &cam, int slices, float *partH, float *partE,
@@ -247,12 +289,12 @@ static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const
   dim3 grid(slices, nfactors);
   if (jac)
   {
-    geo_kernel<C, true><<<grid, SAGE_CTA, 0, stream>>>(factors, cam, partH, partE);
+    geo_kernel<C, true><<<grid, GEO_CTA, 0, stream>>>(factors, cam, partH, partE);
     geo_finalize_kernel<C, true><<<nfactors, 256, 0, stream>>>(factors, slices, partH, partE, out, out_stride);
   }
   else
   {
-    geo_kernel<C, false><<<grid, SAGE_CTA, 0, stream>>>(factors, cam, partH, partE);
+    geo_kernel<C, false><<<grid, GEO_CTA, 0, stream>>>(factors, cam, partH, partE);
     geo_finalize_kernel<C, false><<<nfactors, 256, 0, stream>>>(factors, slices, partH, partE, out, out_stride);
   }
 }

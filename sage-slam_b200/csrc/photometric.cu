@@ -47,54 +47,6 @@ struct PhotoTraits
   static constexpr int CCH = (C / 4 + LPG - 1) / LPG; // code chunks (float4) per lane
 };
 
-struct TapSet
-{
-  int pk;      // pixel_offset * stride | (dx << 1) | dy : clamped base element and whether the +1 taps move
-  float w[4];  // nw, se, sw, ne ; 0 for out-of-bounds taps (zero padding)
-};
-
-// stride = floats per pixel of the map (a multiple of 4, so the two low bits are free for the flags)
-__device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H, int stride)
-{
-  TapSet t;
-  const int x0 = (int)floorf(px), y0 = (int)floorf(py);
-  const float lx = (float)(x0 + 1) - px, ly = (float)(y0 + 1) - py;
-  const float ux = 1.0f - lx, uy = 1.0f - ly;
-  const int x1 = x0 < 0x7fffffff ? x0 + 1 : x0, y1 = y0 < 0x7fffffff ? y0 + 1 : y0; // cvt saturates; avoid wrap-around
-  const bool bx0 = x0 >= 0 && x0 < W, bx1 = x1 >= 0 && x1 < W;
-  const bool by0 = y0 >= 0 && y0 < H, by1 = y1 >= 0 && y1 < H;
-  t.w[0] = (bx0 && by0) ? lx * ly : 0.f; // nw
-  t.w[1] = (bx1 && by1) ? ux * uy : 0.f; // se
-  t.w[2] = (bx0 && by1) ? lx * uy : 0.f; // sw
-  t.w[3] = (bx1 && by0) ? ux * ly : 0.f; // ne
-  const int xa = min(max(x0, 0), W - 1), xb = min(max(x1, 0), W - 1);
-  const int ya = min(max(y0, 0), H - 1), yb = min(max(y1, 0), H - 1);
-  t.pk = ((ya * W + xa) * stride) | ((xb != xa) ? 2 : 0) | ((yb != ya) ? 1 : 0);
-  return t;
-}
-
-__device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
-{
-  TapSet r;
-  r.pk = __shfl_sync(0xffffffffu, t.pk, src);
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    r.w[k] = __shfl_sync(0xffffffffu, t.w[k], src);
-  return r;
-}
-
-// 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
-__device__ __forceinline__ float4 gather4(const float *pnw, const float *pse, const float *psw, const float *pne, const float *w)
-{
-  const float4 a = ldg4(pnw), b = ldg4(pse), c = ldg4(psw), d = ldg4(pne);
-  float4 r;
-  r.x = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3];
-  r.y = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];
-  r.z = a.z * w[0] + b.z * w[1] + c.z * w[2] + d.z * w[3];
-  r.w = a.w * w[0] + b.w * w[1] + c.w * w[2] + d.w * w[3];
-  return r;
-}
-
 // reduce-scatter of 8 values over a group of LPG lanes: lane gl ends with VPL = 8/LPG totals, value index gl*VPL+k
 template <int LPG>
 __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&out)[8 / LPG])
@@ -147,8 +99,17 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
   }
 }
 
+#ifndef PH_MINB
+#define PH_MINB 3
+#endif
+#ifndef PH_UNROLL
+#define PH_UNROLL 4
+#endif
+#define PH_STR2(x) #x
+#define PH_STR(x) PH_STR2(x)
+
 template <int F, int C, int MODE>
-__global__ void __launch_bounds__(PH_CTA, 3)
+__global__ void __launch_bounds__(PH_CTA, PH_MINB)
 photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ CamPyr cam, float *__restrict__ partH,
              float *__restrict__ partE)
 {
@@ -272,7 +233,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
                  (selB[k] == 1 ? cam.fx[l] : selB[k] == 2 ? cam.fy[l] : 1.f);
 
       // -------------------------------------------------------------- lane == channel quad: gathers
-#pragma unroll 2
+_Pragma(PH_STR(unroll PH_UNROLL))
       for (int i = 0; i < LPG; ++i)
       {
         const int src = q * LPG + i;

@@ -143,6 +143,56 @@ __device__ __forceinline__ float block_sum(float v, float *red)
   return r;
 }
 
+// packed bilinear tap descriptor shared between lanes (photometric / geometric gathers)
+struct TapSet
+{
+  int pk;      // pixel_offset * stride | (dx << 1) | dy : clamped base element and whether the +1 taps move
+  float w[4];  // nw, se, sw, ne ; 0 for out-of-bounds taps (zero padding)
+};
+
+// stride = floats per pixel of the map (a multiple of 4, so the two low bits are free for the flags)
+__device__ __forceinline__ TapSet make_tapset(float px, float py, int W, int H, int stride)
+{
+  TapSet t;
+  const int x0 = (int)floorf(px), y0 = (int)floorf(py);
+  const float lx = (float)(x0 + 1) - px, ly = (float)(y0 + 1) - py;
+  const float ux = 1.0f - lx, uy = 1.0f - ly;
+  const int x1 = x0 < 0x7fffffff ? x0 + 1 : x0, y1 = y0 < 0x7fffffff ? y0 + 1 : y0; // cvt saturates; avoid wrap-around
+  const bool bx0 = x0 >= 0 && x0 < W, bx1 = x1 >= 0 && x1 < W;
+  const bool by0 = y0 >= 0 && y0 < H, by1 = y1 >= 0 && y1 < H;
+  t.w[0] = (bx0 && by0) ? lx * ly : 0.f; // nw
+  t.w[1] = (bx1 && by1) ? ux * uy : 0.f; // se
+  t.w[2] = (bx0 && by1) ? lx * uy : 0.f; // sw
+  t.w[3] = (bx1 && by0) ? ux * ly : 0.f; // ne
+  const int xa = min(max(x0, 0), W - 1), xb = min(max(x1, 0), W - 1);
+  const int ya = min(max(y0, 0), H - 1), yb = min(max(y1, 0), H - 1);
+  t.pk = ((ya * W + xa) * stride) | ((xb != xa) ? 2 : 0) | ((yb != ya) ? 1 : 0);
+  return t;
+}
+
+__device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
+{
+  TapSet r;
+  r.pk = __shfl_sync(0xffffffffu, t.pk, src);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    r.w[k] = __shfl_sync(0xffffffffu, t.w[k], src);
+  return r;
+}
+
+// 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
+__device__ __forceinline__ float4 gather4(const float *pnw, const float *pse, const float *psw, const float *pne, const float *w)
+{
+  const float4 a = ldg4(pnw), b = ldg4(pse), c = ldg4(psw), d = ldg4(pne);
+  float4 r;
+  r.x = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3];
+  r.y = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];
+  r.z = a.z * w[0] + b.z * w[1] + c.z * w[2] + d.z * w[3];
+  r.w = a.w * w[0] + b.w * w[1] + c.w * w[2] + d.w * w[3];
+  return r;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // Cooperative symmetric rank-k accumulator: H += Y^T Y for rows Y[r][0..WP) staged in shared memory.
 // The WP x WP result is kept as upper-triangular 4x4 register tiles, one tile per thread, with the
@@ -260,7 +310,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int WP>
+template <int WP, int NSPLIT = 1>
 struct MmaSyrk
 {
   static_assert(WP % 8 == 0, "row width must be a multiple of 8");
@@ -275,18 +325,20 @@ struct MmaSyrk
     return n;
   }
   static constexpr int NTILES = count_tiles();
-  float acc[NTILES][4];
+  static constexpr int TPW = (NTILES + NSPLIT - 1) / NSPLIT; // tiles per cooperating warp (tile t belongs to part t % NSPLIT)
+  float acc[TPW][4];
 
   __device__ __forceinline__ void init()
   {
 #pragma unroll
-    for (int i = 0; i < NTILES; ++i)
+    for (int i = 0; i < TPW; ++i)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         acc[i][k] = 0.f;
   }
 
-  // rows must be a multiple of 8; every lane of the warp calls this
+  // rows must be a multiple of 8; every lane of the warp calls this.  PART selects this warp's share of the tiles.
+  template <int PART = 0>
   __device__ __forceinline__ void accumulate(const float *Y, int rows, int lane)
   {
     const int g = lane >> 2, t = lane & 3;
@@ -311,47 +363,60 @@ struct MmaSyrk
 #pragma unroll
         for (int nj = 2 * mi; nj < NT8; ++nj)
         {
-          mma_tf32(acc[ti], al0, al1, al2, al3, bh[nj][0], bh[nj][1]);
-          mma_tf32(acc[ti], ah0, ah1, ah2, ah3, bl[nj][0], bl[nj][1]);
-          mma_tf32(acc[ti], ah0, ah1, ah2, ah3, bh[nj][0], bh[nj][1]);
+          if (ti % NSPLIT == PART)
+          {
+            float(&d)[4] = acc[ti / NSPLIT];
+            mma_tf32(d, al0, al1, al2, al3, bh[nj][0], bh[nj][1]);
+            mma_tf32(d, ah0, ah1, ah2, ah3, bl[nj][0], bl[nj][1]);
+            mma_tf32(d, ah0, ah1, ah2, ah3, bh[nj][0], bh[nj][1]);
+          }
           ++ti;
         }
       }
     }
   }
 
-  // Sum the warps' accumulators in shared memory (Hs: WP*WP floats, may alias the staging buffer once every warp is
-  // done with it) and write the CTA's WP x WP partial (upper triangle valid) to dst.  Called by all threads.
+  // add this warp's tiles into the WP x WP matrix Hs (shared memory, zero-initialised, exclusive access)
+  template <int PART = 0>
+  __device__ __forceinline__ void add_to(float *Hs, int lane) const
+  {
+    const int g = lane >> 2, t = lane & 3;
+    int ti = 0;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int nj = 2 * mi; nj < NT8; ++nj)
+      {
+        if (ti % NSPLIT == PART)
+        {
+          const float(&d)[4] = acc[ti / NSPLIT];
+          const int r = 16 * mi + g, c = 8 * nj + 2 * t;
+          if (r < WP)
+          {
+            Hs[r * WP + c] += d[0];
+            Hs[r * WP + c + 1] += d[1];
+          }
+          if (r + 8 < WP)
+          {
+            Hs[(r + 8) * WP + c] += d[2];
+            Hs[(r + 8) * WP + c + 1] += d[3];
+          }
+        }
+        ++ti;
+      }
+  }
+
+  // NSPLIT == 1: sum the warps' full accumulators in shared memory (Hs: WP*WP floats, may alias the staging buffer once
+  // every warp is done with it) and write the CTA's WP x WP partial (upper triangle valid) to dst.  Called by all threads.
   __device__ __forceinline__ void store_cta(float *Hs, float *dst, int warp, int lane, int nwarps)
   {
     for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
       Hs[i] = 0.f;
     __syncthreads();
-    const int g = lane >> 2, t = lane & 3;
     for (int w = 0; w < nwarps; ++w)
     {
       if (warp == w)
-      {
-        int ti = 0;
-#pragma unroll
-        for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-          for (int nj = 2 * mi; nj < NT8; ++nj)
-          {
-            const int r = 16 * mi + g, c = 8 * nj + 2 * t;
-            if (r < WP)
-            {
-              Hs[r * WP + c] += acc[ti][0];
-              Hs[r * WP + c + 1] += acc[ti][1];
-            }
-            if (r + 8 < WP)
-            {
-              Hs[(r + 8) * WP + c] += acc[ti][2];
-              Hs[(r + 8) * WP + c + 1] += acc[ti][3];
-            }
-            ++ti;
-          }
-      }
+        add_to<0>(Hs, lane);
       __syncthreads();
     }
     for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
