@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -239,6 +239,12 @@ def run_ours(args):
         pj_ms, pj_n = prof["photo_jac"]
         per_launch_ms = pj_ms / max(pj_n, 1)
         achieved = shard["photo"] * b_photo / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        try:  # DRAM bytes of the same launch from the committed ncu --set full capture (scaled to this rank's pair count)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["photo_jac"]
+            traffic = tj["dram_bytes_per_launch"] / tj["pairs_per_launch"] * shard["photo"]
+        except Exception:
+            pass
         residuals = ba.num_residuals
         ms_per_step = ms / args.steps
         line = {
@@ -255,7 +261,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "photo_kernel<32,32,MAP_JAC> (photometric linearisation, all owned pairs per launch)",
                          "achieved": achieved, "peak": hbm, "peak_source": src, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": shard["photo"] * b_photo},
+                         "traffic": traffic, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": shard["photo"] * b_photo},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "clocks": clocks,
             "lm_trace": [(float(a), float(b)) for a, b in costs[-args.steps:]][:6],
