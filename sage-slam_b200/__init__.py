@@ -5,7 +5,7 @@ ops.py (host mirror of the reference df::*_calculate operator API), local_ba.py 
 multi-GPU plumbing), frames.py / synthetic.py (data contract and synthetic inputs).
 Importing the package never touches CUDA; creating a Context does, and fails loudly without a GPU.
 """
-from . import capi, frames, synthetic  # noqa: F401
+from . import capi, factors, frames, synthetic  # noqa: F401
 from .frames import Keyframe  # noqa: F401
 from .local_ba import LocalBA  # noqa: F401
 from .ops import Context, DeviceKeyframe, SageError  # noqa: F401

@@ -31,7 +31,13 @@
 namespace sage
 {
 
-constexpr int PH_WARPS = 4;
+#ifndef PH_NWARPS
+#define PH_NWARPS 4
+#endif
+#ifndef PH_HALF
+#define PH_HALF 0
+#endif
+constexpr int PH_WARPS = PH_NWARPS;
 constexpr int PH_CTA = PH_WARPS * 32;
 
 template <int F, int C, int MODE>
@@ -115,7 +121,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
 {
   using T = PhotoTraits<F, C, MODE>;
   constexpr int LPG = T::LPG, NG = T::NG, VPL = T::VPL, WP = T::WP, ST = T::ST, CCH = T::CCH;
-  constexpr int ROWS = 64; // two virtual rows per sample, 32 samples per warp batch
+  constexpr int ROWS = PH_HALF ? 32 : 64; // virtual rows staged per warp at a time (two per sample, 32 samples per batch)
   constexpr int STAGE = T::kJac ? PH_WARPS * ROWS * ST : 4;
   constexpr int HS = T::kJac ? WP * WP : 4;
   __shared__ __align__(16) float Y[STAGE > HS ? STAGE : HS];
@@ -343,50 +349,62 @@ _Pragma(PH_STR(unroll PH_UNROLL))
       P0[6] = has_scale ? jdx * d0 / fs.scale0 : 0.f;
       P1[6] = has_scale ? jdy * d0 / fs.scale0 : 0.f;
       const float c11 = on ? l11 : 0.f, c21 = on ? l21 : 0.f, c22 = on ? l22 : 0.f;
-      float *row = Yw + (size_t)(2 * lane) * ST;
-      {
-        float v[8], u[8];
+      float v[8], u[8];
 #pragma unroll
-        for (int k = 0; k < 7; ++k)
-        {
-          v[k] = c11 * P0[k] + c21 * P1[k];
-          u[k] = c22 * P1[k];
-        }
-        v[7] = on ? rho1 : 0.f;
-        u[7] = on ? rho2 : 0.f;
-        *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4 *>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        *reinterpret_cast<float4 *>(row + ST) = make_float4(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<float4 *>(row + ST + 4) = make_float4(u[4], u[5], u[6], u[7]);
+      for (int k = 0; k < 7; ++k)
+      {
+        v[k] = c11 * P0[k] + c21 * P1[k];
+        u[k] = c22 * P1[k];
       }
-      if constexpr (T::kMap)
+      v[7] = on ? rho1 : 0.f;
+      u[7] = on ? rho2 : 0.f;
+      // code columns: P[:, code_i] = jd * scale0 * basis_i (:331-332)  ->  y1 = k1 c, y2 = k2 c
+      const float k1 = (c11 * jdx + c21 * jdy) * fs.scale0;
+      const float k2 = (c22 * jdy) * fs.scale0;
+      // PH_HALF: stage and fold the two virtual rows of the 32 samples one after the other (half the staging buffer)
+#pragma unroll
+      for (int pass = 0; pass < (PH_HALF ? 2 : 1); ++pass)
       {
-        // code columns: P[:, code_i] = jd * scale0 * basis_i (:331-332)  ->  y1 = k1 c, y2 = k2 c   (lane == channel quad)
-        const float k1 = (c11 * jdx + c21 * jdy) * fs.scale0;
-        const float k2 = (c22 * jdy) * fs.scale0;
-#pragma unroll
-        for (int i = 0; i < LPG; ++i)
+        float *row = PH_HALF ? Yw + (size_t)lane * ST : Yw + (size_t)(2 * lane) * ST;
+        if (!PH_HALF || pass == 0)
         {
-          const int src = q * LPG + i;
-          const float s1 = __shfl_sync(0xffffffffu, k1, src), s2 = __shfl_sync(0xffffffffu, k2, src);
-          const int sidx = __shfl_sync(0xffffffffu, idx, src);
-          float *r0 = Yw + (size_t)(2 * src) * ST + 8;
+          *reinterpret_cast<float4 *>(row) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4 *>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (!PH_HALF || pass == 1)
+        {
+          float *r2 = PH_HALF ? row : row + ST;
+          *reinterpret_cast<float4 *>(r2) = make_float4(u[0], u[1], u[2], u[3]);
+          *reinterpret_cast<float4 *>(r2 + 4) = make_float4(u[4], u[5], u[6], u[7]);
+        }
+        if constexpr (T::kMap)
+        {
 #pragma unroll
-          for (int k = 0; k < CCH; ++k)
+          for (int i = 0; i < LPG; ++i) // lane == channel quad
           {
-            const int ch = gl + k * LPG;
-            if (ch < C / 4)
+            const int src = q * LPG + i;
+            const float s1 = __shfl_sync(0xffffffffu, k1, src), s2 = __shfl_sync(0xffffffffu, k2, src);
+            const int sidx = __shfl_sync(0xffffffffu, idx, src);
+            float *r0 = (PH_HALF ? Yw + (size_t)src * ST : Yw + (size_t)(2 * src) * ST) + 8;
+#pragma unroll
+            for (int k = 0; k < CCH; ++k)
             {
-              const float4 cb = ldg4(fs.basis0 + (size_t)sidx * C + ch * 4);
-              *reinterpret_cast<float4 *>(r0 + ch * 4) = make_float4(s1 * cb.x, s1 * cb.y, s1 * cb.z, s1 * cb.w);
-              *reinterpret_cast<float4 *>(r0 + ST + ch * 4) = make_float4(s2 * cb.x, s2 * cb.y, s2 * cb.z, s2 * cb.w);
+              const int ch = gl + k * LPG;
+              if (ch < C / 4)
+              {
+                const float4 cb = ldg4(fs.basis0 + (size_t)sidx * C + ch * 4);
+                if (!PH_HALF || pass == 0)
+                  *reinterpret_cast<float4 *>(r0 + ch * 4) = make_float4(s1 * cb.x, s1 * cb.y, s1 * cb.z, s1 * cb.w);
+                if (!PH_HALF || pass == 1)
+                  *reinterpret_cast<float4 *>(r0 + (PH_HALF ? 0 : ST) + ch * 4) = make_float4(s2 * cb.x, s2 * cb.y, s2 * cb.z, s2 * cb.w);
+              }
             }
           }
         }
+        __syncwarp();
+        syrk.accumulate(Yw, ROWS, lane);
+        __syncwarp();
       }
-      __syncwarp();
-      syrk.accumulate(Yw, ROWS, lane);
-      __syncwarp();
     }
   }
 

@@ -1,0 +1,195 @@
+"""Host mirror of the reference's GTSAM factor classes for the hot path:
+
+    PhotometricFactor   core/gtsam/photometric_factor.cpp:72 (error), :106-219 (linearize), :264-311
+    GeometricFactor     core/gtsam/geometric_factor.cpp:41, :67-233, :300-356
+    ReprojectionFactor  core/gtsam/reprojection_factor.cpp:201, :227-317, :332-396
+
+Same responsibilities as the reference classes: unpack `Values` (pose_wk as (R, t), code, scale), build the
+relative pose T10 = T1^-1 T0 in fp32 (photometric_factor.cpp:280-281), call the operator (here: the C ABI),
+cast AtA/Atb to fp64, apply NearestPsd (core/mapping/mapping_utils.h:104-128) and slice the upper-triangular
+block list of a gtsam::HessianFactor(keys, Gs, gs, f = error)  [E(x) = 1/2 x^T G x - x^T g + 1/2 f].
+
+NearestPsd in the reference forms V^T S V instead of V S V^T, which is not a projection.
+`psd="reference"` reproduces that bit of behaviour, `psd="exact"` is Higham's projection, `psd="none"` skips it.
+GTSAM itself is not available here, so HessianFactor is a plain record with the same fields.
+"""
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from . import ops
+
+F32 = np.float32
+
+
+def pose_key(k):
+    """gtsam::Symbol('p', id)  (core/gtsam/gtsam_utils.h:10-13)"""
+    return ("p", int(k))
+
+
+def code_key(k):
+    return ("c", int(k))
+
+
+def scale_key(k):
+    return ("s", int(k))
+
+
+class Values(dict):
+    """gtsam::Values stand-in: {pose_key: (R [3,3], t [3]), code_key: code [C] (double), scale_key: float}."""
+
+
+def nearest_psd(M, mode="reference"):
+    """NearestPsd (core/mapping/mapping_utils.h:104-128) in fp64."""
+    M = np.asarray(M, dtype=np.float64)
+    if mode == "none":
+        return M
+    B = (M + M.T) / 2
+    _, s, Vt = np.linalg.svd(B)
+    V = Vt.T
+    Hm = (V.T @ np.diag(s) @ V) if mode == "reference" else (V @ np.diag(s) @ V.T)
+    A2 = (B + Hm) / 2
+    A3 = (A2 + A2.T) / 2
+    k, I = 1, np.eye(M.shape[0])
+    while True:
+        try:
+            np.linalg.cholesky(A3)
+            return A3
+        except np.linalg.LinAlgError:
+            A3 = A3 + I * (-np.linalg.eigvalsh(A3).min() * k + 1e-15)
+            k *= 2
+
+
+@dataclass
+class HessianFactor:
+    """gtsam::HessianFactor(keys, Gs, gs, f): Gs is the upper-triangular block list in row-major block order."""
+    keys: List[Tuple[str, int]]
+    dims: List[int]
+    Gs: List[np.ndarray]
+    gs: List[np.ndarray]
+    f: float
+
+    def information(self):
+        """Dense symmetric G and g in the factor's key order."""
+        off = np.concatenate([[0], np.cumsum(self.dims)])
+        n = int(off[-1])
+        G, g = np.zeros((n, n)), np.zeros(n)
+        it = iter(self.Gs)
+        for a in range(len(self.dims)):
+            for b in range(a, len(self.dims)):
+                blk = next(it)
+                G[off[a]:off[a + 1], off[b]:off[b + 1]] = blk
+                G[off[b]:off[b + 1], off[a]:off[a + 1]] = blk.T
+            g[off[a]:off[a + 1]] = self.gs[a].reshape(-1)
+        return G, g
+
+
+def _partition(AtA, Atb, keys, dims, error, psd):
+    G = nearest_psd(np.asarray(AtA, np.float64), psd)
+    g = np.asarray(Atb, np.float64).reshape(-1)
+    off = np.concatenate([[0], np.cumsum(dims)])
+    Gs, gs = [], []
+    for a in range(len(dims)):
+        for b in range(a, len(dims)):
+            Gs.append(G[off[a]:off[a + 1], off[b]:off[b + 1]].copy())
+        gs.append(g[off[a]:off[a + 1]].copy())
+    return HessianFactor(list(keys), list(dims), Gs, gs, float(error))
+
+
+def _rel(p0, p1):
+    R0, t0 = np.asarray(p0[0], F32), np.asarray(p0[1], F32)
+    R1, t1 = np.asarray(p1[0], F32), np.asarray(p1[1], F32)
+    return (R1.T @ R0).astype(F32), (R1.T @ (t0 - t1)).astype(F32), R0, t0, R1, t1
+
+
+class PhotometricFactor:
+    """keys (pose0, pose1, code0, scale0); 10 blocks (photometric_factor.cpp:151-218)."""
+
+    def __init__(self, ctx, kf, fr, factor_weights, dpt_eps=1e-4, psd="reference"):
+        self.ctx, self.kf, self.fr = ctx, kf, fr  # DeviceKeyframe handles; kf.kf.id / fr.kf.id are the frame ids
+        self.weights, self.eps, self.psd = np.asarray(factor_weights, F32), dpt_eps, psd
+        self.keys = [pose_key(kf.kf.id), pose_key(fr.kf.id), code_key(kf.kf.id), scale_key(kf.kf.id)]
+        self.error_ = None
+
+    def dim(self):
+        return 13 + self.kf.C
+
+    def _unpack(self, c):
+        return c[self.keys[0]], c[self.keys[1]], np.asarray(c[self.keys[2]], F32), float(c[self.keys[3]])
+
+    def error(self, c):
+        p0, p1, code, s = self._unpack(c)
+        R10, t10, *_ = _rel(p0, p1)
+        e, _ = ops.photometric_error_calculate(self.ctx, self.kf, self.fr, R10, t10, code, s, self.eps, self.weights)
+        return float(e)
+
+    def linearize(self, c):
+        p0, p1, code, s = self._unpack(c)
+        R10, t10, R0, t0, R1, t1 = _rel(p0, p1)
+        AtA, Atb, e, _ = ops.photometric_jac_error_calculate(self.ctx, self.kf, self.fr, R10, t10, R0, t0, R1, t1, code, s,
+                                                             self.eps, self.weights)
+        self.error_ = e
+        return _partition(AtA, Atb, self.keys, [6, 6, self.kf.C, 1], e, self.psd)
+
+
+class GeometricFactor:
+    """keys (pose0, pose1, code0, code1, scale0, scale1); 21 blocks (geometric_factor.cpp:122-233)."""
+
+    def __init__(self, ctx, kf0, kf1, factor_weight, loss_param, dpt_eps=1e-4, psd="reference"):
+        self.ctx, self.kf0, self.kf1 = ctx, kf0, kf1
+        self.weight, self.loss_param, self.eps, self.psd = factor_weight, loss_param, dpt_eps, psd
+        i, j = kf0.kf.id, kf1.kf.id
+        self.keys = [pose_key(i), pose_key(j), code_key(i), code_key(j), scale_key(i), scale_key(j)]
+
+    def dim(self):
+        return 14 + 2 * self.kf0.C
+
+    def _unpack(self, c):
+        k = self.keys
+        return c[k[0]], c[k[1]], np.asarray(c[k[2]], F32), np.asarray(c[k[3]], F32), float(c[k[4]]), float(c[k[5]])
+
+    def error(self, c):
+        p0, p1, c0, c1, s0, s1 = self._unpack(c)
+        R10, t10, *_ = _rel(p0, p1)
+        e, _ = ops.geometric_error_calculate(self.ctx, self.kf0, self.kf1, R10, t10, c0, c1, s0, s1, self.eps, self.loss_param,
+                                             self.weight)
+        return float(e)
+
+    def linearize(self, c):
+        p0, p1, c0, c1, s0, s1 = self._unpack(c)
+        R10, t10, R0, t0, R1, t1 = _rel(p0, p1)
+        AtA, Atb, e, _ = ops.geometric_jac_error_calculate(self.ctx, self.kf0, self.kf1, R10, t10, R0, t0, R1, t1, c0, c1, s0, s1,
+                                                           self.eps, self.loss_param, self.weight)
+        C = self.kf0.C
+        return _partition(AtA, Atb, self.keys, [6, 6, C, C, 1, 1], e, self.psd)
+
+
+class ReprojectionFactor:
+    """keys (pose0, pose1, code0, scale0); matches are found once by the constructor in the reference
+    (reprojection_factor.cpp:7-193, section 8 f3 = next) and are handed in here."""
+
+    def __init__(self, ctx, kf, fr, matched_locations_1d_0, matched_locations_homo_0, matched_locations_2d_1, factor_weight,
+                 loss_param, inlier_multiplier=1.0, dpt_eps=1e-4, psd="reference"):
+        self.ctx, self.kf, self.fr = ctx, kf, fr
+        self.loc, self.homo, self.m2d = matched_locations_1d_0, matched_locations_homo_0, matched_locations_2d_1
+        self.weight, self.loss_param, self.eps, self.psd = inlier_multiplier * factor_weight, loss_param, dpt_eps, psd
+        self.keys = [pose_key(kf.kf.id), pose_key(fr.kf.id), code_key(kf.kf.id), scale_key(kf.kf.id)]
+
+    def dim(self):
+        return 13 + self.kf.C
+
+    def error(self, c):
+        p0, p1 = c[self.keys[0]], c[self.keys[1]]
+        R10, t10, *_ = _rel(p0, p1)
+        e, _ = ops.reprojection_error_calculate(self.ctx, self.kf, R10, t10, np.asarray(c[self.keys[2]], F32), float(c[self.keys[3]]),
+                                                self.loc, self.homo, self.m2d, self.eps, self.loss_param, self.weight)
+        return float(e)
+
+    def linearize(self, c):
+        p0, p1 = c[self.keys[0]], c[self.keys[1]]
+        R10, t10, R0, t0, R1, t1 = _rel(p0, p1)
+        AtA, Atb, e, _ = ops.reprojection_jac_error_calculate(self.ctx, self.kf, R10, t10, R0, t0, R1, t1,
+                                                              np.asarray(c[self.keys[2]], F32), float(c[self.keys[3]]), self.loc,
+                                                              self.homo, self.m2d, self.eps, self.loss_param, self.weight)
+        return _partition(AtA, Atb, self.keys, [6, 6, self.kf.C, 1], e, self.psd)

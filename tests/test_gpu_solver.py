@@ -127,3 +127,78 @@ def test_track_new_frame_matches_oracle_lm(sage_ctx):
     assert abs(rep["final_error"] - eo) / eo <= 1e-4
     assert np.abs(t - to).max() <= 1e-5 and np.abs(R - Ro).max() <= 1e-5
     assert rep["final_error"] < err(a["R10"], a["t10"])
+
+
+@pytest.mark.gpu
+def test_factor_classes_error_linearize(sage_ctx):
+    """PhotometricFactor / GeometricFactor / ReprojectionFactor::{error, linearize} (row a6) against the oracle, and the
+    invariant the reference authors left commented out (photometric_factor.cpp:124-143):
+    err(x + d) - err(x) ~= d^T AtA d - 2 Atb^T d for a small step d."""
+    import oracle as O
+    from sage_slam_b200 import factors
+
+    kfs = helpers.build_case("small_c8_f16")
+    a = helpers.case_args(kfs)
+    d0, d1 = sage.DeviceKeyframe(sage_ctx, kfs[0]), sage.DeviceKeyframe(sage_ctx, kfs[1])
+    vals = factors.Values()
+    for k in kfs:
+        vals[factors.pose_key(k.id)] = k.pose_wk
+        vals[factors.code_key(k.id)] = k.code.astype(np.float64)
+        vals[factors.scale_key(k.id)] = k.dpt_scale
+    pf = factors.PhotometricFactor(sage_ctx, d0, d1, a["weights"], psd="none")
+    hf = pf.linearize(vals)
+    A, b, e, _ = O.photometric_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["bias0"], a["jac0"], a["code0"],
+                                         a["mask1"], a["loc1d"], a["homo"], a["feat0"], a["feat1"], a["grad1"], a["level_offsets"],
+                                         a["scale0"], a["cams"], a["eps"], a["weights"])
+    G, g = hf.information()
+    assert helpers.rel_err(G, (A + A.T) / 2) <= 1e-4 and helpers.rel_err(g, b) <= 1e-4 and abs(hf.f - e) / e <= 1e-4
+    assert abs(pf.error(vals) - e) / e <= 1e-4
+    assert hf.keys == [("p", 0), ("p", 1), ("c", 0), ("s", 0)] and pf.dim() == 21
+    # quadratic-model invariant on the code block (additive variables): small step along -gradient direction
+    rng = np.random.default_rng(0)
+    dc = 1e-3 * rng.standard_normal(8)
+    v2 = factors.Values(vals)
+    v2[factors.code_key(0)] = vals[factors.code_key(0)] + dc
+    d = np.zeros(21)
+    d[12:20] = dc
+    pred = d @ G @ d - 2 * g @ d
+    act = pf.error(v2) - pf.error(vals)
+    assert abs(pred - act) <= 0.1 * abs(act) + 1e-4 * e
+    gf = factors.GeometricFactor(sage_ctx, d0, d1, a["geo_weight"], a["geo_loss"], psd="exact")
+    hg = gf.linearize(vals)
+    assert len(hg.Gs) == 21 and gf.dim() == 30 and np.linalg.eigvalsh(hg.information()[0]).min() > -1e-9
+    assert abs(gf.error(vals) - hg.f) / hg.f <= 1e-4
+    ma = helpers.match_args(kfs)
+    rf = factors.ReprojectionFactor(sage_ctx, d0, d1, ma["mloc"], ma["mhomo"], ma["m2d"], a["rep_weight"], a["rep_loss"])
+    hr = rf.linearize(vals)
+    assert len(hr.Gs) == 10 and abs(rf.error(vals) - hr.f) / hr.f <= 1e-4
+
+
+@pytest.mark.gpu
+def test_ragged_sample_counts_and_random_subsets(sage_ctx):
+    """N not a multiple of the 32-sample batch, tiny N, and random (non-raster) subsets."""
+    import oracle as O
+    from sage_slam_b200 import ops
+
+    kfs = helpers.build_case("small_c32_f32")
+    rng = np.random.default_rng(4)
+    for n in (1, 31, 33, 1000):
+        sel = np.sort(rng.permutation(len(kfs[0].sampled_locations_1d))[:n])
+        for k in kfs:
+            k.sampled_locations_1d = k.sampled_locations_1d[sel]
+            k.sampled_locations_homo = k.sampled_locations_homo[sel]
+        a = helpers.case_args(kfs)
+        d0, d1 = sage.DeviceKeyframe(sage_ctx, kfs[0]), sage.DeviceKeyframe(sage_ctx, kfs[1])
+        A, b, e, ninl = ops.photometric_jac_error_calculate(sage_ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"],
+                                                            a["code0"], a["scale0"], a["eps"], a["weights"])
+        Ao, bo, eo, no = O.photometric_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["bias0"], a["jac0"],
+                                                 a["code0"], a["mask1"], a["loc1d"], a["homo"], a["feat0"], a["feat1"], a["grad1"],
+                                                 a["level_offsets"], a["scale0"], a["cams"], a["eps"], a["weights"])
+        assert ninl == no and helpers.rel_err(A, Ao) <= 1e-4 and helpers.rel_err(b, bo) <= 1e-4 and abs(e - eo) <= 1e-4 * max(eo, 1e-9)
+        G, gb, ge, gn = ops.geometric_jac_error_calculate(sage_ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"],
+                                                          a["code0"], a["code1"], a["scale0"], a["scale1"], a["eps"], a["geo_loss"],
+                                                          a["geo_weight"])
+        Go, gbo, geo_, gno = O.geometric_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["bias0"], a["jac0"],
+                                                   a["code0"], a["dpt1"], a["dgrad1"], a["basis1"], a["mask1"], a["loc1d"], a["homo"],
+                                                   a["scale0"], a["scale1"], a["cam"], a["eps"], a["geo_loss"], a["geo_weight"])
+        assert gn == gno and helpers.rel_err(G, Go) <= 1e-4 and helpers.rel_err(gb, gbo) <= 1e-4 and abs(ge - geo_) <= 1e-4 * max(geo_, 1e-9)

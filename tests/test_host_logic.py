@@ -120,3 +120,28 @@ def test_factor_packing_and_dense_assembly_layout():
     c1, c2 = 6 * K + 1 * (C + 1), 6 * K + 2 * (C + 1)
     np.testing.assert_allclose(H[c1:c1 + C, c2:c2 + C], mats[1][0][12:12 + C, 12 + C:12 + 2 * C], rtol=1e-6)
     assert local_ba.shard_factors(7, 1, 3) == [1, 4]
+
+
+def test_factor_partition_and_nearest_psd_match_oracle():
+    """factors._partition == the reference's HessianFactor slicing; factors.nearest_psd == the oracle restatement."""
+    from sage_slam_b200 import factors
+
+    rng = np.random.default_rng(9)
+    C = 8
+    D = 13 + C
+    A = rng.standard_normal((D, D))
+    A = (A @ A.T).astype(np.float32)
+    b = rng.standard_normal(D).astype(np.float32)
+    for mode, faithful in (("reference", True), ("exact", False)):
+        np.testing.assert_allclose(factors.nearest_psd(A, mode), O.nearest_psd(A, reference_faithful=faithful), rtol=1e-12, atol=1e-12)
+    keys = [factors.pose_key(3), factors.pose_key(5), factors.code_key(3), factors.scale_key(3)]
+    hf = factors._partition(A, b, keys, [6, 6, C, 1], 2.5, "none")
+    assert len(hf.Gs) == 10 and len(hf.gs) == 4 and hf.f == 2.5
+    assert [g.shape for g in hf.Gs] == [(6, 6), (6, 6), (6, C), (6, 1), (6, 6), (6, C), (6, 1), (C, C), (C, 1), (1, 1)]
+    np.testing.assert_array_equal(hf.Gs[2], A.astype(np.float64)[0:6, 12:12 + C])       # G13
+    np.testing.assert_array_equal(hf.Gs[8], A.astype(np.float64)[12:12 + C, 12 + C:])   # G34
+    G, g = hf.information()
+    np.testing.assert_allclose(G, (A.astype(np.float64) + A.astype(np.float64).T) / 2, rtol=1e-6)
+    np.testing.assert_array_equal(g, b.astype(np.float64))
+    hg = factors._partition(np.eye(14 + 2 * C), np.zeros(14 + 2 * C), list(range(6)), [6, 6, C, C, 1, 1], 0.0, "none")
+    assert len(hg.Gs) == 21
