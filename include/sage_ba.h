@@ -71,6 +71,9 @@ typedef struct sage_ba_keyframe_desc
   int height, width, levels;           /* level-0 size, pyramid levels L                          */
   int feat_channels, code_size;        /* F (16 or 32), C (8, 16 or 32)                           */
   sage_ba_camera camera;               /* level-0 camera; the pyramid is derived like CameraPyramid */
+  const float *feat_map;               /* [F, H, W] feature-net output, OR NULL.  When given, the Gaussian pyramid with
+                                          gradients is built on the device (Mapper::GenerateGaussianPyramidWithGrad,
+                                          mapper.cpp:1385-1426) and the two pyramid pointers below are ignored.     */
   const float *feat_map_pyramid;       /* [F, SP]      Frame::feat_map_pyramid                    */
   const float *feat_map_grad_pyramid;  /* [2, F, SP]   Frame::feat_map_grad_pyramid (0:dx 1:dy)   */
   const float *dpt_map_bias;           /* [H*W]        Frame::dpt_map_bias (may be NULL for a tracked frame) */
@@ -222,6 +225,9 @@ int sage_ba_problem_add_code_prior(sage_ba_problem *p, int kf, const float *init
 int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale, float weight);
 /* hold a keyframe's pose (and optionally scale) fixed: the gauge anchor (mapper.cpp:190-192) */
 int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale);
+/* linear solver: 0 auto, 1 dense Schur complement onto the pose block (cuSOLVER), 2 block-banded Cholesky over keyframes
+ * (chain-shaped covisibility only).  Auto picks 2 when the keyframe bandwidth is <= 7. */
+int sage_ba_problem_set_solver(sage_ba_problem *p, int solver);
 /* restrict this process to the factors with index % world == rank (multi-GPU sharding) */
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);
 

@@ -22,7 +22,7 @@ class Camera(C.Structure):
 class KeyframeDesc(C.Structure):
     _fields_ = [("memory", C.c_int), ("height", C.c_int), ("width", C.c_int), ("levels", C.c_int),
                 ("feat_channels", C.c_int), ("code_size", C.c_int), ("camera", Camera),
-                ("feat_map_pyramid", vp), ("feat_map_grad_pyramid", vp), ("dpt_map_bias", vp), ("dpt_jac_code", vp),
+                ("feat_map", vp), ("feat_map_pyramid", vp), ("feat_map_grad_pyramid", vp), ("dpt_map_bias", vp), ("dpt_jac_code", vp),
                 ("jac_stride_row", C.c_long), ("jac_stride_col", C.c_long), ("video_mask", vp),
                 ("sampled_locations_1d", vp), ("sampled_locations_homo", vp), ("num_samples", C.c_int)]
 
@@ -87,6 +87,7 @@ SIGNATURES = {
     "sage_ba_problem_add_code_prior": (C.c_int, [vp, C.c_int, vp, F]),
     "sage_ba_problem_add_scale_prior": (C.c_int, [vp, C.c_int, F, F]),
     "sage_ba_problem_fix": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+    "sage_ba_problem_set_solver": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "sage_ba_problem_set_state": (C.c_int, [vp, vp, vp, vp, F]),
     "sage_ba_problem_get_state": (C.c_int, [vp, vp, vp, vp]),

@@ -230,21 +230,34 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
   };
   try
   {
-    SAGE_CHECK(d->feat_map_pyramid && d->video_mask, "feat_map_pyramid and video_mask are required");
+    SAGE_CHECK((d->feat_map_pyramid || d->feat_map) && d->video_mask, "feat_map (or feat_map_pyramid) and video_mask are required");
     SAGE_CUDA(cudaMalloc(&kf->fg, sizeof(float) * SP * 3 * F));
     SAGE_CUDA(cudaMalloc(&kf->mask, sizeof(float) * HW));
-    const float *feat = (const float *)stage(d->feat_map_pyramid, sizeof(float) * F * SP);
-    if (d->feat_map_grad_pyramid)
+    if (d->feat_map)
     {
-      const float *grad = (const float *)stage(d->feat_map_grad_pyramid, sizeof(float) * 2 * F * SP);
-      launch_relayout_fg(feat, grad, kf->fg, F, SP, s);
-      ctx->launches += 3;
+      // device-side input builder: masked Gaussian pyramid + gradients straight into the channel-last layout
+      const float *feat0 = (const float *)stage(d->feat_map, sizeof(float) * F * HW);
+      const float *mask0 = (const float *)stage(d->video_mask, sizeof(float) * HW);
+      void *mscr = nullptr;
+      SAGE_CUDA(cudaMalloc(&mscr, sizeof(float) * (HW + 256)));
+      temps.push_back(mscr);
+      ctx->launches += launch_build_pyramid(feat0, mask0, kf->fg, (float *)mscr, kf->pyr, F, s);
     }
     else
     {
-      SAGE_CUDA(cudaMemsetAsync(kf->fg, 0, sizeof(float) * SP * 3 * F, s));
-      launch_relayout_fg(feat, nullptr, kf->fg, F, SP, s);
-      ctx->launches += 1;
+      const float *feat = (const float *)stage(d->feat_map_pyramid, sizeof(float) * F * SP);
+      if (d->feat_map_grad_pyramid)
+      {
+        const float *grad = (const float *)stage(d->feat_map_grad_pyramid, sizeof(float) * 2 * F * SP);
+        launch_relayout_fg(feat, grad, kf->fg, F, SP, s);
+        ctx->launches += 3;
+      }
+      else
+      {
+        SAGE_CUDA(cudaMemsetAsync(kf->fg, 0, sizeof(float) * SP * 3 * F, s));
+        launch_relayout_fg(feat, nullptr, kf->fg, F, SP, s);
+        ctx->launches += 1;
+      }
     }
     SAGE_CUDA(cudaMemcpyAsync(kf->mask, d->video_mask, sizeof(float) * HW, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     if (d->dpt_map_bias)

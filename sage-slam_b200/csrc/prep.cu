@@ -205,3 +205,117 @@ void launch_presample(const float *fg0, const float *bias0, const float *basis0,
 }
 
 } // namespace sage
+
+// ------------------------------------------------------------------------------------------------
+// Per-keyframe input builder: what Mapper::BuildFrame does with torch ops
+// (core/mapping/mapper.cpp:1385-1426 GenerateGaussianPyramidWithGrad, mapping_utils.h:236-252 ComputeSpatialGrad,
+// mapping_utils.cpp:321-342 GenerateMaskPyramid), fused with the channel-last re-layout: the feature net's [F,H,W]
+// output goes straight into fg [SP][3][F] (feature | d/dx | d/dy) without the intermediate [F,SP] / [2,F,SP] tensors.
+// ------------------------------------------------------------------------------------------------
+namespace sage
+{
+
+// nearest-neighbour halving of the mask: F.interpolate(mode=nearest) picks src = floor(dst * in/out)
+__global__ void mask_down_kernel(const float *__restrict__ in, float *__restrict__ out, int Hi, int Wi, int Ho, int Wo)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo)
+    return;
+  const int y = p / Wo, x = p - y * Wo;
+  const int sy = min((int)floorf((float)y * ((float)Hi / (float)Ho)), Hi - 1);
+  const int sx = min((int)floorf((float)x * ((float)Wi / (float)Wo)), Wi - 1);
+  out[p] = in[sy * Wi + sx];
+}
+
+// level 0: fg[p][0][c] = feat[c][p]  (tiled transpose), F <= 32
+__global__ void pyr_level0_kernel(const float *__restrict__ feat, float *__restrict__ fg, int HW, int F)
+{
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+  {
+    const int p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && j < F) ? feat[(size_t)j * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+  {
+    const int p = p0 + j, c = threadIdx.x;
+    if (p < HW && c < F)
+      fg[(size_t)p * 3 * F + c] = tile[c][j];
+  }
+}
+
+// level l from level l-1: 3x3 [1 2 1]^2/16, stride 2, zero padding 1, of (feat * mask) normalised by the same
+// convolution of the mask (+1e-8).  One thread per (output pixel, channel).
+__global__ void pyr_down_kernel(const float *__restrict__ fg_in, const float *__restrict__ mask_in, float *__restrict__ fg_out, int Hi, int Wi,
+                                int Ho, int Wo, int F)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = t % F, p = t / F;
+  if (p >= Ho * Wo)
+    return;
+  const int y = p / Wo, x = p - y * Wo;
+  float acc = 0.f, macc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+    {
+      const int yy = 2 * y - 1 + a, xx = 2 * x - 1 + b;
+      if (yy >= 0 && yy < Hi && xx >= 0 && xx < Wi)
+      {
+        const float k = (a == 1 ? 2.f : 1.f) * (b == 1 ? 2.f : 1.f) * 0.0625f;
+        const float m = mask_in[yy * Wi + xx];
+        acc += k * (fg_in[(size_t)(yy * Wi + xx) * 3 * F + c] * m);
+        macc += k * m;
+      }
+    }
+  fg_out[(size_t)p * 3 * F + c] = acc / (macc + 1.0e-8f);
+}
+
+// central differences with replicate padding of the feature plane -> d/dx, d/dy planes of the same level
+__global__ void pyr_grad_kernel(float *__restrict__ fg, int H, int W, int F)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = t % F, p = t / F;
+  if (p >= H * W)
+    return;
+  const int y = p / W, x = p - y * W;
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  const size_t s = (size_t)3 * F;
+  fg[(size_t)p * s + F + c] = 0.5f * (fg[(size_t)(y * W + xp) * s + c] - fg[(size_t)(y * W + xm) * s + c]);
+  fg[(size_t)p * s + 2 * F + c] = 0.5f * (fg[(size_t)(yp * W + x) * s + c] - fg[(size_t)(ym * W + x) * s + c]);
+}
+
+// feat [F][H*W] (device), mask0 [H*W] (device) -> fg [SP][3][F]; mask_scratch: >= H*W floats. Returns launches.
+int launch_build_pyramid(const float *feat, const float *mask0, float *fg, float *mask_scratch, const CamPyr &cam, int F, cudaStream_t stream)
+{
+  int launches = 0;
+  const int HW0 = cam.w[0] * cam.h[0];
+  pyr_level0_kernel<<<(HW0 + 31) / 32, dim3(32, 8), 0, stream>>>(feat, fg, HW0, F);
+  pyr_grad_kernel<<<(HW0 * F + 255) / 256, 256, 0, stream>>>(fg, cam.h[0], cam.w[0], F);
+  launches += 2;
+  const float *mprev = mask0;
+  // the mask of level l-1 lives in mask_scratch after the first step: ping-pong between its two halves
+  float *mbuf[2] = {mask_scratch, mask_scratch + HW0 / 2 + 64};
+  for (int l = 1; l < cam.L; ++l)
+  {
+    const int Hi = cam.h[l - 1], Wi = cam.w[l - 1], Ho = cam.h[l], Wo = cam.w[l];
+    float *fin = fg + (size_t)cam.off[l - 1] * 3 * F, *fout = fg + (size_t)cam.off[l] * 3 * F;
+    pyr_down_kernel<<<(Ho * Wo * F + 255) / 256, 256, 0, stream>>>(fin, mprev, fout, Hi, Wi, Ho, Wo, F);
+    pyr_grad_kernel<<<(Ho * Wo * F + 255) / 256, 256, 0, stream>>>(fout, Ho, Wo, F);
+    launches += 2;
+    if (l + 1 < cam.L)
+    {
+      float *mnext = mbuf[l & 1];
+      mask_down_kernel<<<(Ho * Wo + 255) / 256, 256, 0, stream>>>(mprev, mnext, Hi, Wi, Ho, Wo);
+      ++launches;
+      mprev = mnext;
+    }
+  }
+  return launches;
+}
+
+} // namespace sage

@@ -392,6 +392,10 @@ struct sage_ba_problem
   PinBuf<double> hcost;
   PinBuf<int> hinfo;
   int potrf_lwork = 0;
+  int bandwidth = 0;       // max |i - j| over the factors' keyframe pairs
+  int solver = 0;          // 0: auto, 1: dense Schur + cuSOLVER, 2: block-banded Cholesky
+  bool use_banded = false; // decided at build time
+  DevBuf<double> band;
   int slices_photo = 32, slices_geo = 32;
 
   sage_ba_allreduce_fn allreduce = nullptr;
@@ -522,6 +526,16 @@ static void problem_build(sage_ba_problem *p)
     p->fixed_h.assign(p->dim(), 0);
   up(p->fixed_d, p->fixed_h);
 
+  p->bandwidth = 0;
+  for (const FactorMeta &m : p->metas)
+    p->bandwidth = std::max(p->bandwidth, std::abs(m.i - m.j));
+  // block-banded Cholesky pays off for chain-shaped graphs; dense Schur + cuSOLVER is the general path
+  const bool banded_ok = p->bandwidth <= 7 && banded_smem_bytes(C, p->bandwidth) <= 200 * 1024 &&
+                         (size_t)K * (p->bandwidth + 1) * (p->bandwidth + 1) <= 4096;
+  p->use_banded = p->solver == 2 ? banded_ok : (p->solver == 1 ? false : banded_ok);
+  SAGE_CHECK(p->solver != 2 || banded_ok, "banded solver requested but the covisibility graph is not narrow-banded");
+  if (p->use_banded)
+    p->band.ensure(banded_workspace_doubles(K, C, p->bandwidth));
   const int n = p->dim();
   p->fbuf.ensure(std::max<size_t>(p->fbuf_count, 4));
   p->cbuf.ensure(std::max<size_t>(p->metas.size() * 2, 4));
@@ -845,6 +859,15 @@ int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale)
   SAGE_PCATCH
 }
 
+int sage_ba_problem_set_solver(sage_ba_problem *p, int solver)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(solver >= 0 && solver <= 2, "solver must be 0 (auto), 1 (dense Schur) or 2 (block-banded)");
+  p->solver = solver;
+  SAGE_PCATCH
+}
+
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world)
 {
   SAGE_PTRY(p)
@@ -973,6 +996,28 @@ int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta)
   damp_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, p->Hd.p, p->gd.p, n, damp);
   ctx__->launches++;
   double *Hd = p->Hd.p, *gd = p->gd.p, *dl = p->delta.p;
+  if (p->use_banded)
+  {
+    SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
+    SAGE_CHECK(launch_banded_solve(Hd, gd, p->band.p, dl, p->info.p, n, p->K, p->C, p->bandwidth, s) == 0, "banded solver launch failed");
+    retract_kernel<<<(p->K + 63) / 64, 64, 0, s>>>(p->state[0][0].p, p->state[0][1].p, p->state[0][2].p, dl, p->state[1][0].p,
+                                                   p->state[1][1].p, p->state[1][2].p, p->K, p->C);
+    ctx__->launches += 2;
+    SAGE_CUDA(cudaGetLastError());
+    if (ps.b)
+    {
+      cudaEventRecord(ps.b, s);
+      ps.b = nullptr;
+    }
+    if (delta)
+    {
+      SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+      SAGE_CUDA(cudaMemcpyAsync(p->hinfo.p, p->info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+      SAGE_CUDA(cudaStreamSynchronize(s));
+      SAGE_CHECK(p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0, "normal equations are not positive definite");
+    }
+    return 0;
+  }
   // H is symmetric, so the row-major buffer is also a valid column-major matrix (lda = n).
   double *A = Hd;                        // pose block            [np x np]
   double *Bt = Hd + np;                  // rows np.., cols 0..np  [nc x np]  (= H_cp)

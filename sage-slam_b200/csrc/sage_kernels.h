@@ -33,4 +33,10 @@ void launch_depth_maps(const float *bias, const float *basis, const float *code_
 void launch_presample(const float *fg0, const float *bias0, const float *basis0, const int *loc1d, const float4 *homo,
                       const float *code_dev, float scale0, const CamPyr &cam, int F, int C, int N, float *out_dpts, float *out_homo,
                       float *out_feats, cudaStream_t stream);
+// banded.cu
+size_t banded_smem_bytes(int C, int b);
+size_t banded_workspace_doubles(int K, int C, int b);
+int launch_banded_solve(const double *Hd, const double *gd, double *band, double *delta, int *info, int n, int K, int C, int b,
+                        cudaStream_t stream);
+int launch_build_pyramid(const float *feat, const float *mask0, float *fg, float *mask_scratch, const CamPyr &cam, int F, cudaStream_t stream);
 } // namespace sage

@@ -98,7 +98,7 @@ class LocalBA:
     """Batched LM over K keyframes and a list of factors; Mapper::MappingStep's role (mapper.cpp:469-612)
     without ISAM2.  State = (pose_wk [K] as (R,t), code [K,C], dpt_scale [K])."""
 
-    def __init__(self, ctx: Context, keyframes, rank=0, world=1):
+    def __init__(self, ctx: Context, keyframes, rank=0, world=1, solver="auto"):
         self.ctx = ctx
         self.kfs = list(keyframes)
         self.K = len(self.kfs)
@@ -110,6 +110,7 @@ class LocalBA:
         self.h = h
         self.rank, self.world = rank, world
         ctx.check(ctx.lib.sage_ba_problem_set_shard(self.h, rank, world))
+        ctx.check(ctx.lib.sage_ba_problem_set_solver(self.h, {"auto": 0, "schur": 1, "banded": 2}[solver]))
         self.factors = []
         self._cb = None
         self._views = {}

@@ -65,7 +65,9 @@ class Context:
 class DeviceKeyframe:
     """Device-resident, re-laid-out copy of a Keyframe (sage_ba_keyframe)."""
 
-    def __init__(self, ctx: Context, kf: Keyframe, with_depth=True):
+    def __init__(self, ctx: Context, kf: Keyframe, with_depth=True, build_pyramid_on_device=False):
+        """build_pyramid_on_device: hand over only the level-0 feature map [F,H,W] (the feature net's output) and let
+        the library build the masked Gaussian pyramid + gradients (Mapper::GenerateGaussianPyramidWithGrad)."""
         self.ctx, self.kf = ctx, kf
         H, W = kf.video_mask.shape
         cam = kf.camera_pyramid[0]
@@ -82,8 +84,11 @@ class DeviceKeyframe:
             self._keep.append(a)
             return a.ctypes.data_as(C.c_void_p)
 
-        d.feat_map_pyramid = hold(kf.feat_map_pyramid)
-        d.feat_map_grad_pyramid = hold(kf.feat_map_grad_pyramid) if kf.feat_map_grad_pyramid is not None else None
+        if build_pyramid_on_device:
+            d.feat_map = hold(kf.feat_map_pyramid[:, :H * W])
+        else:
+            d.feat_map_pyramid = hold(kf.feat_map_pyramid)
+            d.feat_map_grad_pyramid = hold(kf.feat_map_grad_pyramid) if kf.feat_map_grad_pyramid is not None else None
         d.video_mask = hold(kf.video_mask)
         if with_depth:
             d.dpt_map_bias = hold(kf.dpt_map_bias)

@@ -67,3 +67,23 @@ def test_presample_matches_grid_sample(sage_ctx, name):
     mine = sage_run.run_sage(sage_ctx, kfs)
     assert helpers.rel_err(mine["presample_feats"], mine["ref_sfeat0"]) <= 1e-5
     assert helpers.rel_err(mine["presample_dpts"], mine["ref_dpts0"]) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["native_c16_f16", "small_c32_f32"])
+def test_device_pyramid_builder_matches_host_builder(sage_ctx, name):
+    """Row a10/f1: the on-device masked Gaussian pyramid + gradients (csrc/prep.cu) gives the same factor outputs as
+    keyframes whose pyramids were built by the host restatement of Mapper::GenerateGaussianPyramidWithGrad."""
+    import sage_slam_b200 as sage
+    from sage_slam_b200 import ops
+
+    kfs = helpers.build_case(name)
+    a = helpers.case_args(kfs)
+    outs = []
+    for dev_build in (False, True):
+        d0 = sage.DeviceKeyframe(sage_ctx, kfs[0], build_pyramid_on_device=dev_build)
+        d1 = sage.DeviceKeyframe(sage_ctx, kfs[1], build_pyramid_on_device=dev_build)
+        outs.append(ops.photometric_jac_error_calculate(sage_ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"],
+                                                        a["code0"], a["scale0"], a["eps"], a["weights"]))
+    (A0, b0, e0, n0), (A1, b1, e1, n1) = outs
+    assert n0 == n1 and helpers.rel_err(A1, A0) <= 1e-5 and helpers.rel_err(b1, b0) <= 1e-5 and abs(e1 - e0) <= 1e-5 * e0

@@ -10,9 +10,9 @@ import sage_slam_b200 as sage
 from sage_slam_b200 import local_ba
 
 
-def make_ba(ctx, kfs, pairs, rank=0, world=1):
+def make_ba(ctx, kfs, pairs, rank=0, world=1, solver="auto"):
     dk = [sage.DeviceKeyframe(ctx, k) for k in kfs]
-    ba = sage.LocalBA(ctx, dk, rank=rank, world=world)
+    ba = sage.LocalBA(ctx, dk, rank=rank, world=world, solver=solver)
     for i, j in pairs:
         ba.add_photometric(i, j, helpers.PHOTO_WEIGHTS[:pc.PRM["L"]])
     for i, j in pairs:
@@ -202,3 +202,20 @@ def test_ragged_sample_counts_and_random_subsets(sage_ctx):
                                                    a["code0"], a["dpt1"], a["dgrad1"], a["basis1"], a["mask1"], a["loc1d"], a["homo"],
                                                    a["scale0"], a["scale1"], a["cam"], a["eps"], a["geo_loss"], a["geo_weight"])
         assert gn == gno and helpers.rel_err(G, Go) <= 1e-4 and helpers.rel_err(gb, gbo) <= 1e-4 and abs(ge - geo_) <= 1e-4 * max(geo_, 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num_kf", [2, 6])
+def test_banded_cholesky_equals_dense_schur(sage_ctx, num_kf):
+    """The block-banded Cholesky (one launch, chain-shaped covisibility) and the dense Schur-complement + cuSOLVER path
+    solve the same damped system: identical steps to fp64 round-off, for several damping values."""
+    kfs, pairs, _ = pc.build(num_kf)
+    sols = {}
+    for solver in ("schur", "banded"):
+        ba, _ = make_ba(sage_ctx, kfs, pairs, solver=solver)
+        ba.linearize()
+        ba.assemble()
+        sols[solver] = [ba.solve(d, want_delta=True) for d in (1e-4, 1e-2, 1.0)]
+    for a, b in zip(sols["schur"], sols["banded"]):
+        assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(a).max())
+        assert np.abs(a).max() > 0
