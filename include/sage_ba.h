@@ -226,7 +226,7 @@ int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale
 /* hold a keyframe's pose (and optionally scale) fixed: the gauge anchor (mapper.cpp:190-192) */
 int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale);
 /* linear solver: 0 auto, 1 dense Schur complement onto the pose block (cuSOLVER), 2 block-banded Cholesky over keyframes
- * (chain-shaped covisibility only).  Auto picks 2 when the keyframe bandwidth is <= 7. */
+ * (chain-shaped covisibility only; one launch, but slower than 1 on a B200 at K = 32 -- opt-in).  Auto = 1. */
 int sage_ba_problem_set_solver(sage_ba_problem *p, int solver);
 /* restrict this process to the factors with index % world == rank (multi-GPU sharding) */
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);

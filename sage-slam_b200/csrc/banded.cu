@@ -106,25 +106,40 @@ banded_solve_kernel(const double *__restrict__ Hd, const double *__restrict__ gd
         const int o = 1 + e / (S * S), r = (e % (S * S)) / S, c = e % S;
         band[(size_t)((k + o) * (b + 1) + o) * BS + (size_t)r * S + c] = Lc[(size_t)(o - 1) * S * SP1 + r * SP1 + c];
       }
-      // A_ij -= L_ik L_jk^T for k < j <= i <= k + nb
+      // A_ij -= L_ik L_jk^T for k < j <= i <= k + nb, 3x3 register tiles (S = 39 = 13 * 3; generic tail handled by bounds)
       const int npair = nb * (nb + 1) / 2;
-      for (int e = tid; e < npair * S * S; e += nt)
+      const int TS = (S + 2) / 3;
+      for (int e = tid; e < npair * TS * TS; e += nt)
       {
-        int pr = e / (S * S);
-        const int r = (e % (S * S)) / S, c = e % S;
-        int oi = 1, oj = 1; // pair index -> (oi >= oj)
+        int pr = e / (TS * TS);
+        const int r0 = ((e % (TS * TS)) / TS) * 3, c0 = (e % TS) * 3;
+        int oi = 1; // pair index -> (oi >= oj)
         while (pr >= oi)
         {
           pr -= oi;
           ++oi;
         }
-        oj = pr + 1;
-        const double *Li = Lc + (size_t)(oi - 1) * S * SP1 + (size_t)r * SP1;
-        const double *Lj = Lc + (size_t)(oj - 1) * S * SP1 + (size_t)c * SP1;
-        double s = 0.0;
+        const int oj = pr + 1;
+        const double *Li = Lc + (size_t)(oi - 1) * S * SP1;
+        const double *Lj = Lc + (size_t)(oj - 1) * S * SP1;
+        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        const int ra = min(r0, S - 1), rb = min(r0 + 1, S - 1), rc = min(r0 + 2, S - 1);
+        const int ca = min(c0, S - 1), cb = min(c0 + 1, S - 1), cc = min(c0 + 2, S - 1);
         for (int q = 0; q < S; ++q)
-          s += Li[q] * Lj[q];
-        band[(size_t)((k + oi) * (b + 1) + (oi - oj)) * BS + (size_t)r * S + c] -= s;
+        {
+          const double a0 = Li[ra * SP1 + q], a1 = Li[rb * SP1 + q], a2 = Li[rc * SP1 + q];
+          const double b0 = Lj[ca * SP1 + q], b1 = Lj[cb * SP1 + q], b2 = Lj[cc * SP1 + q];
+          acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+          acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+          acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+        }
+        double *dstb = band + (size_t)((k + oi) * (b + 1) + (oi - oj)) * BS;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (r0 + i < S && c0 + j < S)
+              dstb[(size_t)(r0 + i) * S + c0 + j] -= acc[i][j];
       }
     }
     __syncthreads();
@@ -142,29 +157,43 @@ banded_solve_kernel(const double *__restrict__ Hd, const double *__restrict__ gd
     *info = 0;
 
   // ---- forward substitution  L y = g  (y overwrites delta, block by block) ----
+  // Off-diagonal contributions: one thread per (row, previous block) partial dot product, summed through shared memory;
+  // the S x S triangular solve runs column by column on one warp with the diagonal factor staged in shared memory.
+  double *part = Lc; // [b][S] partial sums (Lc is free now)
   for (int k = 0; k < K; ++k)
   {
+    const int nb = min(b, k);
+    for (int e = tid; e < S * S; e += nt)
+      Lkk[(e / S) * SP1 + e % S] = band[(size_t)(k * (b + 1)) * BS + e];
+    for (int e = tid; e < nb * S; e += nt)
+    {
+      const int o = 1 + e / S, r = e % S;
+      const double *Lb = band + (size_t)(k * (b + 1) + o) * BS + (size_t)r * S; // block (k, k-o), row r
+      double s = 0.0;
+      for (int q = 0; q < S; ++q)
+        s += Lb[q] * delta[band_var(k - o, q, K, C)];
+      part[(o - 1) * S + r] = s;
+    }
+    __syncthreads();
     for (int r = tid; r < S; r += nt)
     {
       double s = gd[band_var(k, r, K, C)];
-      for (int o = 1; o <= min(b, k); ++o)
-      {
-        const double *Lb = band + (size_t)(k * (b + 1) + o) * BS + (size_t)r * S; // block (k, k-o), row r
-        for (int q = 0; q < S; ++q)
-          s -= Lb[q] * delta[band_var(k - o, q, K, C)];
-      }
+      for (int o = 0; o < nb; ++o)
+        s -= part[o * S + r];
       vec[r] = s;
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid < 32)
     {
-      const double *Lb = band + (size_t)(k * (b + 1)) * BS;
-      for (int r = 0; r < S; ++r)
+      for (int c = 0; c < S; ++c)
       {
-        double s = vec[r];
-        for (int q = 0; q < r; ++q)
-          s -= Lb[(size_t)r * S + q] * vec[q];
-        vec[r] = s / Lb[(size_t)r * S + r];
+        const double xc = vec[c] / Lkk[c * SP1 + c];
+        __syncwarp();
+        for (int r = c + 1 + tid; r < S; r += 32)
+          vec[r] -= Lkk[r * SP1 + c] * xc;
+        if (tid == 0)
+          vec[c] = xc;
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -175,27 +204,38 @@ banded_solve_kernel(const double *__restrict__ Hd, const double *__restrict__ gd
   // ---- backward substitution  L^T x = y ----
   for (int k = K - 1; k >= 0; --k)
   {
+    const int nb = min(b, K - 1 - k);
+    for (int e = tid; e < S * S; e += nt)
+      Lkk[(e / S) * SP1 + e % S] = band[(size_t)(k * (b + 1)) * BS + e];
+    for (int e = tid; e < nb * S; e += nt)
+    {
+      const int o = 1 + e / S, r = e % S;
+      const double *Lb = band + (size_t)((k + o) * (b + 1) + o) * BS; // block (k+o, k): use its transpose
+      double s = 0.0;
+      for (int q = 0; q < S; ++q)
+        s += Lb[(size_t)q * S + r] * delta[band_var(k + o, q, K, C)];
+      part[(o - 1) * S + r] = s;
+    }
+    __syncthreads();
     for (int r = tid; r < S; r += nt)
     {
       double s = delta[band_var(k, r, K, C)];
-      for (int o = 1; o <= min(b, K - 1 - k); ++o)
-      {
-        const double *Lb = band + (size_t)((k + o) * (b + 1) + o) * BS; // block (k+o, k): use its transpose
-        for (int q = 0; q < S; ++q)
-          s -= Lb[(size_t)q * S + r] * delta[band_var(k + o, q, K, C)];
-      }
+      for (int o = 0; o < nb; ++o)
+        s -= part[o * S + r];
       vec[r] = s;
     }
     __syncthreads();
-    if (tid == 0)
+    if (tid < 32)
     {
-      const double *Lb = band + (size_t)(k * (b + 1)) * BS;
-      for (int r = S - 1; r >= 0; --r)
+      for (int c = S - 1; c >= 0; --c)
       {
-        double s = vec[r];
-        for (int q = r + 1; q < S; ++q)
-          s -= Lb[(size_t)q * S + r] * vec[q];
-        vec[r] = s / Lb[(size_t)r * S + r];
+        const double xc = vec[c] / Lkk[c * SP1 + c];
+        __syncwarp();
+        for (int r = tid; r < c; r += 32)
+          vec[r] -= Lkk[c * SP1 + r] * xc; // (L^T)[r][c] = L[c][r]
+        if (tid == 0)
+          vec[c] = xc;
+        __syncwarp();
       }
     }
     __syncthreads();
