@@ -174,6 +174,19 @@ int sage_ba_tracker_reproj_error(sage_ba_context *ctx, const sage_ba_camera *cam
                                  const float *dpts, const float *homo, const float *match2d, int num_matches,
                                  float eps, float loss_param, float weight, float *error, float *n_inliers);
 
+/* df::tracker_match_geom_jac_error_calculate (cuda/match_geometry_factor_kernels.cpp:1385-1421), ..._with_scale
+ * (:1423-1459) and tracker_match_geom_error_calculate (:1361-1383): 3-D point-to-point term between matched keypoints,
+ * Fair loss per axis, normalised by the number of matches.  All arrays are HOST arrays; sampled_dpts_0 is the (scaled)
+ * depth exactly as the reference passes it.  with_scale != 0 -> 7x7 system (scale_0 column). */
+int sage_ba_tracker_match_geom_jac_error(sage_ba_context *ctx, const float *R, const float *t, const float *sampled_dpts_0,
+                                         const float *matched_dpts_1, const float *sampled_locations_homo_0,
+                                         const float *matched_locations_homo_1, int num_matches, int with_scale, float scale0,
+                                         float loss_param, float weight, float *AtA, float *Atb, float *error);
+int sage_ba_tracker_match_geom_error(sage_ba_context *ctx, const float *R, const float *t, const float *sampled_dpts_0,
+                                     const float *matched_dpts_1, const float *sampled_locations_homo_0,
+                                     const float *matched_locations_homo_1, int num_matches, float loss_param, float weight,
+                                     float *error);
+
 /* ------------------------------------------------------------------------------------------
  * CameraTracker::TrackNewFrame LM loop (core/system/camera_tracker.cpp:1034-1310, loop
  * :1156-1279): damped Gauss-Newton on the 6-DoF relative pose T_ck of `frame1` w.r.t. `kf0`,
@@ -190,6 +203,8 @@ typedef struct sage_ba_tracker_config
   float photo_weights[SAGE_BA_MAX_LEVELS];
   int use_photo, use_reproj;
   float reproj_loss_param, reproj_weight; /* loss param and inlier_multiplier*factor weight */
+  int use_match_geom;                     /* TrackFrame (7-DoF) only */
+  float match_geom_loss_param, match_geom_weight;
 } sage_ba_tracker_config;
 
 typedef struct sage_ba_tracker_report
@@ -204,6 +219,16 @@ int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyframe *kf0, c
                             const float *code0, float scale0, const sage_ba_tracker_config *cfg, float *R, float *t,
                             const float *match_dpts, const float *match_homo, const float *match2d, int num_matches,
                             sage_ba_tracker_report *report);
+
+/* CameraTracker::TrackFrame (core/system/camera_tracker.cpp:1312-1672, loop :1479-1630): 7-DoF LM on the relative pose AND
+ * the depth scale of `frame0` (the frame being tracked, sampled at its own points) against the reference keyframe `kf1`;
+ * photometric term with the scale column + optional match-geometry term.  R, t, scale: in = initial guess, out = estimate.
+ * match arrays (HOST): unscaled keypoint depths of frame0 [M], their rays [M,3], matched depths / rays in kf1.
+ * Returns 0 on success; 2 when the photometric term reports no overlap and no match-geometry term is enabled (:1500-1504). */
+int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe *frame0, const sage_ba_keyframe *kf1, const float *code0,
+                        const sage_ba_tracker_config *cfg, float *R, float *t, float *scale, const float *match_unscaled_dpts_0,
+                        const float *match_homo_0, const float *match_dpts_1, const float *match_homo_1, int num_matches,
+                        sage_ba_tracker_report *report);
 
 /* ------------------------------------------------------------------------------------------
  * Batched local bundle adjustment (new; the reference delegates this to GTSAM ISAM2,

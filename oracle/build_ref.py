@@ -1,7 +1,7 @@
 """Compile the reference's OWN factor kernels into oracle/_ref/ (TEST INFRASTRUCTURE).
 
-The three hot-path translation units of the reference
-(/root/reference/system/sources/cuda/{photometric,geometric,reprojection}_factor_kernels.cpp)
+The four kernel translation units of the reference
+(/root/reference/system/sources/cuda/{photometric,geometric,reprojection,match_geometry}_factor_kernels.cpp)
 are compiled where they lie, UNMODIFIED, as CUDA for sm_100a against this image's libtorch,
 plus our pybind front (oracle/ref_ext.cpp).  Two shims make that possible without editing
 them: ref_shims/sage_ref_compat.h (force-included; re-adds the ::detail::scalar_type
@@ -24,7 +24,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/system"
 OUT = os.path.join(HERE, "_ref")
 CONFIGS = [(8, 16), (16, 16), (32, 32)]
-SOURCES = ["photometric_factor_kernels.cpp", "geometric_factor_kernels.cpp", "reprojection_factor_kernels.cpp"]
+SOURCES = ["photometric_factor_kernels.cpp", "geometric_factor_kernels.cpp", "reprojection_factor_kernels.cpp",
+           "match_geometry_factor_kernels.cpp"]
 
 
 def available():

@@ -74,6 +74,13 @@ def run_case(name, far):
     out.update(trkrep_AtA=AtA.cpu().numpy(), trkrep_Atb=Atb.cpu().numpy().reshape(-1), trkrep_err=e)
     out["trkrep_err_only"] = mod.tracker_reproj_error(R["R10"], R["t10"], mdpts, mhomo, m2d, cam, a["eps"], a["rep_loss"],
                                                       a["rep_weight"])
+    mh1, md1 = T(ma["mhomo1"], dev), T(ma["mdpts1"], dev)
+    AtA, Atb, e = mod.tracker_match_geom_jac_error(R["R10"], R["t10"], mdpts, md1, mhomo, mh1, ma["mg_loss"], ma["mg_weight"])
+    out.update(mg_AtA=AtA.cpu().numpy(), mg_Atb=Atb.cpu().numpy().reshape(-1), mg_err=e)
+    AtA, Atb, e = mod.tracker_match_geom_jac_error_with_scale(R["R10"], R["t10"], mdpts, md1, mhomo, mh1, a["scale0"], ma["mg_loss"],
+                                                              ma["mg_weight"])
+    out.update(mgs_AtA=AtA.cpu().numpy(), mgs_Atb=Atb.cpu().numpy().reshape(-1), mgs_err=e)
+    out["mg_err_only"] = mod.tracker_match_geom_error(R["R10"], R["t10"], mdpts, md1, mhomo, mh1, ma["mg_loss"], ma["mg_weight"])
     out["cam_pyramid"] = np.array(mod.camera_pyramid(cam, L), np.float32)
     out["sig"] = np.array([float(np.abs(a["feat0"]).sum()), float(np.abs(a["jac0"]).sum()), float(a["R10"].sum()),
                            float(ta["sfeat0"].sum()), float(ma["m2d"].sum())])

@@ -245,6 +245,29 @@ def tracker_reproj_error(R, t, dpts0, homo, match2d, cam, eps, loss_param, weigh
     return e.value, n.value
 
 
+
+def tracker_match_geom_jac_error(R, t, dpts0, dpts1, homo0, homo1, loss_param, weight, scale0=None, dtype=np.float32):
+    """tracker_match_geom_jac_error_calculate (scale0 None, 6x6) or ..._with_scale (7x7); dpts0 is the SCALED depth."""
+    f = getattr(lib(), "oracle_tracker_match_geom_jac_error" + _suffix(dtype))
+    with_scale = scale0 is not None
+    D = 7 if with_scale else 6
+    A, b, e, _ = _out(D)
+    R, t, dpts0, dpts1, homo0, homo1 = [_r(x, dtype) for x in (R, t, dpts0, dpts1, homo0, homo1)]
+    f(_p(A), _p(b), ctypes.byref(e), _p(R), _p(t), _p(dpts0), _p(dpts1), _p(homo0), _p(homo1),
+      _s(scale0 if with_scale else 1.0, dtype), _s(loss_param, dtype), _s(weight, dtype), ctypes.c_int(len(dpts0)),
+      ctypes.c_int(int(with_scale)))
+    return A, b, e.value
+
+
+def tracker_match_geom_error(R, t, dpts0, dpts1, homo0, homo1, loss_param, weight, dtype=np.float32):
+    f = getattr(lib(), "oracle_tracker_match_geom_error" + _suffix(dtype))
+    e = ctypes.c_double(0)
+    R, t, dpts0, dpts1, homo0, homo1 = [_r(x, dtype) for x in (R, t, dpts0, dpts1, homo0, homo1)]
+    f(ctypes.byref(e), _p(R), _p(t), _p(dpts0), _p(dpts1), _p(homo0), _p(homo1), _s(loss_param, dtype), _s(weight, dtype),
+      ctypes.c_int(len(dpts0)))
+    return e.value
+
+
 # --------------------------------------------------------------------------------------
 # host-side restatements
 # --------------------------------------------------------------------------------------
@@ -419,6 +442,59 @@ def nearest_psd(M, reference_faithful=True):
         A3 = A3 + I * (-np.linalg.eigvalsh(A3).min() * k + 1e-15)
         k *= 2
     return A3
+
+
+def tracker_lm7(jac_fn, err_fn, R, t, scale, init_damp=1e-4, min_damp=1e-6, max_damp=1e-2, damp_dec=10.0, damp_inc=100.0,
+                max_iters=40, jac_thresh=1e-2, min_grad=1e-8, min_param_inc=1e-8):
+    """CameraTracker::TrackFrame 7-DoF LM loop (core/system/camera_tracker.cpp:1479-1630): relative pose + scale_0.
+    jac_fn(R,t,s)->(AtA 7x7, Atb 7, err), err_fn(R,t,s)->err."""
+    f = np.float32
+    R, t, scale = np.asarray(R, f), np.asarray(t, f), f(scale)
+    prev_error, curr_error = f(0), f(1)
+    damp, it = f(init_damp), 0
+    trace = []
+    cand_err = curr_error
+    while True:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = abs(curr_error - prev_error) / prev_error
+        if ratio > jac_thresh:
+            A, b, e = jac_fn(R, t, scale)
+            AtA, Atb = np.asarray(A, f), np.asarray(b, f).reshape(-1)
+            if it == 0:
+                curr_error = f(e)
+            update_jac = True
+        else:
+            update_jac = False
+        it += 1
+        diag = np.diag(np.diag(AtA))
+        sol = np.linalg.solve((AtA + damp * diag).astype(np.float64), Atb.astype(np.float64)).astype(f)
+        rotvec = rotation_to_angle_axis(R).astype(f)
+        x = np.concatenate([t.reshape(-1), rotvec, [scale]])
+        if np.abs(Atb).max() < min_grad or (sol / (np.abs(x) + f(1e-8))).max() < min_param_inc:
+            break
+        while True:
+            Rc, tc = retract(R, t, sol[:6])
+            Rc, tc, sc = Rc.astype(f), tc.astype(f), f(scale + sol[6])
+            cand_err = f(err_fn(Rc, tc, sc))
+            if cand_err < curr_error:
+                break
+            elif damp < max_damp:
+                damp = f(min(max(min_damp, damp * damp_inc), max_damp))
+                sol = np.linalg.solve((AtA + damp * diag).astype(np.float64), Atb.astype(np.float64)).astype(f)
+            else:
+                break
+        accepted = not (cand_err >= curr_error and damp >= max_damp)
+        trace.append((it, float(damp), bool(accepted), float(cand_err)))
+        if not accepted:
+            break
+        R, t, scale = Rc, tc, sc
+        if update_jac:
+            prev_error = curr_error
+        curr_error = cand_err
+        damp = f(min(max(min_damp, damp / damp_dec), max_damp))
+        if it >= max_iters:
+            break
+    return R, t, float(scale), float(curr_error), trace
 
 
 def tracker_lm(jac_fn, err_fn, R, t, init_damp=1e-4, min_damp=1e-6, max_damp=1e-2, damp_dec=10.0, damp_inc=100.0,

@@ -7,6 +7,7 @@
 #include "photometric_factor_kernels.h"
 #include "geometric_factor_kernels.h"
 #include "reprojection_factor_kernels.h"
+#include "match_geometry_factor_kernels.h"
 
 #ifndef DF_CODE_SIZE
 #error "DF_CODE_SIZE / DF_FEAT_SIZE must be defined"
@@ -152,6 +153,32 @@ double tracker_reproj_error(at::Tensor R, at::Tensor t, at::Tensor dpts0, at::Te
   return df::tracker_reproj_error_calculate(R, t, dpts0, homo, match2d, make_cam(cam), (float)eps, (float)loss_param,
                                             (float)weight);
 }
+std::tuple<at::Tensor, at::Tensor, double> tracker_match_geom_jac_error(at::Tensor R, at::Tensor t, at::Tensor dpts0, at::Tensor dpts1,
+                                                                        at::Tensor homo0, at::Tensor homo1, double loss_param,
+                                                                        double weight)
+{
+  at::Tensor AtA, Atb;
+  float err = 0;
+  df::tracker_match_geom_jac_error_calculate(AtA, Atb, err, R, t, dpts0, dpts1, homo0, homo1, (float)loss_param, (float)weight);
+  return {AtA, Atb, (double)err};
+}
+
+std::tuple<at::Tensor, at::Tensor, double> tracker_match_geom_jac_error_with_scale(at::Tensor R, at::Tensor t, at::Tensor dpts0,
+                                                                                   at::Tensor dpts1, at::Tensor homo0, at::Tensor homo1,
+                                                                                   double scale0, double loss_param, double weight)
+{
+  at::Tensor AtA, Atb;
+  float err = 0;
+  df::tracker_match_geom_jac_error_calculate_with_scale(AtA, Atb, err, R, t, dpts0, dpts1, homo0, homo1, (float)scale0,
+                                                        (float)loss_param, (float)weight);
+  return {AtA, Atb, (double)err};
+}
+
+double tracker_match_geom_error(at::Tensor R, at::Tensor t, at::Tensor dpts0, at::Tensor dpts1, at::Tensor homo0, at::Tensor homo1,
+                                double loss_param, double weight)
+{
+  return df::tracker_match_geom_error_calculate(R, t, dpts0, dpts1, homo0, homo1, (float)loss_param, (float)weight);
+}
 } // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -170,4 +197,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
   m.def("reprojection_error", &reprojection_error);
   m.def("tracker_reproj_jac_error", &tracker_reproj_jac_error);
   m.def("tracker_reproj_error", &tracker_reproj_error);
+  m.def("tracker_match_geom_jac_error", &tracker_match_geom_jac_error);
+  m.def("tracker_match_geom_jac_error_with_scale", &tracker_match_geom_jac_error_with_scale);
+  m.def("tracker_match_geom_error", &tracker_match_geom_error);
 }

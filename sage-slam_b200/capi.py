@@ -33,7 +33,8 @@ class TrackerConfig(C.Structure):
                 ("jac_update_err_inc_threshold", C.c_float), ("min_grad_thresh", C.c_float),
                 ("min_param_inc_thresh", C.c_float), ("dpt_eps", C.c_float), ("photo_weights", C.c_float * MAX_LEVELS),
                 ("use_photo", C.c_int), ("use_reproj", C.c_int), ("reproj_loss_param", C.c_float),
-                ("reproj_weight", C.c_float)]
+                ("reproj_weight", C.c_float), ("use_match_geom", C.c_int), ("match_geom_loss_param", C.c_float),
+                ("match_geom_weight", C.c_float)]
 
 
 class TrackerReport(C.Structure):
@@ -77,6 +78,10 @@ SIGNATURES = {
     "sage_ba_reprojection_error": (C.c_int, [vp, vp, vp, vp, vp, F, vp, vp, vp, C.c_int, F, F, F, vp, vp]),
     "sage_ba_tracker_reproj_jac_error": (C.c_int, [vp, C.POINTER(Camera), vp, vp, vp, vp, vp, C.c_int, F, F, F, vp, vp, vp, vp]),
     "sage_ba_tracker_reproj_error": (C.c_int, [vp, C.POINTER(Camera), vp, vp, vp, vp, vp, C.c_int, F, F, F, vp, vp]),
+    "sage_ba_tracker_match_geom_jac_error": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, F, F, F, vp, vp, vp]),
+    "sage_ba_tracker_match_geom_error": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, F, F, vp]),
+    "sage_ba_track_frame": (C.c_int, [vp, vp, vp, vp, C.POINTER(TrackerConfig), vp, vp, vp, vp, vp, vp, vp, C.c_int,
+                                      C.POINTER(TrackerReport)]),
     "sage_ba_track_new_frame": (C.c_int, [vp, vp, vp, vp, F, C.POINTER(TrackerConfig), vp, vp, vp, vp, vp, C.c_int,
                                           C.POINTER(TrackerReport)]),
     "sage_ba_problem_create": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]),

@@ -411,6 +411,7 @@ static PhotoFactor photo_trk_factor(const sage_ba_keyframe *fr1, const float *R,
   fill_pose(f.R10, f.t10, R, t);
   f.scale0 = scale0;
   f.eps = eps;
+  f.dmul = 1.f;
   memcpy(f.w, weights, sizeof(float) * fr1->L);
   return f;
 }
@@ -423,6 +424,24 @@ static const float *pack_homo_scratch(sage_ba_context *ctx, const float *homo3, 
   ctx->launches += 1;
   return h4;
 }
+
+} // extern "C"
+
+namespace sage
+{
+// tracker photometric term with an explicit depth multiplier (TrackFrame optimises the scale of the sampled depths)
+void run_tracker_photo(sage_ba_context *ctx, bool jac, const sage_ba_keyframe *frame1, const float *R, const float *t,
+                       const float *dpts_dev, const float *homo3_dev, const float *feats_dev, int N, float dmul, float scale0, float eps,
+                       const float *weights, float *AtA, float *Atb, float *error, float *n_inl)
+{
+  const float *h4 = pack_homo_scratch(ctx, homo3_dev, N);
+  PhotoFactor f = photo_trk_factor(frame1, R, t, dpts_dev, h4, feats_dev, N, scale0, eps, weights);
+  f.dmul = dmul;
+  run_photo_single(ctx, jac ? PH_TRK_JAC : PH_TRK_ERR, frame1->F, frame1->C, f, frame1->pyr, scale0 != 0.f ? 7 : 6, AtA, Atb, error, n_inl);
+}
+} // namespace sage
+
+extern "C" {
 
 int sage_ba_tracker_photo_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *frame1, const float *R, const float *t,
                                     const float *sampled_dpts_0, const float *sampled_locations_homo_0, const float *sampled_features_0,
@@ -687,3 +706,79 @@ int sage_ba_tracker_reproj_error(sage_ba_context *ctx, const sage_ba_camera *cam
 }
 
 } // extern "C"
+
+// tracker match-geometry ----------------------------------------------------------------------------
+namespace sage
+{
+void run_match_geom_single(sage_ba_context *ctx, bool jac, const float *R, const float *t, const float *dpts0, const float *dpts1,
+                           const float *homo0, const float *homo1, int M, float dmul, float scale0, float loss_param, float weight,
+                           float *AtA, float *Atb, float *error)
+{
+  SAGE_CHECK(M >= 0 && M <= 4096, "num_matches out of range");
+  cudaStream_t s = ctx->stream;
+  const int D = scale0 != 0.f ? 7 : 6;
+  float *dm = ctx->trk_m_homo.ensure((size_t)std::max(M, 1) * 8);
+  float *hm = ctx->hout.ensure(std::max<size_t>((size_t)M * 8, (size_t)D * D + D + 2));
+  memcpy(hm, homo0, sizeof(float) * 3 * M);
+  memcpy(hm + 3 * M, homo1, sizeof(float) * 3 * M);
+  memcpy(hm + 6 * M, dpts0, sizeof(float) * M);
+  memcpy(hm + 7 * M, dpts1, sizeof(float) * M);
+  SAGE_CUDA(cudaMemcpyAsync(dm, hm, sizeof(float) * 8 * M, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  MatchGeomFactor f;
+  memset(&f, 0, sizeof(f));
+  f.homo0 = dm;
+  f.homo1 = dm + 3 * M;
+  f.dpts0 = dm + 6 * M;
+  f.dpts1 = dm + 7 * M;
+  f.M = M;
+  memcpy(f.R, R, 9 * sizeof(float));
+  memcpy(f.t, t, 3 * sizeof(float));
+  f.dmul = dmul;
+  f.scale0 = scale0;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
+  float *out = ctx->out.ensure(nout);
+  MatchGeomFactor *df = reinterpret_cast<MatchGeomFactor *>(ctx->factor.ensure(1024));
+  MatchGeomFactor *hf = reinterpret_cast<MatchGeomFactor *>(ctx->hfactor.ensure(1024));
+  *hf = f;
+  SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(MatchGeomFactor), cudaMemcpyHostToDevice, s));
+  launch_match_geom(jac, df, 1, out, 1, D, s);
+  ctx->launches += 1;
+  SAGE_CUDA(cudaGetLastError());
+  SAGE_CUDA(cudaMemcpyAsync(hm, out, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  if (jac)
+  {
+    memcpy(AtA, hm, sizeof(float) * D * D);
+    memcpy(Atb, hm + D * D, sizeof(float) * D);
+  }
+  *error = hm[nout - 2];
+}
+} // namespace sage
+
+extern "C" int sage_ba_tracker_match_geom_jac_error(sage_ba_context *ctx, const float *R, const float *t, const float *sampled_dpts_0,
+                                                    const float *matched_dpts_1, const float *sampled_locations_homo_0,
+                                                    const float *matched_locations_homo_1, int num_matches, int with_scale,
+                                                    float scale0, float loss_param, float weight, float *AtA, float *Atb, float *error)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(!with_scale || scale0 != 0.f, "scale0 must be non-zero");
+  run_match_geom_single(ctx, true, R, t, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0, matched_locations_homo_1, num_matches,
+                        1.f, with_scale ? scale0 : 0.f, loss_param, weight, AtA, Atb, error);
+  SAGE_CATCH
+}
+
+extern "C" int sage_ba_tracker_match_geom_error(sage_ba_context *ctx, const float *R, const float *t, const float *sampled_dpts_0,
+                                                const float *matched_dpts_1, const float *sampled_locations_homo_0,
+                                                const float *matched_locations_homo_1, int num_matches, float loss_param, float weight,
+                                                float *error)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  run_match_geom_single(ctx, false, R, t, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0, matched_locations_homo_1, num_matches,
+                        1.f, 0.f, loss_param, weight, nullptr, nullptr, error);
+  SAGE_CATCH
+}

@@ -196,7 +196,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       d0 = fs.scale0 * (__ldg(fs.bias0 + idx) + mydot);
     }
     else
-      d0 = __ldg(fs.dpts0 + nc);
+      d0 = fs.dmul * __ldg(fs.dpts0 + nc);
     const float rx = fs.R10[0] * hx + fs.R10[1] * hy + fs.R10[2] * hz;
     const float ry = fs.R10[3] * hx + fs.R10[4] * hy + fs.R10[5] * hz;
     const float rz = fs.R10[6] * hx + fs.R10[7] * hy + fs.R10[8] * hz;

@@ -184,6 +184,115 @@ reproj_kernel(const ReprojFactor *__restrict__ factors, float *__restrict__ out,
   }
 }
 
+
+// tracker match-geometry: 3 rows per match [pose 6 | scale | rhs], normalised by the number of matches (torch::mean,
+// K/match_geometry_factor_kernels.cpp:1380, :1405-1418); one CTA, M <= 4096.
+template <bool JAC>
+__global__ void __launch_bounds__(SAGE_CTA)
+match_geom_kernel(const MatchGeomFactor *__restrict__ factors, float *__restrict__ out, int out_stride, int D)
+{
+  constexpr int WP = 8, STEP = 64;
+  __shared__ __align__(16) float Y[JAC ? 3 * STEP * WP : 4];
+  __shared__ __align__(16) float Hs[JAC ? WP * WP : 4];
+  __shared__ MatchGeomFactor fs;
+  __shared__ float red[32];
+  __shared__ float s_e;
+  {
+    const int *src = reinterpret_cast<const int *>(factors + blockIdx.x);
+    int *dst = reinterpret_cast<int *>(&fs);
+    for (int i = threadIdx.x; i < (int)(sizeof(MatchGeomFactor) / 4); i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads();
+  const int M = fs.M;
+  Syrk<WP> syrk;
+  if constexpr (JAC)
+    syrk.init();
+  float err_acc = 0.f;
+  const float sq = sqrtf(fs.loss_param);
+  for (int base = 0; base < M; base += STEP)
+  {
+    const int tI = threadIdx.x;
+    if (tI < STEP)
+    {
+      const int m = base + tI;
+      float *rows = Y + (size_t)(3 * tI) * WP;
+      if (m < M)
+      {
+        const float hx = fs.homo0[m * 3 + 0], hy = fs.homo0[m * 3 + 1], hz = fs.homo0[m * 3 + 2];
+        const float d0 = fs.dmul * fs.dpts0[m], d1 = fs.dpts1[m];
+        const float r[3] = {fs.R[0] * hx + fs.R[1] * hy + fs.R[2] * hz, fs.R[3] * hx + fs.R[4] * hy + fs.R[5] * hz,
+                            fs.R[6] * hx + fs.R[7] * hy + fs.R[8] * hz};
+        const float p[3] = {d0 * r[0] + fs.t[0], d0 * r[1] + fs.t[1], d0 * r[2] + fs.t[2]};
+        const float Jp[3][6] = {{1.f, 0.f, 0.f, 0.f, p[2], -p[1]}, {0.f, 1.f, 0.f, -p[2], 0.f, p[0]}, {0.f, 0.f, 1.f, p[1], -p[0], 0.f}};
+        float e = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+          const float diff = d1 * fs.homo1[m * 3 + i] - p[i];
+          const float nrm = fabsf(diff) / sq;
+          e += nrm - logf(1.0f + nrm);
+          if constexpr (JAC)
+          {
+            const float w = sqrtf(1.0f / (fs.loss_param * (1.0f + nrm)));
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+              rows[i * WP + j] = w * Jp[i][j];
+            rows[i * WP + 6] = fs.scale0 != 0.f ? w * (r[i] * d0 / fs.scale0) : 0.f;
+            rows[i * WP + 7] = w * diff;
+          }
+        }
+        err_acc += 2.0f * e;
+      }
+      else if constexpr (JAC)
+      {
+        for (int k = 0; k < 3 * WP; ++k)
+          rows[k] = 0.f;
+      }
+    }
+    if constexpr (JAC)
+    {
+      __syncthreads();
+      syrk.accumulate(Y, 3 * STEP);
+      __syncthreads();
+    }
+  }
+  if constexpr (JAC)
+    syrk.store(Y, Hs);
+  const float es = block_sum(err_acc, red);
+  if (threadIdx.x == 0)
+    s_e = M > 0 ? fs.weight * es / (float)M : 0.f;
+  __syncthreads();
+  float *o = out + (size_t)fs.out * out_stride;
+  const int eb = JAC ? D * D + D : 0;
+  if (threadIdx.x == 0)
+  {
+    o[eb] = s_e;
+    o[eb + 1] = (float)M;
+  }
+  if constexpr (JAC)
+  {
+    const float sc = M > 0 ? fs.weight / (float)M : 0.f;
+    for (int e = threadIdx.x; e < D * D + D; e += blockDim.x)
+    {
+      const int r = e < D * D ? e / D : e - D * D;
+      const int c = e < D * D ? e % D : 7;
+      o[e] = Hs[r * WP + c] * sc;
+    }
+  }
+}
+
+int launch_match_geom(bool jac, const MatchGeomFactor *factors, int nfactors, float *out, int out_stride, int D, cudaStream_t stream)
+{
+  if (nfactors <= 0)
+    return 0;
+  if (jac)
+    match_geom_kernel<true><<<nfactors, SAGE_CTA, 0, stream>>>(factors, out, out_stride, D);
+  else
+    match_geom_kernel<false><<<nfactors, SAGE_CTA, 0, stream>>>(factors, out, out_stride, D);
+  return 0;
+}
+
 template <int C>
 static void launch_reproj_c(bool jac, bool tracker, const ReprojFactor *f, int nf, float *out, int out_stride, cudaStream_t s)
 {

@@ -38,6 +38,7 @@ struct PhotoFactor
   float scale0, eps;
   float w[SAGE_MAX_LEVELS];
   int out; // slot in the factor output buffers
+  float dmul; // tracker form: depth = dmul * dpts0[n] (TrackFrame optimises the scale of frame 0)
 };
 
 struct GeoFactor
@@ -66,6 +67,18 @@ struct ReprojFactor
   float code0[SAGE_MAX_CODE];
   float scale0, eps, loss_param, weight;
   float fx, fy, cx, cy;
+  int out;
+};
+
+// tracker match-geometry factor (3-D point-to-point, Fair loss): K/match_geometry_factor_kernels.cpp:83-292
+struct MatchGeomFactor
+{
+  const float *dpts0, *dpts1; // [M] depth of the keypoint in frame 0 (before dmul) and of its match in frame 1
+  const float *homo0, *homo1; // [M][3]
+  int M;
+  float R[9], t[3];
+  float dmul, scale0; // depth multiplier; scale0 == 0 -> 6-DoF form (no scale column)
+  float loss_param, weight;
   int out;
 };
 

@@ -89,6 +89,18 @@ struct PinBuf
 
 } // namespace sage
 
+struct sage_ba_context;
+struct sage_ba_keyframe;
+namespace sage
+{
+void run_tracker_photo(sage_ba_context *ctx, bool jac, const sage_ba_keyframe *frame1, const float *R, const float *t,
+                       const float *dpts_dev, const float *homo3_dev, const float *feats_dev, int N, float dmul, float scale0, float eps,
+                       const float *weights, float *AtA, float *Atb, float *error, float *n_inl);
+void run_match_geom_single(sage_ba_context *ctx, bool jac, const float *R, const float *t, const float *dpts0, const float *dpts1,
+                           const float *homo0, const float *homo1, int M, float dmul, float scale0, float loss_param, float weight,
+                           float *AtA, float *Atb, float *error);
+} // namespace sage
+
 struct sage_ba_context
 {
   int device = 0;

@@ -22,6 +22,8 @@ int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, i
 int launch_reproj(bool jac, bool tracker, int C, const ReprojFactor *factors, int nfactors, float *out, int out_stride,
                   cudaStream_t stream);
 
+int launch_match_geom(bool jac, const MatchGeomFactor *factors, int nfactors, float *out, int out_stride, int D, cudaStream_t stream);
+
 // prep.cu
 void launch_relayout_fg(const float *feat, const float *grad, float *fg, int F, long SP, cudaStream_t stream);
 void launch_relayout_basis(const float *jac, long stride_row, long stride_col, float *basis, int HW, int C, cudaStream_t stream);

@@ -274,3 +274,172 @@ extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyfr
     return 1;
   }
 }
+
+
+// CameraTracker::TrackFrame (core/system/camera_tracker.cpp:1312-1672): the same damped Gauss-Newton loop on 7 variables,
+// relative pose + depth scale of the tracked frame (UpdateVariables :467-489: scale += delta[6]; LMConvergence :527-550).
+extern "C" int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe *frame0, const sage_ba_keyframe *kf1, const float *code0,
+                                   const sage_ba_tracker_config *cfg, float *R, float *t, float *scale, const float *m_udpts0,
+                                   const float *m_homo0, const float *m_dpts1, const float *m_homo1, int num_matches,
+                                   sage_ba_tracker_report *report)
+{
+  if (!ctx)
+    return 1;
+  try
+  {
+    SAGE_CHECK(frame0 && kf1 && cfg && R && t && scale, "null argument");
+    SAGE_CUDA(cudaSetDevice(ctx->device));
+    const int N = frame0->N, L = frame0->L, F = frame0->F;
+    const bool use_photo = cfg->use_photo != 0, use_mg = cfg->use_match_geom != 0;
+    SAGE_CHECK(use_photo || use_mg, "at least one factor should be enabled");
+    if (use_mg && num_matches <= 3)
+      throw Error{"not enough feature matches (camera_tracker.cpp:1389-1393)"};
+    float *d_udpts = ctx->trk_dpts.ensure(std::max(N, 1));
+    float *d_homo = ctx->trk_homo.ensure((size_t)std::max(N, 1) * 3);
+    float *d_feats = ctx->trk_feats.ensure((size_t)L * std::max(N, 1) * F);
+    if (use_photo) // unscaled depths (dpt_map / dpt_scale) and the tracked frame's own features at its sample points
+      SAGE_CHECK(sage_ba_tracker_presample(ctx, frame0, code0, 1.0f, d_udpts, d_homo, d_feats) == 0, ctx->err);
+
+    sage_ba_tracker_report rep;
+    memset(&rep, 0, sizeof(rep));
+    float wsum = 0.f;
+    for (int l = 0; l < L; ++l)
+      wsum += cfg->photo_weights[l];
+    auto jac_fn = [&](const float *Rg, const float *tg, float sg, float *AtA, float *Atb, float *err) {
+      for (int i = 0; i < 49; ++i)
+        AtA[i] = 0.f;
+      for (int i = 0; i < 7; ++i)
+        Atb[i] = 0.f;
+      float e_photo = 0.f, e_mg = 0.f, A[49], b[7];
+      if (use_photo)
+      {
+        run_tracker_photo(ctx, true, kf1, Rg, tg, d_udpts, d_homo, d_feats, N, sg, sg, cfg->dpt_eps, cfg->photo_weights, A, b, &e_photo,
+                          nullptr);
+        for (int i = 0; i < 49; ++i)
+          AtA[i] += A[i];
+        for (int i = 0; i < 7; ++i)
+          Atb[i] += b[i];
+      }
+      if (use_mg)
+      {
+        run_match_geom_single(ctx, true, Rg, tg, m_udpts0, m_dpts1, m_homo0, m_homo1, num_matches, sg, sg, cfg->match_geom_loss_param,
+                              cfg->match_geom_weight, A, b, &e_mg);
+        for (int i = 0; i < 49; ++i)
+          AtA[i] += A[i];
+        for (int i = 0; i < 7; ++i)
+          Atb[i] += b[i];
+      }
+      *err = e_photo + e_mg;
+      rep.jacobian_evals++;
+    };
+    auto err_fn = [&](const float *Rg, const float *tg, float sg) -> float {
+      float e_photo = 0.f, e_mg = 0.f;
+      if (use_photo)
+        run_tracker_photo(ctx, false, kf1, Rg, tg, d_udpts, d_homo, d_feats, N, sg, 0.f, cfg->dpt_eps, cfg->photo_weights, nullptr, nullptr,
+                          &e_photo, nullptr);
+      if (use_mg)
+        run_match_geom_single(ctx, false, Rg, tg, m_udpts0, m_dpts1, m_homo0, m_homo1, num_matches, sg, 0.f, cfg->match_geom_loss_param,
+                              cfg->match_geom_weight, nullptr, nullptr, &e_mg);
+      rep.error_evals++;
+      return e_photo + e_mg;
+    };
+    auto clampd = [&](float d) { return std::min(std::max(cfg->min_damp, d), cfg->max_damp); };
+
+    float Rg[9], tg[3], Rc[9], tc[3], sg = *scale, sc = *scale;
+    memcpy(Rg, R, sizeof(Rg));
+    memcpy(tg, t, sizeof(tg));
+    float AtA[49], Atb[7], damped[49], sol[7];
+    float prev_error = 0.f, curr_error = 1.f, cand_error = 1.f;
+    float damp = cfg->init_damp;
+    long iter = 0;
+    bool update_jac = true;
+    int rc = 0;
+    while (true)
+    {
+      if (std::fabs(curr_error - prev_error) / prev_error > cfg->jac_update_err_inc_threshold)
+      {
+        float e = 0.f;
+        jac_fn(Rg, tg, sg, AtA, Atb, &e);
+        if (iter == 0)
+          curr_error = e;
+        update_jac = true;
+      }
+      else
+        update_jac = false;
+      if (curr_error >= wsum * 9.9f && !use_mg) // no overlap (:1500-1504)
+      {
+        rc = 2;
+        break;
+      }
+      iter += 1;
+      auto solve = [&]() {
+        for (int i = 0; i < 49; ++i)
+          damped[i] = AtA[i];
+        for (int i = 0; i < 7; ++i)
+          damped[i * 7 + i] = AtA[i * 7 + i] + damp * AtA[i * 7 + i];
+        if (!solve_small(damped, Atb, 7, sol))
+          for (int i = 0; i < 7; ++i)
+            sol[i] = 0.f;
+      };
+      solve();
+      float rotvec[3];
+      rotation_to_angle_axis(Rg, 1.0e-6f, rotvec);
+      float max_grad = 0.f, max_inc = -INFINITY;
+      for (int i = 0; i < 7; ++i)
+      {
+        max_grad = std::max(max_grad, std::fabs(Atb[i]));
+        const float x = i < 3 ? tg[i] : (i < 6 ? rotvec[i - 3] : sg);
+        max_inc = std::max(max_inc, sol[i] / (std::fabs(x) + 1.0e-8f));
+      }
+      if (max_grad < cfg->min_grad_thresh || max_inc < cfg->min_param_inc_thresh)
+        break;
+      while (true)
+      {
+        float dR[9], dt[3];
+        se3_exp_host(sol + 3, sol, dR, dt);
+        for (int r = 0; r < 3; ++r)
+        {
+          for (int c = 0; c < 3; ++c)
+            Rc[r * 3 + c] = dR[r * 3] * Rg[c] + dR[r * 3 + 1] * Rg[3 + c] + dR[r * 3 + 2] * Rg[6 + c];
+          tc[r] = dR[r * 3] * tg[0] + dR[r * 3 + 1] * tg[1] + dR[r * 3 + 2] * tg[2] + dt[r];
+        }
+        sc = sg + sol[6];
+        cand_error = err_fn(Rc, tc, sc);
+        if (cand_error < curr_error)
+          break;
+        else if (damp < cfg->max_damp)
+        {
+          damp = clampd(damp * cfg->damp_inc_factor);
+          solve();
+        }
+        else
+          break;
+      }
+      if (cand_error >= curr_error && damp >= cfg->max_damp)
+        break;
+      memcpy(Rg, Rc, sizeof(Rg));
+      memcpy(tg, tc, sizeof(tg));
+      sg = sc;
+      if (update_jac)
+        prev_error = curr_error;
+      curr_error = cand_error;
+      damp = clampd(damp / cfg->damp_dec_factor);
+      if (iter >= cfg->max_num_iters)
+        break;
+    }
+    memcpy(R, Rg, sizeof(Rg));
+    memcpy(t, tg, sizeof(tg));
+    *scale = sg;
+    rep.iterations = (int)iter;
+    rep.final_error = curr_error;
+    rep.final_damp = damp;
+    if (report)
+      *report = rep;
+    return rc;
+  }
+  catch (const sage::Error &e)
+  {
+    ctx->err = e.msg;
+    return 1;
+  }
+}

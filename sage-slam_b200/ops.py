@@ -289,3 +289,59 @@ def track_new_frame(ctx, kf0, frame1, code_0, scale_0, rotation, translation, ph
                                               _p(mh), _p(m2), M, C.byref(rep)))
     return R, t, {"iterations": rep.iterations, "jacobian_evals": rep.jacobian_evals, "error_evals": rep.error_evals,
                   "final_error": rep.final_error, "final_damp": rep.final_damp}
+
+
+def tracker_match_geom_jac_error_calculate(ctx, rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0,
+                                           matched_locations_homo_1, loss_param, weight, scale_0=None):
+    """tracker_match_geom_jac_error_calculate (6x6) or ..._with_scale (7x7) (cuda/match_geometry_factor_kernels.h)."""
+    D = 7 if scale_0 is not None else 6
+    AtA, Atb = np.zeros((D, D), F32), np.zeros((D,), F32)
+    err = C.c_float(0)
+    R, t, d0, d1, h0, h1 = [_f(x) for x in (rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0,
+                                            matched_locations_homo_1)]
+    ctx.check(ctx.lib.sage_ba_tracker_match_geom_jac_error(ctx.h, _p(R), _p(t), _p(d0), _p(d1), _p(h0), _p(h1), len(d0),
+                                                           int(scale_0 is not None), float(scale_0 or 0.0), float(loss_param),
+                                                           float(weight), _p(AtA), _p(Atb), C.byref(err)))
+    return AtA, Atb, err.value
+
+
+def tracker_match_geom_error_calculate(ctx, rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0,
+                                       matched_locations_homo_1, loss_param, weight):
+    err = C.c_float(0)
+    R, t, d0, d1, h0, h1 = [_f(x) for x in (rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0,
+                                            matched_locations_homo_1)]
+    ctx.check(ctx.lib.sage_ba_tracker_match_geom_error(ctx.h, _p(R), _p(t), _p(d0), _p(d1), _p(h0), _p(h1), len(d0),
+                                                       float(loss_param), float(weight), C.byref(err)))
+    return err.value
+
+
+def track_frame(ctx, frame0, kf1, code_0, rotation, translation, scale, photo_weights, dpt_eps=1e-4, max_num_iters=40, init_damp=1e-4,
+                min_damp=1e-6, max_damp=1e-2, damp_dec_factor=10.0, damp_inc_factor=100.0, jac_update_err_inc_threshold=1e-2,
+                min_grad_thresh=1e-8, min_param_inc_thresh=1e-8, matches=None, match_geom_loss_param=1.0, match_geom_weight=0.0,
+                use_photo=True):
+    """CameraTracker::TrackFrame (camera_tracker.cpp:1312-1672): 7-DoF LM on relative pose + depth scale of frame0.
+    matches = (unscaled_dpts_0 [M], homo_0 [M,3], dpts_1 [M], homo_1 [M,3]) or None.  Returns (R, t, scale, report)."""
+    cfg = capi.TrackerConfig()
+    cfg.max_num_iters = max_num_iters
+    cfg.init_damp, cfg.min_damp, cfg.max_damp = init_damp, min_damp, max_damp
+    cfg.damp_dec_factor, cfg.damp_inc_factor = damp_dec_factor, damp_inc_factor
+    cfg.jac_update_err_inc_threshold = jac_update_err_inc_threshold
+    cfg.min_grad_thresh, cfg.min_param_inc_thresh, cfg.dpt_eps = min_grad_thresh, min_param_inc_thresh, dpt_eps
+    for i, w in enumerate(photo_weights):
+        cfg.photo_weights[i] = float(w)
+    cfg.use_photo, cfg.use_match_geom = int(use_photo), int(matches is not None)
+    cfg.match_geom_loss_param, cfg.match_geom_weight = match_geom_loss_param, match_geom_weight
+    R, t, c = _f(rotation).copy(), _f(translation).copy(), _f(code_0)
+    s = C.c_float(float(scale))
+    arrs = [None] * 4
+    M = 0
+    if matches is not None:
+        arrs = [_f(x) for x in matches]
+        M = len(arrs[0])
+    rep = capi.TrackerReport()
+    rc = ctx.lib.sage_ba_track_frame(ctx.h, frame0.h, kf1.h, _p(c), C.byref(cfg), _p(R), _p(t), C.byref(s), _p(arrs[0]), _p(arrs[1]),
+                                     _p(arrs[2]), _p(arrs[3]), M, C.byref(rep))
+    if rc == 1:
+        ctx.check(rc)
+    return R, t, s.value, {"iterations": rep.iterations, "jacobian_evals": rep.jacobian_evals, "error_evals": rep.error_evals,
+                           "final_error": rep.final_error, "final_damp": rep.final_damp, "no_overlap": rc == 2}

@@ -102,7 +102,15 @@ def tracker_args(kfs, args):
 def match_args(kfs, M=200):
     loc, homo, uv = sage.synthetic.make_matches(kfs[0], kfs[1], M=M)
     dpts = kfs[0].dpt_map.reshape(-1)[loc].astype(F32)
-    return dict(mloc=loc, mhomo=homo, m2d=uv, mdpts=dpts)
+    # 3-D form of the same matches for the match-geometry term: ray + depth of the matched pixel in frame 1
+    cam = kfs[1].camera_pyramid[0]
+    H, W = kfs[1].video_mask.shape
+    homo1 = np.stack([(uv[:, 0] - cam[2]) / cam[0], (uv[:, 1] - cam[3]) / cam[1], np.ones(len(uv), F32)], 1).astype(F32)
+    px = np.clip(np.round(uv[:, 0]).astype(int), 0, W - 1)
+    py = np.clip(np.round(uv[:, 1]).astype(int), 0, H - 1)
+    dpts1 = kfs[1].dpt_map[py, px].astype(F32)
+    mg_loss = float(0.03 * np.mean(kfs[0].dpt_map_bias.astype(np.float64) ** 2))
+    return dict(mloc=loc, mhomo=homo, m2d=uv, mdpts=dpts, mhomo1=homo1, mdpts1=dpts1, mg_loss=mg_loss, mg_weight=0.2)
 
 
 def rel_err(a, b):

@@ -45,6 +45,14 @@ def run_oracle(kfs, dtype=np.float32):
     out.update(trkrep_AtA=A, trkrep_Atb=b, trkrep_err=e)
     out["trkrep_err_only"], _ = O.tracker_reproj_error(a["R10"], a["t10"], ma["mdpts"], ma["mhomo"], ma["m2d"], a["cam"], a["eps"],
                                                        a["rep_loss"], a["rep_weight"], dtype=dtype)
+    A, b, e = O.tracker_match_geom_jac_error(a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"], ma["mg_loss"],
+                                             ma["mg_weight"], dtype=dtype)
+    out.update(mg_AtA=A, mg_Atb=b, mg_err=e)
+    A, b, e = O.tracker_match_geom_jac_error(a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"], ma["mg_loss"],
+                                             ma["mg_weight"], scale0=a["scale0"], dtype=dtype)
+    out.update(mgs_AtA=A, mgs_Atb=b, mgs_err=e)
+    out["mg_err_only"] = O.tracker_match_geom_error(a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"],
+                                                    ma["mg_loss"], ma["mg_weight"], dtype=dtype)
     out["cam_pyramid"] = O.camera_pyramid(a["cam"], a["L"])
     out["sig"] = np.array([float(np.abs(a["feat0"]).sum()), float(np.abs(a["jac0"]).sum()), float(a["R10"].sum()),
                            float(ta["sfeat0"].sum()), float(ma["m2d"].sum())])

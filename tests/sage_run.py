@@ -48,6 +48,14 @@ def run_sage(ctx, kfs):
     out.update(trkrep_AtA=A, trkrep_Atb=b, trkrep_err=e)
     out["trkrep_err_only"], _ = ops.tracker_reproj_error_calculate(ctx, a["cam"], a["R10"], a["t10"], ma["mdpts"], ma["mhomo"],
                                                                    ma["m2d"], a["eps"], a["rep_loss"], a["rep_weight"])
+    A, b, e = ops.tracker_match_geom_jac_error_calculate(ctx, a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"],
+                                                         ma["mg_loss"], ma["mg_weight"])
+    out.update(mg_AtA=A, mg_Atb=b, mg_err=e)
+    A, b, e = ops.tracker_match_geom_jac_error_calculate(ctx, a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"],
+                                                         ma["mg_loss"], ma["mg_weight"], scale_0=a["scale0"])
+    out.update(mgs_AtA=A, mgs_Atb=b, mgs_err=e)
+    out["mg_err_only"] = ops.tracker_match_geom_error_calculate(ctx, a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"],
+                                                                ma["mhomo1"], ma["mg_loss"], ma["mg_weight"])
     out["cam_pyramid"] = d0.cameras()[0]
     out["ref_sfeat0"] = ta["sfeat0"]
     out["ref_dpts0"] = ta["dpts0"]

@@ -13,7 +13,7 @@ import sage_run
 
 GOLDEN = os.path.join(helpers.ROOT, "tests", "golden")
 TOL = 1e-4
-KEYS = ["photo", "geo", "rep", "trk", "trks", "trkrep"]
+KEYS = ["photo", "geo", "rep", "trk", "trks", "trkrep", "mg", "mgs"]
 
 
 def _compare(mine, ref, label):

@@ -219,3 +219,42 @@ def test_banded_cholesky_equals_dense_schur(sage_ctx, num_kf):
     for a, b in zip(sols["schur"], sols["banded"]):
         assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(a).max())
         assert np.abs(a).max() > 0
+
+
+@pytest.mark.gpu
+def test_track_frame_7dof_matches_oracle_lm(sage_ctx):
+    """CameraTracker::TrackFrame (7-DoF: relative pose + depth scale; photometric-with-scale + match-geometry-with-scale)
+    in C++ over the C ABI vs the Python restatement of the loop driving the CPU oracle."""
+    import oracle as O
+    from sage_slam_b200 import ops
+
+    kfs = helpers.build_case("small_c8_f16")
+    a = helpers.case_args(kfs)
+    ta = helpers.tracker_args(kfs, a)
+    ma = helpers.match_args(kfs)
+    d0, d1 = sage.DeviceKeyframe(sage_ctx, kfs[0]), sage.DeviceKeyframe(sage_ctx, kfs[1])
+    s0 = np.float32(a["scale0"])
+    udpts = (ta["dpts0"] / s0).astype(np.float32)          # unscaled_photo_dpts_0 (camera_tracker.cpp:1411)
+    mud = (ma["mdpts"] / s0).astype(np.float32)            # unscaled_inlier_keypoint_dpts_0 (:1402)
+    matches = (mud, ma["mhomo"], ma["mdpts1"], ma["mhomo1"])
+    R, t, s, rep = ops.track_frame(sage_ctx, d0, d1, a["code0"], a["R10"], a["t10"], float(s0), a["weights"], max_num_iters=5,
+                                   matches=matches, match_geom_loss_param=ma["mg_loss"], match_geom_weight=ma["mg_weight"])
+
+    def jac(Rg, tg, sg):
+        A, b, e, _ = O.tracker_photo_jac_error(Rg, tg, a["mask1"], np.float32(sg) * udpts, a["homo"], ta["sfeat0"], a["feat1"], a["grad1"],
+                                               a["level_offsets"], a["cams"], a["eps"], a["weights"], scale0=sg)
+        A2, b2, e2 = O.tracker_match_geom_jac_error(Rg, tg, np.float32(sg) * mud, ma["mdpts1"], ma["mhomo"], ma["mhomo1"], ma["mg_loss"],
+                                                    ma["mg_weight"], scale0=sg)
+        return A + A2, b + b2, e + e2
+
+    def err(Rg, tg, sg):
+        e1 = O.tracker_photo_error(Rg, tg, a["mask1"], np.float32(sg) * udpts, a["homo"], ta["sfeat0"], a["feat1"], a["level_offsets"],
+                                   a["cams"], a["eps"], a["weights"])[0]
+        return e1 + O.tracker_match_geom_error(Rg, tg, np.float32(sg) * mud, ma["mdpts1"], ma["mhomo"], ma["mhomo1"], ma["mg_loss"],
+                                               ma["mg_weight"])
+
+    Ro, to, so, eo, trace = O.tracker_lm7(jac, err, a["R10"], a["t10"], s0, max_iters=5)
+    assert rep["iterations"] == len(trace) and not rep["no_overlap"]
+    assert abs(rep["final_error"] - eo) / eo <= 1e-4
+    assert np.abs(t - to).max() <= 1e-5 and np.abs(R - Ro).max() <= 1e-5 and abs(s - so) <= 1e-5
+    assert rep["final_error"] < err(a["R10"], a["t10"], s0)
