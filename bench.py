@@ -234,6 +234,10 @@ def run_ours(args):
             dist.all_reduce(ll)
             launches = int(ll[0])
 
+        tracker = None
+        if rank == 0 and world == 1 and not args.no_tracker:
+            tracker = tracker_bench(ctx, sage, kfs, dkfs, wl)
+
     if rank == 0:
         hbm, src = load_peaks()
         b_photo, b_photo_err, b_geo = algorithmic_bytes(wl)
@@ -268,11 +272,42 @@ def run_ours(args):
             "clocks": clocks,
             "lm_trace": [(float(a), float(b)) for a, b in costs[-args.steps:]][:6],
         }
+        if tracker is not None:
+            line["config2_tracker"] = tracker
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl, kfs, pairs, len(pairs))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def tracker_bench(ctx, sage, kfs, dkfs, wl, reps=5):
+    """BASELINE configs[1]: CameraTracker::TrackNewFrame, 1 reference KF vs 1 live frame at 320x256x32, photometric +
+    reprojection (M = 256), 10 LM iterations -- latency of the whole call (pre-sampling + LM loop, host solve included)."""
+    import torch
+
+    from sage_slam_b200 import ops
+
+    k0, k1 = kfs[1], kfs[0]  # reference keyframe, frame to track
+    R0, t0 = k0.pose_wk
+    R1, t1 = k1.pose_wk
+    R10 = (R1.T @ R0).astype(np.float32)
+    t10 = (R1.T @ (t0 - t1)).astype(np.float32)
+    loc, homo, uv = sage.synthetic.make_matches(k0, k1, M=256)
+    dpts = k0.dpt_map.reshape(-1)[loc].astype(np.float32)
+    times, rep = [], None
+    for r in range(reps + 1):
+        torch.cuda.synchronize()
+        t_0 = time.perf_counter()
+        _, _, rep = ops.track_new_frame(ctx, dkfs[1], dkfs[0], k0.code, k0.dpt_scale, R10, t10, PHOTO_W[:wl["L"]], dpt_eps=EPS,
+                                        max_num_iters=10, matches=(dpts, homo, uv), reproj_loss_param=0.03 * wl["W"] ** 2,
+                                        reproj_weight=0.1)
+        torch.cuda.synchronize()
+        if r:
+            times.append((time.perf_counter() - t_0) * 1e3)
+    return {"workload": "TrackNewFrame: 1 KF vs 1 frame, 320x256, F=32, L=4, dense N=81920, photometric + reprojection M=256, max 10 LM iters",
+            "ms_per_track": float(np.median(times)), "lm_iterations": rep["iterations"], "jacobian_evals": rep["jacobian_evals"],
+            "error_evals": rep["error_evals"], "final_error": rep["final_error"]}
 
 
 def cpu_sample(kfs, pair, wl):
@@ -432,6 +467,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--small", action="store_true", help="tiny debug workload (not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tracker", action="store_true", help="skip the configs[1] tracker latency measurement")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference-gpu: sub-sample N points per keyframe (0 = dense)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

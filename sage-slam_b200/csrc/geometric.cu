@@ -25,6 +25,14 @@ struct GeoCam
   int W, H;
 };
 
+#ifndef GEO_MINB
+#define GEO_MINB 8
+#endif
+#ifndef GEO_UNROLL
+#define GEO_UNROLL 4
+#endif
+#define GEO_STR2(x) #x
+#define GEO_STR(x) GEO_STR2(x)
 constexpr int GEO_WARPS = 2;
 constexpr int GEO_CTA = GEO_WARPS * 32;
 
@@ -40,15 +48,14 @@ struct GeoTraits
 };
 
 template <int C, bool JAC>
-__global__ void __launch_bounds__(GEO_CTA, 6)
+__global__ void __launch_bounds__(GEO_CTA, GEO_MINB)
 geo_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__restrict__ partH, float *__restrict__ partE)
 {
   using T = GeoTraits<C>;
   constexpr int LPG = T::LPG, WP = T::WP, ST = T::ST;
   constexpr int ROWS = GEO_WARPS * 32;
   constexpr int STAGE = JAC ? ROWS * ST : 4;
-  constexpr int HS = JAC ? WP * WP : 4;
-  __shared__ __align__(16) float Y[STAGE > HS ? STAGE : HS];
+  __shared__ __align__(16) float Y[STAGE];
   __shared__ GeoFactor fs;
   __shared__ float red[32];
   {
@@ -160,7 +167,7 @@ geo_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__res
       *reinterpret_cast<float4 *>(row + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
       // ---------------------------------------------------------------- lane == channel quad: code columns
       const float k0 = sw * kc0, k1 = -(sw * fs.scale1); // :695-696
-#pragma unroll 2
+_Pragma(GEO_STR(unroll GEO_UNROLL))
       for (int i = 0; i < LPG; ++i)
       {
         const int src = q * LPG + i;
@@ -189,18 +196,11 @@ geo_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__res
   const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   if constexpr (JAC)
   {
-    __syncthreads();
-    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
-      Y[i] = 0.f;
-    __syncthreads();
-    if (warp == 0)
-      syrk.template add_to<0>(Y, lane);
-    else
-      syrk.template add_to<1>(Y, lane); // disjoint tiles: no race between the two warps
-    __syncthreads();
     float *dst = partH + slot * (WP * WP);
-    for (int i = threadIdx.x; i < WP * WP; i += blockDim.x)
-      dst[i] = Y[i];
+    if (warp == 0)
+      syrk.template store_tiles<0>(dst, lane);
+    else
+      syrk.template store_tiles<1>(dst, lane); // disjoint tiles covering the upper triangle: no reduction needed
   }
   const float es = block_sum(err_acc, red);
   const float cs = block_sum(inl_acc, red);

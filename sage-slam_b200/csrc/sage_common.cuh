@@ -419,6 +419,31 @@ struct MmaSyrk
       }
   }
 
+  // write (not add) this warp's tiles straight to a WP x WP matrix in global memory: with NSPLIT cooperating warps the
+  // tile sets are disjoint and together cover the whole upper triangle, so no reduction or zero-fill is needed
+  template <int PART = 0>
+  __device__ __forceinline__ void store_tiles(float *dst, int lane) const
+  {
+    const int g = lane >> 2, t = lane & 3;
+    int ti = 0;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int nj = 2 * mi; nj < NT8; ++nj)
+      {
+        if (ti % NSPLIT == PART)
+        {
+          const float(&d)[4] = acc[ti / NSPLIT];
+          const int r = 16 * mi + g, c = 8 * nj + 2 * t;
+          if (r < WP)
+            *reinterpret_cast<float2 *>(dst + r * WP + c) = make_float2(d[0], d[1]);
+          if (r + 8 < WP)
+            *reinterpret_cast<float2 *>(dst + (r + 8) * WP + c) = make_float2(d[2], d[3]);
+        }
+        ++ti;
+      }
+  }
+
   // NSPLIT == 1: sum the warps' full accumulators in shared memory (Hs: WP*WP floats, may alias the staging buffer once
   // every warp is done with it) and write the CTA's WP x WP partial (upper triangle valid) to dst.  Called by all threads.
   __device__ __forceinline__ void store_cta(float *Hs, float *dst, int warp, int lane, int nwarps)
