@@ -187,6 +187,44 @@ int sage_ba_tracker_match_geom_error(sage_ba_context *ctx, const float *R, const
                                      const float *matched_locations_homo_1, int num_matches, float loss_param, float weight,
                                      float *error);
 
+/* df::match_geometry_jac_error_calculate<CS> (cuda/match_geometry_factor_kernels.cpp:1675-1823) and
+ * df::match_geometry_error_calculate<CS> (:1567-1673): 3-D point-to-point term between matched keypoints of two
+ * keyframes, depths from each keyframe's bias/basis/code/scale.  Variable order of the (14+2C)-square system:
+ * [pose0 6 | pose1 6 | code0 C | code1 C | scale0 | scale1].  loss_type mirrors the reference's robust_loss_type
+ * string.  Location / homogeneous arrays are HOST arrays of num_matches entries. */
+enum
+{
+  SAGE_BA_LOSS_FAIR = 0,     /* "fair"     */
+  SAGE_BA_LOSS_L2 = 1,       /* "L2"       */
+  SAGE_BA_LOSS_HUBER = 2,    /* "huber"    */
+  SAGE_BA_LOSS_UNBIASED = 3  /* "unbiased" */
+};
+int sage_ba_match_geometry_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                     const float *R10, const float *t10, const float *R0, const float *t0, const float *R1,
+                                     const float *t1, const float *code0, const float *code1, float scale0, float scale1,
+                                     const int32_t *sampled_locations_1d_0, const int32_t *matched_locations_1d_1,
+                                     const float *sampled_locations_homo_0, const float *matched_locations_homo_1,
+                                     int num_matches, float loss_param, float weight, int loss_type, float *AtA, float *Atb,
+                                     float *error);
+int sage_ba_match_geometry_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                 const float *R10, const float *t10, const float *code0, const float *code1, float scale0,
+                                 float scale1, const int32_t *sampled_locations_1d_0, const int32_t *matched_locations_1d_1,
+                                 const float *sampled_locations_homo_0, const float *matched_locations_homo_1,
+                                 int num_matches, float loss_param, float weight, int loss_type, float *error);
+
+/* df::loop_mg_jac_error_calculate (:1511-1565) and df::loop_mg_error_calculate (:1479-1509): the loop-closure
+ * pose/scale graph's factor (core/deepfactors.cpp:409-573).  14x14 system, order [pose0 6 | pose1 6 | scale0 | scale1];
+ * the depth arrays are the UNSCALED depths of the matched keypoints (HOST arrays). */
+int sage_ba_loop_mg_jac_error(sage_ba_context *ctx, const float *R10, const float *t10, const float *R0, const float *t0,
+                              const float *R1, const float *t1, const float *sampled_unscaled_dpts_0,
+                              const float *matched_unscaled_dpts_1, const float *sampled_locations_homo_0,
+                              const float *matched_locations_homo_1, int num_matches, float scale0, float scale1,
+                              float loss_param, float weight, float *AtA, float *Atb, float *error);
+int sage_ba_loop_mg_error(sage_ba_context *ctx, const float *R10, const float *t10, const float *sampled_unscaled_dpts_0,
+                          const float *matched_unscaled_dpts_1, const float *sampled_locations_homo_0,
+                          const float *matched_locations_homo_1, int num_matches, float scale0, float scale1,
+                          float loss_param, float weight, float *error);
+
 /* ------------------------------------------------------------------------------------------
  * CameraTracker::TrackNewFrame LM loop (core/system/camera_tracker.cpp:1034-1310, loop
  * :1156-1279): damped Gauss-Newton on the 6-DoF relative pose T_ck of `frame1` w.r.t. `kf0`,

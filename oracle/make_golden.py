@@ -81,6 +81,24 @@ def run_case(name, far):
                                                               ma["mg_weight"])
     out.update(mgs_AtA=AtA.cpu().numpy(), mgs_Atb=Atb.cpu().numpy().reshape(-1), mgs_err=e)
     out["mg_err_only"] = mod.tracker_match_geom_error(R["R10"], R["t10"], mdpts, md1, mhomo, mh1, ma["mg_loss"], ma["mg_weight"])
+    # mapping-side match geometry (all four robust losses) and the loop-closure form
+    jac1 = T(np.ascontiguousarray(a["jac1"].T), dev).t()
+    bias1, code1 = T(a["bias1"], dev), T(a["code1"], dev)
+    mloc1 = T(ma["mloc1"], dev, torch.int32)
+    for lt in helpers.MG_LOSSES:
+        AtA, Atb, e = mod.match_geometry_jac_error(R["R10"], R["t10"], R["R0"], R["t0"], R["R1"], R["t1"], R["bias0"], bias1, jac0, jac1,
+                                                   R["code0"], code1, mhomo, mh1, mloc, mloc1, a["scale0"], a["scale1"], ma["mg_loss"],
+                                                   ma["mg_weight"], lt)
+        out.update({f"mmg_{lt}_AtA": AtA.cpu().numpy(), f"mmg_{lt}_Atb": Atb.cpu().numpy().reshape(-1), f"mmg_{lt}_err": e})
+        out[f"mmg_{lt}_err_only"] = mod.match_geometry_error(R["R10"], R["t10"], R["bias0"], bias1, jac0, jac1, R["code0"], code1, mhomo,
+                                                             mh1, mloc, mloc1, a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"],
+                                                             lt)
+    mu0, mu1 = T(ma["mud0"], dev), T(ma["mud1"], dev)
+    AtA, Atb, e = mod.loop_mg_jac_error(R["R10"], R["t10"], R["R0"], R["t0"], R["R1"], R["t1"], mu0, mu1, mhomo, mh1, a["scale0"],
+                                        a["scale1"], ma["mg_loss"], ma["mg_weight"])
+    out.update(lmg_AtA=AtA.cpu().numpy(), lmg_Atb=Atb.cpu().numpy().reshape(-1), lmg_err=e)
+    out["lmg_err_only"] = mod.loop_mg_error(R["R10"], R["t10"], mu0, mu1, mhomo, mh1, a["scale0"], a["scale1"], ma["mg_loss"],
+                                            ma["mg_weight"])
     out["cam_pyramid"] = np.array(mod.camera_pyramid(cam, L), np.float32)
     out["sig"] = np.array([float(np.abs(a["feat0"]).sum()), float(np.abs(a["jac0"]).sum()), float(a["R10"].sum()),
                            float(ta["sfeat0"].sum()), float(ma["m2d"].sum())])

@@ -268,6 +268,69 @@ def tracker_match_geom_error(R, t, dpts0, dpts1, homo0, homo1, loss_param, weigh
     return e.value
 
 
+LOSS_TYPES = {"fair": 0, "L2": 1, "huber": 2, "unbiased": 3}
+
+
+def _mg_call(fname, with_pose, R10, t10, R0, t0, R1, t1, bias0, bias1, jac0, jac1, code0, code1, loc0, loc1, dpts0, dpts1,
+             homo0, homo1, scale0, scale1, loss_param, weight, loss_type, dtype):
+    f = getattr(lib(), fname + _suffix(dtype))
+    loop = bias0 is None
+    M = len(homo0)
+    null = ctypes.c_void_p(0)
+    zero = ctypes.c_long(0)
+    if loop:
+        CS = 0
+        maps = [null, null, null, zero, zero, null, zero, zero, null, null, null, null]
+        dp = [_r(dpts0, dtype), _r(dpts1, dtype)]
+        keep = dp
+        depth_args = [_p(dp[0]), _p(dp[1])]
+    else:
+        jac0, jac1 = np.asarray(jac0, dtype=dtype), np.asarray(jac1, dtype=dtype)
+        CS = jac0.shape[1]
+        b0, b1, c0, c1 = [_r(x, dtype) for x in (bias0, bias1, code0, code1)]
+        l0, l1 = _r(loc0, np.int32), _r(loc1, np.int32)
+        keep = [b0, b1, c0, c1, l0, l1, jac0, jac1]
+        maps = [_p(b0), _p(b1), _p(jac0), *_jac_strides(jac0), _p(jac1), *_jac_strides(jac1), _p(c0), _p(c1), _p(l0), _p(l1)]
+        depth_args = [null, null]
+    h0, h1 = _r(homo0, dtype), _r(homo1, dtype)
+    tail = [*maps, *depth_args, _p(h0), _p(h1), _s(scale0, dtype), _s(scale1, dtype), _s(loss_param, dtype), _s(weight, dtype),
+            ctypes.c_int(M), ctypes.c_int(CS), ctypes.c_int(LOSS_TYPES[loss_type] if isinstance(loss_type, str) else int(loss_type))]
+    e = ctypes.c_double(0)
+    if with_pose:
+        D = 14 + 2 * CS
+        A, b, _, _ = _out(D)
+        poses = [_r(x, dtype) for x in (R10, t10, R0, t0, R1, t1)]
+        f(_p(A), _p(b), ctypes.byref(e), *[_p(x) for x in poses], *tail)
+        return A, b, e.value
+    poses = [_r(x, dtype) for x in (R10, t10)]
+    f(ctypes.byref(e), *[_p(x) for x in poses], *tail)
+    return e.value
+
+
+def match_geometry_jac_error(R10, t10, R0, t0, R1, t1, bias0, bias1, jac0, jac1, code0, code1, homo0, homo1, loc0, loc1,
+                             scale0, scale1, loss_param, weight, loss_type="fair", dtype=np.float32):
+    """df::match_geometry_jac_error_calculate<CS>; order [pose0 pose1 code0 code1 scale0 scale1]."""
+    return _mg_call("oracle_match_geometry_jac_error", True, R10, t10, R0, t0, R1, t1, bias0, bias1, jac0, jac1, code0, code1,
+                    loc0, loc1, None, None, homo0, homo1, scale0, scale1, loss_param, weight, loss_type, dtype)
+
+
+def match_geometry_error(R10, t10, bias0, bias1, jac0, jac1, code0, code1, homo0, homo1, loc0, loc1, scale0, scale1,
+                         loss_param, weight, loss_type="fair", dtype=np.float32):
+    return _mg_call("oracle_match_geometry_error", False, R10, t10, None, None, None, None, bias0, bias1, jac0, jac1, code0,
+                    code1, loc0, loc1, None, None, homo0, homo1, scale0, scale1, loss_param, weight, loss_type, dtype)
+
+
+def loop_mg_jac_error(R10, t10, R0, t0, R1, t1, dpts0, dpts1, homo0, homo1, scale0, scale1, loss_param, weight, dtype=np.float32):
+    """df::loop_mg_jac_error_calculate; dpts are UNSCALED depths; order [pose0 pose1 scale0 scale1]."""
+    return _mg_call("oracle_match_geometry_jac_error", True, R10, t10, R0, t0, R1, t1, None, None, None, None, None, None,
+                    None, None, dpts0, dpts1, homo0, homo1, scale0, scale1, loss_param, weight, 0, dtype)
+
+
+def loop_mg_error(R10, t10, dpts0, dpts1, homo0, homo1, scale0, scale1, loss_param, weight, dtype=np.float32):
+    return _mg_call("oracle_match_geometry_error", False, R10, t10, None, None, None, None, None, None, None, None, None, None,
+                    None, None, dpts0, dpts1, homo0, homo1, scale0, scale1, loss_param, weight, 0, dtype)
+
+
 # --------------------------------------------------------------------------------------
 # host-side restatements
 # --------------------------------------------------------------------------------------

@@ -179,6 +179,44 @@ double tracker_match_geom_error(at::Tensor R, at::Tensor t, at::Tensor dpts0, at
 {
   return df::tracker_match_geom_error_calculate(R, t, dpts0, dpts1, homo0, homo1, (float)loss_param, (float)weight);
 }
+std::tuple<at::Tensor, at::Tensor, double> match_geometry_jac_error(
+    at::Tensor R10, at::Tensor t10, at::Tensor R0, at::Tensor t0, at::Tensor R1, at::Tensor t1, at::Tensor bias0, at::Tensor bias1,
+    at::Tensor jac0, at::Tensor jac1, at::Tensor code0, at::Tensor code1, at::Tensor homo0, at::Tensor homo1, at::Tensor loc0,
+    at::Tensor loc1, double scale0, double scale1, double loss_param, double weight, std::string loss_type)
+{
+  at::Tensor AtA, Atb;
+  float err = 0;
+  df::match_geometry_jac_error_calculate<CS>(AtA, Atb, err, R10, t10, R0, t0, R1, t1, bias0, bias1, jac0, jac1, code0, code1, homo0,
+                                             homo1, loc0, loc1, (float)scale0, (float)scale1, (float)loss_param, (float)weight,
+                                             loss_type);
+  return {AtA, Atb, (double)err};
+}
+
+double match_geometry_error(at::Tensor R, at::Tensor t, at::Tensor bias0, at::Tensor bias1, at::Tensor jac0, at::Tensor jac1,
+                            at::Tensor code0, at::Tensor code1, at::Tensor homo0, at::Tensor homo1, at::Tensor loc0, at::Tensor loc1,
+                            double scale0, double scale1, double loss_param, double weight, std::string loss_type)
+{
+  return df::match_geometry_error_calculate<CS>(R, t, bias0, bias1, jac0, jac1, code0, code1, homo0, homo1, loc0, loc1, (float)scale0,
+                                                (float)scale1, (float)loss_param, (float)weight, loss_type);
+}
+
+std::tuple<at::Tensor, at::Tensor, double> loop_mg_jac_error(at::Tensor R10, at::Tensor t10, at::Tensor R0, at::Tensor t0, at::Tensor R1,
+                                                             at::Tensor t1, at::Tensor dpts0, at::Tensor dpts1, at::Tensor homo0,
+                                                             at::Tensor homo1, double scale0, double scale1, double loss_param,
+                                                             double weight)
+{
+  at::Tensor AtA, Atb;
+  float err = 0;
+  df::loop_mg_jac_error_calculate(AtA, Atb, err, R10, t10, R0, t0, R1, t1, dpts0, dpts1, homo0, homo1, (float)scale0, (float)scale1,
+                                  (float)loss_param, (float)weight);
+  return {AtA, Atb, (double)err};
+}
+
+double loop_mg_error(at::Tensor R, at::Tensor t, at::Tensor dpts0, at::Tensor dpts1, at::Tensor homo0, at::Tensor homo1, double scale0,
+                     double scale1, double loss_param, double weight)
+{
+  return df::loop_mg_error_calculate(R, t, dpts0, dpts1, homo0, homo1, (float)scale0, (float)scale1, (float)loss_param, (float)weight);
+}
 } // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -200,4 +238,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
   m.def("tracker_match_geom_jac_error", &tracker_match_geom_jac_error);
   m.def("tracker_match_geom_jac_error_with_scale", &tracker_match_geom_jac_error_with_scale);
   m.def("tracker_match_geom_error", &tracker_match_geom_error);
+  m.def("match_geometry_jac_error", &match_geometry_jac_error);
+  m.def("match_geometry_error", &match_geometry_error);
+  m.def("loop_mg_jac_error", &loop_mg_jac_error);
+  m.def("loop_mg_error", &loop_mg_error);
 }

@@ -782,3 +782,158 @@ extern "C" int sage_ba_tracker_match_geom_error(sage_ba_context *ctx, const floa
                         1.f, 0.f, loss_param, weight, nullptr, nullptr, error);
   SAGE_CATCH
 }
+
+// mapping-side match-geometry / loop-closure match-geometry ---------------------------------------------
+namespace sage
+{
+static void run_map_match_geom_single(sage_ba_context *ctx, bool jac, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                      const float *R10, const float *t10, const float *R0, const float *t0, const float *R1,
+                                      const float *code0, const float *code1, float scale0, float scale1, const int32_t *loc0,
+                                      const int32_t *loc1, const float *dpts0, const float *dpts1, const float *homo0, const float *homo1,
+                                      int M, float loss_param, float weight, int loss_type, float *AtA, float *Atb, float *error)
+{
+  SAGE_CHECK(M >= 0 && M <= 4096, "num_matches out of range");
+  SAGE_CHECK(loss_type >= 0 && loss_type <= 3, "unknown robust loss type");
+  const bool loop = kf0 == nullptr;
+  int C = 0;
+  if (!loop)
+  {
+    SAGE_CHECK(kf1 && kf0->C == kf1->C, "keyframes disagree on code size");
+    C = kf0->C;
+    for (int m = 0; m < M; ++m)
+      SAGE_CHECK(loc0[m] >= 0 && loc0[m] < kf0->H * kf0->W && loc1[m] >= 0 && loc1[m] < kf1->H * kf1->W, "match location out of range");
+  }
+  cudaStream_t s = ctx->stream;
+  const int D = 14 + 2 * C;
+  float *dm = ctx->trk_m_homo.ensure((size_t)std::max(M, 1) * 8);
+  float *hm = ctx->hout.ensure(std::max<size_t>((size_t)M * 8, (size_t)D * D + D + 2));
+  memcpy(hm, homo0, sizeof(float) * 3 * M);
+  memcpy(hm + 3 * M, homo1, sizeof(float) * 3 * M);
+  if (loop)
+  {
+    memcpy(hm + 6 * M, dpts0, sizeof(float) * M);
+    memcpy(hm + 7 * M, dpts1, sizeof(float) * M);
+  }
+  else
+  {
+    memcpy(hm + 6 * M, loc0, sizeof(int32_t) * M);
+    memcpy(hm + 7 * M, loc1, sizeof(int32_t) * M);
+  }
+  SAGE_CUDA(cudaMemcpyAsync(dm, hm, sizeof(float) * 8 * M, cudaMemcpyHostToDevice, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  MapMatchGeomFactor f;
+  memset(&f, 0, sizeof(f));
+  f.homo0 = dm;
+  f.homo1 = dm + 3 * M;
+  if (loop)
+  {
+    f.dpts0 = dm + 6 * M;
+    f.dpts1 = dm + 7 * M;
+  }
+  else
+  {
+    f.loc0 = reinterpret_cast<const int *>(dm + 6 * M);
+    f.loc1 = reinterpret_cast<const int *>(dm + 7 * M);
+    f.bias0 = kf0->bias;
+    f.basis0 = kf0->basis;
+    f.bias1 = kf1->bias;
+    f.basis1 = kf1->basis;
+    memcpy(f.code0, code0, sizeof(float) * C);
+    memcpy(f.code1, code1, sizeof(float) * C);
+  }
+  f.M = M;
+  memcpy(f.R10, R10, 9 * sizeof(float));
+  memcpy(f.t10, t10, 3 * sizeof(float));
+  if (jac)
+  {
+    memcpy(f.R0, R0, 9 * sizeof(float));
+    memcpy(f.t0, t0, 3 * sizeof(float));
+    memcpy(f.R1, R1, 9 * sizeof(float));
+  }
+  f.scale0 = scale0;
+  f.scale1 = scale1;
+  f.loss_param = loss_param;
+  f.weight = weight;
+  f.loss_type = loss_type;
+  const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
+  float *out = ctx->out.ensure(nout);
+  MapMatchGeomFactor *df = reinterpret_cast<MapMatchGeomFactor *>(ctx->factor.ensure(1024));
+  MapMatchGeomFactor *hf = reinterpret_cast<MapMatchGeomFactor *>(ctx->hfactor.ensure(1024));
+  static_assert(sizeof(MapMatchGeomFactor) <= 1024, "factor staging buffer too small");
+  *hf = f;
+  SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(MapMatchGeomFactor), cudaMemcpyHostToDevice, s));
+  SAGE_CHECK(launch_map_match_geom(jac, C, df, 1, out, 1, s) == 0, "unsupported code_size");
+  ctx->launches += 1;
+  SAGE_CUDA(cudaGetLastError());
+  SAGE_CUDA(cudaMemcpyAsync(hm, out, nout * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  if (jac)
+  {
+    memcpy(AtA, hm, sizeof(float) * D * D);
+    memcpy(Atb, hm + D * D, sizeof(float) * D);
+  }
+  *error = hm[nout - 2];
+}
+} // namespace sage
+
+extern "C" int sage_ba_match_geometry_jac_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1,
+                                                const float *R10, const float *t10, const float *R0, const float *t0, const float *R1,
+                                                const float *t1, const float *code0, const float *code1, float scale0, float scale1,
+                                                const int32_t *sampled_locations_1d_0, const int32_t *matched_locations_1d_1,
+                                                const float *sampled_locations_homo_0, const float *matched_locations_homo_1,
+                                                int num_matches, float loss_param, float weight, int loss_type, float *AtA, float *Atb,
+                                                float *error)
+{
+  (void)t1;
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(kf0 && kf1, "null keyframe");
+  SAGE_CHECK(scale0 != 0.f && scale1 != 0.f, "scales must be non-zero");
+  run_map_match_geom_single(ctx, true, kf0, kf1, R10, t10, R0, t0, R1, code0, code1, scale0, scale1, sampled_locations_1d_0,
+                            matched_locations_1d_1, nullptr, nullptr, sampled_locations_homo_0, matched_locations_homo_1, num_matches,
+                            loss_param, weight, loss_type, AtA, Atb, error);
+  SAGE_CATCH
+}
+
+extern "C" int sage_ba_match_geometry_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *kf1, const float *R10,
+                                            const float *t10, const float *code0, const float *code1, float scale0, float scale1,
+                                            const int32_t *sampled_locations_1d_0, const int32_t *matched_locations_1d_1,
+                                            const float *sampled_locations_homo_0, const float *matched_locations_homo_1, int num_matches,
+                                            float loss_param, float weight, int loss_type, float *error)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CHECK(kf0 && kf1, "null keyframe");
+  run_map_match_geom_single(ctx, false, kf0, kf1, R10, t10, nullptr, nullptr, nullptr, code0, code1, scale0, scale1,
+                            sampled_locations_1d_0, matched_locations_1d_1, nullptr, nullptr, sampled_locations_homo_0,
+                            matched_locations_homo_1, num_matches, loss_param, weight, loss_type, nullptr, nullptr, error);
+  SAGE_CATCH
+}
+
+extern "C" int sage_ba_loop_mg_jac_error(sage_ba_context *ctx, const float *R10, const float *t10, const float *R0, const float *t0,
+                                         const float *R1, const float *t1, const float *sampled_unscaled_dpts_0,
+                                         const float *matched_unscaled_dpts_1, const float *sampled_locations_homo_0,
+                                         const float *matched_locations_homo_1, int num_matches, float scale0, float scale1,
+                                         float loss_param, float weight, float *AtA, float *Atb, float *error)
+{
+  (void)t1;
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  run_map_match_geom_single(ctx, true, nullptr, nullptr, R10, t10, R0, t0, R1, nullptr, nullptr, scale0, scale1, nullptr, nullptr,
+                            sampled_unscaled_dpts_0, matched_unscaled_dpts_1, sampled_locations_homo_0, matched_locations_homo_1,
+                            num_matches, loss_param, weight, 0, AtA, Atb, error);
+  SAGE_CATCH
+}
+
+extern "C" int sage_ba_loop_mg_error(sage_ba_context *ctx, const float *R10, const float *t10, const float *sampled_unscaled_dpts_0,
+                                     const float *matched_unscaled_dpts_1, const float *sampled_locations_homo_0,
+                                     const float *matched_locations_homo_1, int num_matches, float scale0, float scale1, float loss_param,
+                                     float weight, float *error)
+{
+  SAGE_TRY(ctx)
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  run_map_match_geom_single(ctx, false, nullptr, nullptr, R10, t10, nullptr, nullptr, nullptr, nullptr, nullptr, scale0, scale1, nullptr,
+                            nullptr, sampled_unscaled_dpts_0, matched_unscaled_dpts_1, sampled_locations_homo_0,
+                            matched_locations_homo_1, num_matches, loss_param, weight, 0, nullptr, nullptr, error);
+  SAGE_CATCH
+}

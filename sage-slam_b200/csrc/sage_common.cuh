@@ -82,6 +82,22 @@ struct MatchGeomFactor
   int out;
 };
 
+// mapping-side match-geometry factor (K/match_geometry_factor_kernels.cpp:421-1039, :1090-1359) and its loop-closure
+// form (:296-417, :1043-1086; bias0 == nullptr, unscaled depths given per match).
+struct MapMatchGeomFactor
+{
+  const float *bias0, *basis0, *bias1, *basis1; // [HW], [HW][C] pixel-major ; nullptr -> loop form
+  const int *loc0, *loc1;                       // [M]
+  const float *dpts0, *dpts1;                   // loop form: [M] unscaled depths
+  const float *homo0, *homo1;                   // [M][3]
+  int M;
+  float R10[9], t10[3], R0[9], t0[3], R1[9];
+  float code0[SAGE_MAX_CODE], code1[SAGE_MAX_CODE];
+  float scale0, scale1, loss_param, weight;
+  int loss_type; // 0 fair, 1 L2, 2 huber, 3 unbiased
+  int out;
+};
+
 __device__ __forceinline__ bool within(int x, int y, int W, int H) { return x >= 0 && x < W && y >= 0 && y < H; }
 
 // bilinear tap set: floor / floor+1, weights from those integers (photometric_factor_kernels.cpp:146-156)

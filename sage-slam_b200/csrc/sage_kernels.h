@@ -23,6 +23,7 @@ int launch_reproj(bool jac, bool tracker, int C, const ReprojFactor *factors, in
                   cudaStream_t stream);
 
 int launch_match_geom(bool jac, const MatchGeomFactor *factors, int nfactors, float *out, int out_stride, int D, cudaStream_t stream);
+int launch_map_match_geom(bool jac, int C, const MapMatchGeomFactor *factors, int nfactors, float *out, int out_stride, cudaStream_t stream);
 
 // prep.cu
 void launch_relayout_fg(const float *feat, const float *grad, float *fg, int F, long SP, cudaStream_t stream);

@@ -315,6 +315,66 @@ def tracker_match_geom_error_calculate(ctx, rotation, translation, sampled_dpts_
     return err.value
 
 
+LOSS_TYPES = {"fair": 0, "L2": 1, "huber": 2, "unbiased": 3}  # robust_loss_type strings of match_geometry_factor_kernels.h
+
+
+def _i32(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int32))
+
+
+def match_geometry_jac_error_calculate(ctx, kf0, kf1, rotation10, translation10, rotation0, translation0, rotation1, translation1,
+                                       code_0, code_1, sampled_locations_homo_0, matched_locations_homo_1, sampled_locations_1d_0,
+                                       matched_locations_1d_1, scale_0, scale_1, loss_param, weight, robust_loss_type="fair"):
+    """match_geometry_jac_error_calculate<CS> (cuda/match_geometry_factor_kernels.h:41-56); the per-frame bias / basis tensors of the
+    reference signature live in the keyframe handles."""
+    D = 14 + 2 * kf0.C
+    AtA, Atb = np.zeros((D, D), F32), np.zeros((D,), F32)
+    err = C.c_float(0)
+    a = [_f(x) for x in (rotation10, translation10, rotation0, translation0, rotation1, translation1, code_0, code_1)]
+    h0, h1 = _f(sampled_locations_homo_0), _f(matched_locations_homo_1)
+    l0, l1 = _i32(sampled_locations_1d_0), _i32(matched_locations_1d_1)
+    ctx.check(ctx.lib.sage_ba_match_geometry_jac_error(ctx.h, kf0.h, kf1.h, *[_p(x) for x in a], float(scale_0), float(scale_1), _p(l0),
+                                                       _p(l1), _p(h0), _p(h1), len(l0), float(loss_param), float(weight),
+                                                       LOSS_TYPES[robust_loss_type], _p(AtA), _p(Atb), C.byref(err)))
+    return AtA, Atb, err.value
+
+
+def match_geometry_error_calculate(ctx, kf0, kf1, rotation, translation, code_0, code_1, sampled_locations_homo_0,
+                                   matched_locations_homo_1, sampled_locations_1d_0, matched_locations_1d_1, scale_0, scale_1,
+                                   loss_param, weight, robust_loss_type="fair"):
+    err = C.c_float(0)
+    a = [_f(x) for x in (rotation, translation, code_0, code_1)]
+    h0, h1 = _f(sampled_locations_homo_0), _f(matched_locations_homo_1)
+    l0, l1 = _i32(sampled_locations_1d_0), _i32(matched_locations_1d_1)
+    ctx.check(ctx.lib.sage_ba_match_geometry_error(ctx.h, kf0.h, kf1.h, *[_p(x) for x in a], float(scale_0), float(scale_1), _p(l0),
+                                                   _p(l1), _p(h0), _p(h1), len(l0), float(loss_param), float(weight),
+                                                   LOSS_TYPES[robust_loss_type], C.byref(err)))
+    return err.value
+
+
+def loop_mg_jac_error_calculate(ctx, rotation10, translation10, rotation0, translation0, rotation1, translation1,
+                                sampled_unscaled_dpts_0, matched_unscaled_dpts_1, sampled_locations_homo_0, matched_locations_homo_1,
+                                scale_0, scale_1, loss_param, weight):
+    """loop_mg_jac_error_calculate (cuda/match_geometry_factor_kernels.h:67-77): 14x14, order [pose0 pose1 scale0 scale1]."""
+    AtA, Atb = np.zeros((14, 14), F32), np.zeros((14,), F32)
+    err = C.c_float(0)
+    a = [_f(x) for x in (rotation10, translation10, rotation0, translation0, rotation1, translation1, sampled_unscaled_dpts_0,
+                         matched_unscaled_dpts_1, sampled_locations_homo_0, matched_locations_homo_1)]
+    ctx.check(ctx.lib.sage_ba_loop_mg_jac_error(ctx.h, *[_p(x) for x in a], len(a[6]), float(scale_0), float(scale_1), float(loss_param),
+                                                float(weight), _p(AtA), _p(Atb), C.byref(err)))
+    return AtA, Atb, err.value
+
+
+def loop_mg_error_calculate(ctx, rotation, translation, sampled_unscaled_dpts_0, matched_unscaled_dpts_1, sampled_locations_homo_0,
+                            matched_locations_homo_1, scale_0, scale_1, loss_param, weight):
+    err = C.c_float(0)
+    a = [_f(x) for x in (rotation, translation, sampled_unscaled_dpts_0, matched_unscaled_dpts_1, sampled_locations_homo_0,
+                         matched_locations_homo_1)]
+    ctx.check(ctx.lib.sage_ba_loop_mg_error(ctx.h, *[_p(x) for x in a], len(a[2]), float(scale_0), float(scale_1), float(loss_param),
+                                            float(weight), C.byref(err)))
+    return err.value
+
+
 def track_frame(ctx, frame0, kf1, code_0, rotation, translation, scale, photo_weights, dpt_eps=1e-4, max_num_iters=40, init_damp=1e-4,
                 min_damp=1e-6, max_damp=1e-2, damp_dec_factor=10.0, damp_inc_factor=100.0, jac_update_err_inc_threshold=1e-2,
                 min_grad_thresh=1e-8, min_param_inc_thresh=1e-8, matches=None, match_geom_loss_param=1.0, match_geom_weight=0.0,

@@ -63,7 +63,7 @@ def case_args(kfs, i=0, j=1):
     s1 = F32(b.dpt_scale)
     return dict(
         R10=R10, t10=t10, R0=a.pose_wk[0], t0=a.pose_wk[1], R1=b.pose_wk[0], t1=b.pose_wk[1],
-        bias0=a.dpt_map_bias, jac0=a.dpt_jac_code, code0=a.code, code1=b.code, scale0=float(a.dpt_scale),
+        bias0=a.dpt_map_bias, jac0=a.dpt_jac_code, bias1=b.dpt_map_bias, jac1=b.dpt_jac_code, code0=a.code, code1=b.code, scale0=float(a.dpt_scale),
         scale1=float(b.dpt_scale), mask1=b.video_mask, loc1d=a.sampled_locations_1d, homo=a.sampled_locations_homo,
         feat0=a.feat_map_pyramid, feat1=b.feat_map_pyramid, grad1=b.feat_map_grad_pyramid,
         level_offsets=a.level_offsets, cams=cams, eps=EPS, weights=np.array(PHOTO_WEIGHTS[:L], F32),
@@ -110,7 +110,15 @@ def match_args(kfs, M=200):
     py = np.clip(np.round(uv[:, 1]).astype(int), 0, H - 1)
     dpts1 = kfs[1].dpt_map[py, px].astype(F32)
     mg_loss = float(0.03 * np.mean(kfs[0].dpt_map_bias.astype(np.float64) ** 2))
-    return dict(mloc=loc, mhomo=homo, m2d=uv, mdpts=dpts, mhomo1=homo1, mdpts1=dpts1, mg_loss=mg_loss, mg_weight=0.2)
+    # mapping / loop-closure forms: 1-D location of the matched pixel in frame 1 and the UNSCALED depths of both keypoints
+    loc1 = (py * W + px).astype(np.int32)
+    mud0 = (kfs[0].dpt_map_bias[loc] + kfs[0].dpt_jac_code[loc] @ kfs[0].code).astype(F32)
+    mud1 = (kfs[1].dpt_map_bias[loc1] + kfs[1].dpt_jac_code[loc1] @ kfs[1].code).astype(F32)
+    return dict(mloc=loc, mhomo=homo, m2d=uv, mdpts=dpts, mhomo1=homo1, mdpts1=dpts1, mg_loss=mg_loss, mg_weight=0.2, mloc1=loc1,
+                mud0=mud0, mud1=mud1)
+
+
+MG_LOSSES = ("fair", "L2", "huber", "unbiased")
 
 
 def rel_err(a, b):

@@ -53,6 +53,19 @@ def run_oracle(kfs, dtype=np.float32):
     out.update(mgs_AtA=A, mgs_Atb=b, mgs_err=e)
     out["mg_err_only"] = O.tracker_match_geom_error(a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"], ma["mhomo1"],
                                                     ma["mg_loss"], ma["mg_weight"], dtype=dtype)
+    for lt in helpers.MG_LOSSES:
+        A, b, e = O.match_geometry_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["bias0"], a["bias1"], a["jac0"],
+                                             a["jac1"], a["code0"], a["code1"], ma["mhomo"], ma["mhomo1"], ma["mloc"], ma["mloc1"],
+                                             a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"], lt, dtype=dtype)
+        out.update({f"mmg_{lt}_AtA": A, f"mmg_{lt}_Atb": b, f"mmg_{lt}_err": e})
+        out[f"mmg_{lt}_err_only"] = O.match_geometry_error(a["R10"], a["t10"], a["bias0"], a["bias1"], a["jac0"], a["jac1"], a["code0"],
+                                                           a["code1"], ma["mhomo"], ma["mhomo1"], ma["mloc"], ma["mloc1"], a["scale0"],
+                                                           a["scale1"], ma["mg_loss"], ma["mg_weight"], lt, dtype=dtype)
+    A, b, e = O.loop_mg_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], ma["mud0"], ma["mud1"], ma["mhomo"],
+                                  ma["mhomo1"], a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"], dtype=dtype)
+    out.update(lmg_AtA=A, lmg_Atb=b, lmg_err=e)
+    out["lmg_err_only"] = O.loop_mg_error(a["R10"], a["t10"], ma["mud0"], ma["mud1"], ma["mhomo"], ma["mhomo1"], a["scale0"],
+                                          a["scale1"], ma["mg_loss"], ma["mg_weight"], dtype=dtype)
     out["cam_pyramid"] = O.camera_pyramid(a["cam"], a["L"])
     out["sig"] = np.array([float(np.abs(a["feat0"]).sum()), float(np.abs(a["jac0"]).sum()), float(a["R10"].sum()),
                            float(ta["sfeat0"].sum()), float(ma["m2d"].sum())])

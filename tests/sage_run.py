@@ -56,6 +56,19 @@ def run_sage(ctx, kfs):
     out.update(mgs_AtA=A, mgs_Atb=b, mgs_err=e)
     out["mg_err_only"] = ops.tracker_match_geom_error_calculate(ctx, a["R10"], a["t10"], ma["mdpts"], ma["mdpts1"], ma["mhomo"],
                                                                 ma["mhomo1"], ma["mg_loss"], ma["mg_weight"])
+    for lt in helpers.MG_LOSSES:
+        A, b, e = ops.match_geometry_jac_error_calculate(ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["code0"],
+                                                         a["code1"], ma["mhomo"], ma["mhomo1"], ma["mloc"], ma["mloc1"], a["scale0"],
+                                                         a["scale1"], ma["mg_loss"], ma["mg_weight"], lt)
+        out.update({f"mmg_{lt}_AtA": A, f"mmg_{lt}_Atb": b, f"mmg_{lt}_err": e})
+        out[f"mmg_{lt}_err_only"] = ops.match_geometry_error_calculate(ctx, d0, d1, a["R10"], a["t10"], a["code0"], a["code1"], ma["mhomo"],
+                                                                       ma["mhomo1"], ma["mloc"], ma["mloc1"], a["scale0"], a["scale1"],
+                                                                       ma["mg_loss"], ma["mg_weight"], lt)
+    A, b, e = ops.loop_mg_jac_error_calculate(ctx, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], ma["mud0"], ma["mud1"],
+                                              ma["mhomo"], ma["mhomo1"], a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"])
+    out.update(lmg_AtA=A, lmg_Atb=b, lmg_err=e)
+    out["lmg_err_only"] = ops.loop_mg_error_calculate(ctx, a["R10"], a["t10"], ma["mud0"], ma["mud1"], ma["mhomo"], ma["mhomo1"],
+                                                      a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"])
     out["cam_pyramid"] = d0.cameras()[0]
     out["ref_sfeat0"] = ta["sfeat0"]
     out["ref_dpts0"] = ta["dpts0"]

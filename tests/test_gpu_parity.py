@@ -13,7 +13,7 @@ import sage_run
 
 GOLDEN = os.path.join(helpers.ROOT, "tests", "golden")
 TOL = 1e-4
-KEYS = ["photo", "geo", "rep", "trk", "trks", "trkrep", "mg", "mgs"]
+KEYS = ["photo", "geo", "rep", "trk", "trks", "trkrep", "mg", "mgs", "lmg"] + [f"mmg_{lt}" for lt in helpers.MG_LOSSES]
 
 
 def _compare(mine, ref, label):
@@ -54,6 +54,8 @@ def test_kernels_match_reference_golden(sage_ctx, name, far):
     fn = os.path.join(GOLDEN, f"{name}{'_far' if far else ''}.npz")
     assert os.path.exists(fn), "golden fixture missing: run oracle/make_golden.py on a GPU box"
     ref = dict(np.load(fn))
+    for k in KEYS:
+        assert f"{k}_AtA" in ref and f"{k}_err" in ref, f"golden fixture lacks {k}: regenerate with oracle/make_golden.py"
     kfs = helpers.build_case(name, far=far)
     mine = sage_run.run_sage(sage_ctx, kfs)
     _compare(mine, ref, f"{name} far={far} vs reference kernels")

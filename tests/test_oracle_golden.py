@@ -20,6 +20,9 @@ def test_oracle_reproduces_reference_kernels(name, far):
     kfs = helpers.build_case(name, far=far)
     orc = oracle_run.run_oracle(kfs, np.float32)
     np.testing.assert_allclose(orc["sig"], ref["sig"], rtol=1e-6, err_msg="seeded inputs differ from the golden run")
+    for lt in helpers.MG_LOSSES:
+        assert f"mmg_{lt}_AtA" in ref and f"mmg_{lt}_err_only" in ref, "golden fixture predates the match-geometry factors"
+    assert "lmg_AtA" in ref and "lmg_err_only" in ref
     for k, v in ref.items():
         if k in ("sig",):
             continue
