@@ -226,6 +226,27 @@ int sage_ba_loop_mg_error(sage_ba_context *ctx, const float *R10, const float *t
                           float loss_param, float weight, float *error);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense descriptor cycle-matching: the torch expression chain in the
+ * constructors of ReprojectionFactor (core/gtsam/reprojection_factor.cpp:57-92) and
+ * MatchGeometryFactor (core/gtsam/match_geometry_factor.cpp:62-97) and in
+ * CameraTracker::FeatureMatchingGeo (core/system/camera_tracker.cpp:798-834):
+ *   m_k = argmax_p -sum_c (desc0[c, kp_k] - desc1[c, p])^2,   c_k = argmax_p -sum_c (desc1[c, m_k] - desc0[c, p])^2,
+ *   keypoint k is an inlier when |pixel(kp_k) - pixel(c_k)|^2 <= cyc_consis_thresh^2.
+ * feat_desc_{0,1}: [channels, H, W] (Frame::feat_desc, channel-major), HOST or DEVICE per `memory`;
+ * channels in {8, 16, 32, 64}.  keypoint_locations_1d: HOST [K] int64 = valid_locations_1d[keypoint_indexes]
+ * (the reference's mt19937 shuffle stays with the caller).  Outputs (HOST; any may be NULL except num_inliers):
+ *   raw_matched_locations_1d_1 [K], cyc_matched_locations_1d_0 [K],
+ *   inlier_positions [<= K]: positions 0..K-1 of the inlier keypoints in ascending order (torch::nonzero order), so
+ *   matched_keypoint_indexes = keypoint_indexes[inlier_positions], matched_locations_1d_1 = raw[inlier_positions].
+ * kernel_ms: optional, device time of the six launches (CUDA events on the context stream).
+ * Responses are evaluated in fp32 exactly as written above (unfused, channel order), ties keep the lowest pixel index.
+ * ---------------------------------------------------------------------------------------- */
+int sage_ba_cycle_match(sage_ba_context *ctx, int memory, const float *feat_desc_0, const float *feat_desc_1, int channels, int height,
+                        int width, const int64_t *keypoint_locations_1d, int num_keypoints, float cyc_consis_thresh,
+                        int32_t *raw_matched_locations_1d_1, int32_t *cyc_matched_locations_1d_0, int32_t *inlier_positions,
+                        int *num_inliers, float *kernel_ms);
+
+/* ------------------------------------------------------------------------------------------
  * CameraTracker::TrackNewFrame LM loop (core/system/camera_tracker.cpp:1034-1310, loop
  * :1156-1279): damped Gauss-Newton on the 6-DoF relative pose T_ck of `frame1` w.r.t. `kf0`,
  * photometric (+ optional reprojection) terms, same damping / acceptance / convergence rules.

@@ -334,6 +334,51 @@ def loop_mg_error(R10, t10, dpts0, dpts1, homo0, homo1, scale0, scale1, loss_par
 # --------------------------------------------------------------------------------------
 # host-side restatements
 # --------------------------------------------------------------------------------------
+def cycle_match(feat_desc_0, feat_desc_1, keypoint_locations_1d, cyc_consis_thresh, chunk=64):
+    """Dense descriptor cycle-matching, restating core/gtsam/reprojection_factor.cpp:57-92 (identical in
+    match_geometry_factor.cpp:62-97 and camera_tracker.cpp:798-834) expression by expression:
+      response[k, p] = -sum_c square(q[c, k] - desc[c, p])  (fp32; sub, square and the channel sum are separate roundings,
+      channels added in order), argmax over p (first maximum), return pass with the matched descriptors, then the
+      cycle distance test on fmod(loc, W) / floor(loc / W).
+    Keypoints are processed `chunk` at a time only to bound memory; per-element arithmetic is unchanged."""
+    d0 = np.asarray(feat_desc_0, np.float32)
+    d0 = d0.reshape((-1,) + d0.shape[-2:])
+    d1 = np.asarray(feat_desc_1, np.float32).reshape(d0.shape)
+    C, H, W = d0.shape
+    d0 = d0.reshape(C, H * W)
+    d1 = d1.reshape(C, H * W)
+    kp = np.asarray(keypoint_locations_1d, np.int64)
+
+    def best(q, desc):  # q [C, K]
+        out = np.zeros(q.shape[1], np.int64)
+        for k0 in range(0, q.shape[1], chunk):
+            qq = q[:, k0:k0 + chunk]
+            acc = np.zeros((qq.shape[1], desc.shape[1]), np.float32)
+            for c in range(C):
+                d = qq[c][:, None] - desc[c][None, :]
+                acc += d * d
+            out[k0:k0 + chunk] = np.argmax(-acc, axis=1)
+        return out
+
+    raw1 = best(d0[:, kp], d1)
+    cyc0 = best(d1[:, raw1], d0)
+    fw = np.float32(W)
+    kx, ky = np.fmod(kp.astype(np.float32), fw), np.floor(kp.astype(np.float32) / fw)
+    cx, cy = np.fmod(cyc0.astype(np.float32), fw), np.floor(cyc0.astype(np.float32) / fw)
+    dist = np.square(kx - cx) + np.square(ky - cy)
+    sel = np.nonzero(dist <= np.float32(cyc_consis_thresh) * np.float32(cyc_consis_thresh))[0]
+    loc1 = raw1[sel]
+    return {"raw_matched_locations_1d_1": raw1.astype(np.int32), "cyc_matched_locations_1d_0": cyc0.astype(np.int32),
+            "inlier_within_keypoint_indexes": sel.astype(np.int64), "matched_locations_1d_1": loc1.astype(np.int32),
+            "matched_locations_2d_1": np.stack([np.fmod(loc1.astype(np.float32), fw), np.floor(loc1.astype(np.float32) / fw)], 1)}
+
+
+def update_depth(dpt_map_bias, dpt_jac_code, code, dpt_scale):
+    """UpdateDepth (core/mapping/mapping_utils.h:216-222): dpt_map = scale * (bias + jac . code), fp32."""
+    b = np.asarray(dpt_map_bias, np.float32).reshape(-1)
+    return (np.float32(dpt_scale) * (b + np.asarray(dpt_jac_code, np.float32) @ np.asarray(code, np.float32))).astype(np.float32)
+
+
 def camera_pyramid(cam, levels):
     """CameraPyramid<float>(cam, levels): common/camera_pyramid.h:18-32 +
     PinholeCamera::ResizeViewport (common/pinhole_camera_impl.h:120-132).  fp32 arithmetic,

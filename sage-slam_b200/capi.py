@@ -84,6 +84,7 @@ SIGNATURES = {
     "sage_ba_match_geometry_error": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, F, F, vp, vp, vp, vp, C.c_int, F, F, C.c_int, vp]),
     "sage_ba_loop_mg_jac_error": (C.c_int, [vp] + [vp] * 10 + [C.c_int, F, F, F, F, vp, vp, vp]),
     "sage_ba_loop_mg_error": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, F, F, F, F, vp]),
+    "sage_ba_cycle_match": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, F, vp, vp, vp, c_int_p, c_float_p]),
     "sage_ba_track_frame": (C.c_int, [vp, vp, vp, vp, C.POINTER(TrackerConfig), vp, vp, vp, vp, vp, vp, vp, C.c_int,
                                       C.POINTER(TrackerReport)]),
     "sage_ba_track_new_frame": (C.c_int, [vp, vp, vp, vp, F, C.POINTER(TrackerConfig), vp, vp, vp, vp, vp, C.c_int,

@@ -119,6 +119,10 @@ struct sage_ba_context
   sage::DevBuf<float> tmp_code;
   // tracker scratch
   sage::DevBuf<float> trk_dpts, trk_homo, trk_feats, trk_m_dpts, trk_m_homo, trk_m_2d;
+  // descriptor cycle-matching scratch (descriptor.cu)
+  sage::DevBuf<float> dm_maps, dm_float;
+  sage::DevBuf<int> dm_int;
+  sage::PinBuf<int> dm_hint;
 };
 
 struct sage_ba_keyframe

@@ -375,6 +375,39 @@ def loop_mg_error_calculate(ctx, rotation, translation, sampled_unscaled_dpts_0,
     return err.value
 
 
+def cycle_feature_matching(ctx, feat_desc_0, feat_desc_1, keypoint_locations_1d, cyc_consis_thresh, device_ptrs=None, timing=False):
+    """Dense descriptor cycle-matching of the factor constructors / FeatureMatchingGeo
+    (core/gtsam/reprojection_factor.cpp:57-92, core/system/camera_tracker.cpp:798-834).
+
+    feat_desc_{0,1}: [C, H, W] (or [1, C, H, W]) float32, channel-major like Frame::feat_desc.
+    keypoint_locations_1d: [K] = valid_locations_1d[keypoint_indexes].
+    device_ptrs=(ptr0, ptr1, C, H, W): the maps already live on the device (the arrays are then ignored).
+    Returns dict(raw_matched_locations_1d_1 [K], cyc_matched_locations_1d_0 [K], inlier_within_keypoint_indexes [M],
+    matched_locations_1d_1 [M], matched_locations_2d_1 [M,2]) -- names as in the reference -- plus kernel_ms with timing=True."""
+    kp = np.ascontiguousarray(keypoint_locations_1d, dtype=np.int64)
+    K = len(kp)
+    if device_ptrs is None:
+        d0 = _f(feat_desc_0).reshape((-1,) + tuple(np.shape(feat_desc_0)[-2:]))
+        d1 = _f(feat_desc_1).reshape(d0.shape)
+        Cd, H, W = d0.shape
+        p0, p1, mem = _p(d0), _p(d1), capi.HOST
+    else:
+        p0, p1, Cd, H, W = device_ptrs
+        p0, p1, mem = C.c_void_p(p0), C.c_void_p(p1), capi.DEVICE
+    raw, cyc, sel = np.zeros(K, np.int32), np.zeros(K, np.int32), np.zeros(K, np.int32)
+    m, ms = C.c_int(0), C.c_float(0)
+    ctx.check(ctx.lib.sage_ba_cycle_match(ctx.h, mem, p0, p1, int(Cd), int(H), int(W), _p(kp), K, float(cyc_consis_thresh), _p(raw),
+                                          _p(cyc), _p(sel), C.byref(m), C.byref(ms) if timing else None))
+    sel = sel[:m.value].astype(np.int64)
+    loc1 = raw[sel]
+    out = {"raw_matched_locations_1d_1": raw, "cyc_matched_locations_1d_0": cyc, "inlier_within_keypoint_indexes": sel,
+           "matched_locations_1d_1": loc1,
+           "matched_locations_2d_1": np.stack([np.fmod(loc1.astype(F32), F32(W)), np.floor(loc1.astype(F32) / F32(W))], 1)}
+    if timing:
+        out["kernel_ms"] = ms.value
+    return out
+
+
 def track_frame(ctx, frame0, kf1, code_0, rotation, translation, scale, photo_weights, dpt_eps=1e-4, max_num_iters=40, init_damp=1e-4,
                 min_damp=1e-6, max_damp=1e-2, damp_dec_factor=10.0, damp_inc_factor=100.0, jac_update_err_inc_threshold=1e-2,
                 min_grad_thresh=1e-8, min_param_inc_thresh=1e-8, matches=None, match_geom_loss_param=1.0, match_geom_weight=0.0,

@@ -7,6 +7,8 @@ is sin(omega_k . X + phi_k) evaluated at the 3-D surface point X, so warped feat
 between views and LM converges.  Pyramids, gradients, sample points and the depth basis are
 built exactly as the reference builds them (frames.py).
 """
+import os
+
 import numpy as np
 
 from .frames import (F32, Keyframe, camera_pyramid, gaussian_pyramid_with_grad, level_offsets, mask_pyramid,
@@ -90,6 +92,12 @@ def make_scene(num_kf=2, W=128, H=96, L=4, F=16, C=8, num_samples=None, mask="fu
 
         if num_samples is None or num_samples >= len(loc_all):
             loc, homo = loc_all, homo_all
+            tile = os.environ.get("SAGE_SAMPLE_TILE", "")
+            if tile:
+                tw, th = (int(v) for v in tile.split("x"))
+                yy, xx = loc // W, loc % W
+                order = np.lexsort((xx % tw, yy % th, xx // tw, yy // th))
+                loc, homo = loc[order], homo[order]
         else:
             sel = np.sort(np.random.default_rng(seed + 1000 + k).permutation(len(loc_all))[:num_samples])
             loc, homo = loc_all[sel], homo_all[sel]
