@@ -319,6 +319,10 @@ int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses /* [K,12] R
                               const float *codes /* [K,C] */, const float *scales /* [K] */, float eps);
 int sage_ba_problem_get_state(sage_ba_problem *p, float *poses, float *codes, float *scales);
 
+/* Mapper::UpdateMap (core/mapping/mapper.cpp:1141-1180): hand the accepted estimate back to the map.  poses [K,12],
+ * codes [K,C], scales [K] are HOST; dpt_maps [K, H*W] (HOST or DEVICE per `memory`) receives, per keyframe,
+ * UpdateDepth(...) = scale * (dpt_map_bias + dpt_jac_code . code)  (core/mapping/mapping_utils.h:216-222).  Any may be NULL. */
+int sage_ba_problem_update_map(sage_ba_problem *p, float *poses, float *codes, float *scales, float *dpt_maps, int memory);
 int sage_ba_problem_dim(const sage_ba_problem *p);         /* K * (7 + C)                       */
 int sage_ba_problem_num_factors(const sage_ba_problem *p); /* all kinds, priors included        */
 long sage_ba_problem_num_residuals(const sage_ba_problem *p); /* scalar residual rows per linearisation */

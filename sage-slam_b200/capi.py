@@ -101,6 +101,7 @@ SIGNATURES = {
     "sage_ba_problem_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
     "sage_ba_problem_set_state": (C.c_int, [vp, vp, vp, vp, F]),
     "sage_ba_problem_get_state": (C.c_int, [vp, vp, vp, vp]),
+    "sage_ba_problem_update_map": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),
     "sage_ba_problem_dim": (C.c_int, [vp]),
     "sage_ba_problem_num_factors": (C.c_int, [vp]),
     "sage_ba_problem_num_residuals": (C.c_long, [vp]),

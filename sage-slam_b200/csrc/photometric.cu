@@ -112,13 +112,13 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
 #define PH_MINB 3
 #endif
 #ifndef PH_MINB_ERR
-#define PH_MINB_ERR PH_MINB
+#define PH_MINB_ERR 4 // error-only kernels: 128 registers, 16 warps per SM
 #endif
 #ifndef PH_UNROLL
 #define PH_UNROLL 4
 #endif
 #ifndef PH_UNROLL_ERR
-#define PH_UNROLL_ERR PH_UNROLL
+#define PH_UNROLL_ERR 8 // error-only kernels fetch 5 lines per sample-level instead of 13: twice the samples in flight (2.67 -> 2.50 ms)
 #endif
 #define PH_STR2(x) #x
 #define PH_STR(x) PH_STR2(x)

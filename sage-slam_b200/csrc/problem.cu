@@ -152,6 +152,32 @@ __global__ void depth_unscaled_batched_kernel(const KfMaps *maps, const float *c
   m.dscr[p] = __ldg(m.bias + p) + acc;
 }
 
+// UpdateDepth for every keyframe (core/mapping/mapping_utils.h:216-222): dpt_map = scale * (bias + basis . code), in the reference's
+// operation order (GEMV first, then the bias, then the scale).  out: [K][HW]
+__global__ void update_depth_batched_kernel(const KfMaps *maps, const float *codes, const float *scales, int HW, int C, float *out)
+{
+  __shared__ float sc[SAGE_MAX_CODE];
+  const int k = blockIdx.y;
+  if (threadIdx.x < C)
+    sc[threadIdx.x] = codes[k * C + threadIdx.x];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW)
+    return;
+  const KfMaps m = maps[k];
+  float acc = 0.f;
+  const float4 *row = reinterpret_cast<const float4 *>(m.basis + (size_t)p * C);
+  for (int c = 0; c < C / 4; ++c)
+  {
+    const float4 b = __ldg(row + c);
+    acc = fmaf(b.x, sc[4 * c + 0], acc);
+    acc = fmaf(b.y, sc[4 * c + 1], acc);
+    acc = fmaf(b.z, sc[4 * c + 2], acc);
+    acc = fmaf(b.w, sc[4 * c + 3], acc);
+  }
+  out[(size_t)k * HW + p] = scales[k] * (__ldg(m.bias + p) + acc);
+}
+
 __global__ void depth_pack_batched_kernel(const KfMaps *maps, int H, int W)
 {
   const KfMaps m = maps[blockIdx.y];
@@ -385,7 +411,7 @@ struct sage_ba_problem
   DevBuf<int> errpos_d, costpos_d;
   DevBuf<KfMaps> maps_d;
   DevBuf<float> state[2][3]; // [which][poses, codes, scales]
-  DevBuf<float> fbuf, cbuf, partH, partE;
+  DevBuf<float> fbuf, cbuf, partH, partE, depth_out;
   DevBuf<double> Hm, gv, Hd, gd, delta, prior_cost, total_cost, work;
   DevBuf<int> info;
   DevBuf<unsigned char> fixed_d;
@@ -898,6 +924,33 @@ int sage_ba_problem_get_state(sage_ba_problem *p, float *poses, float *codes, fl
   SAGE_CUDA(cudaMemcpyAsync(poses, p->state[0][0].p, sizeof(float) * p->K * 12, cudaMemcpyDeviceToHost, s));
   SAGE_CUDA(cudaMemcpyAsync(codes, p->state[0][1].p, sizeof(float) * p->K * p->C, cudaMemcpyDeviceToHost, s));
   SAGE_CUDA(cudaMemcpyAsync(scales, p->state[0][2].p, sizeof(float) * p->K, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_update_map(sage_ba_problem *p, float *poses, float *codes, float *scales, float *dpt_maps, int memory)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(memory == SAGE_BA_HOST || memory == SAGE_BA_DEVICE, "memory must be SAGE_BA_HOST or SAGE_BA_DEVICE");
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  const size_t HW = (size_t)p->H * p->W;
+  if (poses)
+    SAGE_CUDA(cudaMemcpyAsync(poses, p->state[0][0].p, sizeof(float) * p->K * 12, cudaMemcpyDeviceToHost, s));
+  if (codes)
+    SAGE_CUDA(cudaMemcpyAsync(codes, p->state[0][1].p, sizeof(float) * p->K * p->C, cudaMemcpyDeviceToHost, s));
+  if (scales)
+    SAGE_CUDA(cudaMemcpyAsync(scales, p->state[0][2].p, sizeof(float) * p->K, cudaMemcpyDeviceToHost, s));
+  if (dpt_maps)
+  {
+    float *dst = memory == SAGE_BA_DEVICE ? dpt_maps : p->depth_out.ensure((size_t)p->K * HW);
+    dim3 grid((unsigned)((HW + 255) / 256), p->K);
+    update_depth_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, p->state[0][1].p, p->state[0][2].p, (int)HW, p->C, dst);
+    ctx__->launches++;
+    SAGE_CUDA(cudaGetLastError());
+    if (memory == SAGE_BA_HOST)
+      SAGE_CUDA(cudaMemcpyAsync(dpt_maps, dst, sizeof(float) * p->K * HW, cudaMemcpyDeviceToHost, s));
+  }
   SAGE_CUDA(cudaStreamSynchronize(s));
   SAGE_PCATCH
 }

@@ -120,9 +120,13 @@ class Keyframe:
     sampled_locations_homo: np.ndarray  # [N,3]
     temporal_connections: List[int] = field(default_factory=list)
     pose_wk_true: Optional[tuple] = None
+    feat_desc: Optional[np.ndarray] = None      # [Cd,H,W] descriptor map (Frame::feat_desc, frame.h:86)
+    dpt_map_stored: Optional[np.ndarray] = None  # [H,W] as last written by the mapper's UpdateMap (mapper.cpp:1168)
 
     @property
     def dpt_map(self):
-        """UpdateDepth (mapping_utils.h:216-222): scale * (bias + jac . code), [H,W]."""
+        """Frame::dpt_map: the map UpdateMap stored, else UpdateDepth (mapping_utils.h:216-222) = scale * (bias + jac . code)."""
+        if self.dpt_map_stored is not None:
+            return self.dpt_map_stored
         H, W = self.video_mask.shape
         return (F32(self.dpt_scale) * (self.dpt_map_bias + self.dpt_jac_code @ self.code)).reshape(H, W).astype(F32)

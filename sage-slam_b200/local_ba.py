@@ -154,6 +154,17 @@ class LocalBA:
         self.ctx.check(self.ctx.lib.sage_ba_problem_get_state(self.h, _p(P), _p(c), _p(s)))
         return [(P[k, :9].reshape(3, 3).copy(), P[k, 9:].copy()) for k in range(self.K)], c, s
 
+    def update_map(self, want_depth=True):
+        """Mapper::UpdateMap's payload (mapper.cpp:1141-1180): (poses, codes, scales, dpt_maps [K,HW]); the depth maps are
+        UpdateDepth(...) evaluated on the device for the current estimate."""
+        P = np.zeros((self.K, 12), F32)
+        c = np.zeros((self.K, self.C), F32)
+        s = np.zeros((self.K,), F32)
+        HW = self.kfs[0].H * self.kfs[0].W
+        d = np.zeros((self.K, HW), F32) if want_depth else None
+        self.ctx.check(self.ctx.lib.sage_ba_problem_update_map(self.h, _p(P), _p(c), _p(s), _p(d), capi.HOST))
+        return [(P[k, :9].reshape(3, 3).copy(), P[k, 9:].copy()) for k in range(self.K)], c, s, d
+
     @property
     def dim(self):
         return int(self.ctx.lib.sage_ba_problem_dim(self.h))

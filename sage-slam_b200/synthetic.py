@@ -41,7 +41,7 @@ def _smooth_field(rng, H, W, sigma):
     return f / (f.std() + 1e-12)
 
 
-def make_scene(num_kf=2, W=128, H=96, L=4, F=16, C=8, num_samples=None, mask="full", seed=1234, pose_noise=0.01,
+def make_scene(num_kf=2, W=128, H=96, L=4, F=16, C=8, num_samples=None, mask="full", seed=1234, pose_noise=0.01, with_desc=False,
                step=0.04, rot_step_deg=1.5, back_connections=3):
     """Returns a list of Keyframe (reference layouts, float32).
 
@@ -113,7 +113,8 @@ def make_scene(num_kf=2, W=128, H=96, L=4, F=16, C=8, num_samples=None, mask="fu
             feat_map_pyramid=pyr, feat_map_grad_pyramid=grad, dpt_map_bias=bias, dpt_jac_code=jac,
             code=np.zeros(C, dtype=F32), dpt_scale=1.0, sampled_locations_1d=loc, sampled_locations_homo=homo,
             temporal_connections=[j for j in range(max(0, k - back_connections), k)],
-            pose_wk_true=(R_true.astype(F32), t_true.astype(F32))))
+            pose_wk_true=(R_true.astype(F32), t_true.astype(F32)),
+            feat_desc=feat if with_desc else None))
     return kfs
 
 
