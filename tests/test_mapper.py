@@ -21,8 +21,13 @@ def _scene():
     return kfs
 
 
-def _pose_err(kfs):
-    return float(np.mean([np.linalg.norm(k.pose_wk[1] - k.pose_wk_true[1]) for k in kfs[1:]]))
+def _rot_err_deg(kfs):
+    """largest rotation error against the ground truth (translations are only defined up to the free global depth scale)"""
+    out = 0.0
+    for k in kfs[1:]:
+        c = (np.trace(k.pose_wk[0].astype(np.float64).T @ k.pose_wk_true[0].astype(np.float64)) - 1.0) / 2.0
+        out = max(out, float(np.degrees(np.arccos(np.clip(c, -1.0, 1.0)))))
+    return out
 
 
 def test_keyframe_dpt_map_follows_update_depth():
@@ -52,13 +57,12 @@ def test_mapping_step_and_update_map(sage_ctx):
     assert kinds.count("reproj") == 2 * n_links, mp.match_stats
     assert all(n > 0.5 * K for n, K in mp.match_stats.values()), mp.match_stats  # consistent synthetic views: most keypoints match
     R0, t0 = kfs[0].pose_wk[0].copy(), kfs[0].pose_wk[1].copy()
-    before = _pose_err(kfs)
     rep = mp.mapping_step()
     assert rep["final_cost"] < 0.5 * rep["initial_cost"], rep
     assert rep["accepted"] >= 1
     np.testing.assert_array_equal(kfs[0].pose_wk[0], R0)  # gauge keyframe: pose held
     np.testing.assert_array_equal(kfs[0].pose_wk[1], t0)
-    assert _pose_err(kfs) < before
+    assert _rot_err_deg(kfs) < 1.0
     for kf in kfs:
         want = oracle.update_depth(kf.dpt_map_bias, kf.dpt_jac_code, kf.code, kf.dpt_scale)
         np.testing.assert_allclose(kf.dpt_map.reshape(-1), want, rtol=2e-6, atol=1e-7)
