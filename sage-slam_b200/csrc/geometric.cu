@@ -299,6 +299,21 @@ static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const
   }
 }
 
+// resident CTAs per SM of the kernel the given configuration launches (occupancy API); 0 for an unsupported C
+int geo_ctas_per_sm(bool jac, int C)
+{
+  int n = 0;
+#define SAGE_OCC(CC)                                                                                          \
+  if (C == CC)                                                                                                \
+    jac ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, geo_kernel<CC, true>, GEO_CTA, 0)                 \
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, geo_kernel<CC, false>, GEO_CTA, 0);
+  SAGE_OCC(32)
+  SAGE_OCC(16)
+  SAGE_OCC(8)
+#undef SAGE_OCC
+  return n;
+}
+
 int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, int H, float fx, float fy, float cx, float cy,
                int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream)
 {

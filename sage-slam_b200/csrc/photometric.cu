@@ -611,6 +611,27 @@ static void launch_photo_fc(int mode, const PhotoFactor *factors, int nfactors, 
 int photo_row_width(int mode, int C) { return (mode == PH_MAP_JAC || mode == PH_MAP_ERR) ? 8 + C : 8; }
 int photo_samples_per_cta() { return PH_WARPS * 32; }
 
+// resident CTAs per SM of the kernel the given configuration launches (occupancy API); 0 for an unsupported (F, C)
+int photo_ctas_per_sm(int mode, int F, int C)
+{
+  int n = 0;
+#define SAGE_OCC(FF, CC)                                                                                               \
+  if (F == FF && C == CC)                                                                                              \
+  {                                                                                                                    \
+    if (mode == PH_MAP_JAC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_MAP_JAC>, PH_CTA, 0); \
+    else if (mode == PH_MAP_ERR) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_MAP_ERR>, PH_CTA, 0); \
+    else if (mode == PH_TRK_JAC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_TRK_JAC>, PH_CTA, 0); \
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_TRK_ERR>, PH_CTA, 0);               \
+  }
+  SAGE_OCC(32, 32)
+  SAGE_OCC(16, 16)
+  SAGE_OCC(16, 8)
+  SAGE_OCC(32, 16)
+  SAGE_OCC(16, 32)
+#undef SAGE_OCC
+  return n;
+}
+
 // returns 0 on success, -1 for an unsupported (F, C)
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
                  float *partE, float *out, int out_stride, int D, cudaStream_t stream)

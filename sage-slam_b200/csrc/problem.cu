@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "sage_internal.h"
 
 using namespace sage;
@@ -422,7 +424,7 @@ struct sage_ba_problem
   int solver = 0;          // 0: auto, 1: dense Schur + cuSOLVER, 2: block-banded Cholesky
   bool use_banded = false; // decided at build time
   DevBuf<double> band;
-  int slices_photo = 32, slices_geo = 32;
+  int slices_photo = 32, slices_geo = 32, slices_photo_err = 32, slices_geo_err = 32; // CTAs per factor (linearise / error-only)
 
   sage_ba_allreduce_fn allreduce = nullptr;
   void *allreduce_user = nullptr;
@@ -568,18 +570,42 @@ static void problem_build(sage_ba_problem *p)
   p->cbuf.ensure(std::max<size_t>(p->metas.size() * 2, 4));
   SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf.cap * sizeof(float), s));
   SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->cbuf.cap * sizeof(float), s));
-  // slices: enough CTAs to fill the machine a few times over, but never more steps than samples
-  const int sps_p = 4 * photo_samples_per_cta(), sps_g = (32 / (C / 4)) * (SAGE_CTA / 32);
-  // photometric: 3 CTAs of 4 warps per SM; aim for ~6 waves so the tail is small.  geometric: 2 CTAs of 8 warps per SM.
-  const int target_p = 18 * ctx->num_sms, target_g = 8 * ctx->num_sms;
-  p->slices_photo = std::max(1, std::min((p->N + sps_p - 1) / sps_p, std::max(4, target_p / std::max(1, p->n_photo))));
-  p->slices_geo = std::max(1, std::min((p->N + sps_g - 1) / sps_g, std::max(4, target_g / std::max(1, p->n_geo))));
-  p->slices_photo = std::min(p->slices_photo, 128);
-  p->slices_geo = std::min(p->slices_geo, 64);
+  // slices = CTAs per factor.  The factor kernels run a handful of waves, so the count is chosen to END on a full wave:
+  // slices = floor(waves * resident_CTAs / factors) for the largest wave count that still leaves every CTA a few thousand
+  // samples (per-CTA cost: factor load, partial store, one more partial for the finalize kernel).  Measured on B200,
+  // 32 KF / 180 pairs: photometric linearisation 7.41 ms at 14 slices (5.7 waves) vs 7.19 ms at 12 (4.9 waves); error pass
+  // 2.51 -> 2.24 ms at 16; geometric 3.00 -> 2.60 ms at 46 (7.0 waves instead of 0.9).
+  auto pick = [&](int nfac, int ctas_per_sm, int max_waves, int min_samples_per_cta) {
+    if (nfac <= 0)
+      return 1;
+    const int slots = std::max(1, ctas_per_sm) * ctx->num_sms;
+    const int cap = std::max(1, p->N / std::max(1, min_samples_per_cta));
+    for (int w = max_waves; w >= 1; --w)
+    {
+      const int sl = w * slots / nfac;
+      if (sl >= 1 && sl <= cap)
+        return sl;
+    }
+    return std::max(1, std::min(cap, slots / nfac));
+  };
+  p->slices_photo = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_JAC, p->F, C), 5, 2048);
+  p->slices_photo_err = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_ERR, p->F, C), 5, 2048);
+  p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C), 7, 1024);
+  p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C), 8, 512);
+  // tuning aid: override the heuristics above
+  if (const char *e = getenv("SAGE_BA_SLICES_PHOTO"))
+    p->slices_photo = std::max(1, atoi(e));
+  if (const char *e = getenv("SAGE_BA_SLICES_GEO"))
+    p->slices_geo = std::max(1, atoi(e));
+  if (const char *e = getenv("SAGE_BA_SLICES_PHOTO_ERR"))
+    p->slices_photo_err = std::max(1, atoi(e));
+  if (const char *e = getenv("SAGE_BA_SLICES_GEO_ERR"))
+    p->slices_geo_err = std::max(1, atoi(e));
   const int WPp = 8 + C, WPg = 16 + 2 * C;
   const size_t nh = std::max((size_t)p->n_photo * p->slices_photo * WPp * WPp, (size_t)p->n_geo * p->slices_geo * WPg * WPg);
   p->partH.ensure(std::max<size_t>(nh, 4));
-  p->partE.ensure(std::max<size_t>(2 * std::max((size_t)p->n_photo * p->slices_photo, (size_t)p->n_geo * p->slices_geo), 4));
+  p->partE.ensure(std::max<size_t>(2 * std::max((size_t)p->n_photo * std::max(p->slices_photo, p->slices_photo_err),
+                                                 (size_t)p->n_geo * std::max(p->slices_geo, p->slices_geo_err)), 4));
   p->Hm.ensure((size_t)n * n);
   p->Hd.ensure((size_t)n * n);
   p->gv.ensure(n);
@@ -640,7 +666,7 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
   if (p->n_photo)
   {
     ProfScope ps(p, jac ? SAGE_BA_PROF_PHOTO_JAC : SAGE_BA_PROF_PHOTO_ERR);
-    SAGE_CHECK(launch_photo(jac ? PH_MAP_JAC : PH_MAP_ERR, p->F, p->C, p->photo_d.p, p->n_photo, k0->pyr, p->slices_photo, p->partH.p,
+    SAGE_CHECK(launch_photo(jac ? PH_MAP_JAC : PH_MAP_ERR, p->F, p->C, p->photo_d.p, p->n_photo, k0->pyr, jac ? p->slices_photo : p->slices_photo_err, p->partH.p,
                             p->partE.p, out, 1, 13 + p->C, s) == 0,
                "unsupported (feat_channels, code_size)");
     ctx->launches += 2;
@@ -649,7 +675,7 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
   {
     const sage_ba_camera &cam = k0->cams[0];
     ProfScope ps(p, jac ? SAGE_BA_PROF_GEO_JAC : SAGE_BA_PROF_GEO_ERR);
-    SAGE_CHECK(launch_geo(jac, p->C, p->geo_d.p, p->n_geo, p->W, p->H, cam.fx, cam.fy, cam.u0, cam.v0, p->slices_geo, p->partH.p,
+    SAGE_CHECK(launch_geo(jac, p->C, p->geo_d.p, p->n_geo, p->W, p->H, cam.fx, cam.fy, cam.u0, cam.v0, jac ? p->slices_geo : p->slices_geo_err, p->partH.p,
                           p->partE.p, out, 1, s) == 0,
                "unsupported code_size");
     ctx->launches += 2;

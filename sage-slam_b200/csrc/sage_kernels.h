@@ -10,11 +10,13 @@ enum { PH_MAP_JAC = 0, PH_MAP_ERR = 1, PH_TRK_JAC = 2, PH_TRK_ERR = 3 };
 // photometric.cu
 int photo_row_width(int mode, int C);
 int photo_samples_per_cta();
+int photo_ctas_per_sm(int mode, int F, int C);
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
                  float *partE, float *out, int out_stride, int D, cudaStream_t stream);
 
 // geometric.cu
 int geo_row_width(int C);
+int geo_ctas_per_sm(bool jac, int C);
 int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, int H, float fx, float fy, float cx, float cy,
                int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream);
 
