@@ -309,8 +309,10 @@ int sage_ba_problem_add_code_prior(sage_ba_problem *p, int kf, const float *init
 int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale, float weight);
 /* hold a keyframe's pose (and optionally scale) fixed: the gauge anchor (mapper.cpp:190-192) */
 int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale);
-/* linear solver: 0 auto, 1 dense Schur complement onto the pose block (cuSOLVER), 2 block-banded Cholesky over keyframes
- * (chain-shaped covisibility only; one launch, but slower than 1 on a B200 at K = 32 -- opt-in).  Auto = 1. */
+/* linear solver: 0 auto = Schur complement onto the pose block fused into one Cholesky factorisation (the code+scale block is
+ * ordered first, so cuSOLVER potrf eliminates it, forms S in the trailing 6K x 6K block and factors it; 3 launches);
+ * 1 the same elimination as explicit steps (potrf H_cc, trsm, syrk, potrf S; ~40 launches, kept as a cross-check);
+ * 2 block-banded Cholesky over keyframes (chain-shaped covisibility only; one launch, slower on a B200 at K = 32 -- opt-in). */
 int sage_ba_problem_set_solver(sage_ba_problem *p, int solver);
 /* restrict this process to the factors with index % world == rank (multi-GPU sharding) */
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);

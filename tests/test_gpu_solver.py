@@ -211,13 +211,14 @@ def test_banded_cholesky_equals_dense_schur(sage_ctx, num_kf):
     solve the same damped system: identical steps to fp64 round-off, for several damping values."""
     kfs, pairs, _ = pc.build(num_kf)
     sols = {}
-    for solver in ("schur", "banded"):
+    for solver in ("auto", "schur", "banded"):
         ba, _ = make_ba(sage_ctx, kfs, pairs, solver=solver)
         ba.linearize()
         ba.assemble()
         sols[solver] = [ba.solve(d, want_delta=True) for d in (1e-4, 1e-2, 1.0)]
-    for a, b in zip(sols["schur"], sols["banded"]):
+    for a, b, c in zip(sols["schur"], sols["banded"], sols["auto"]):
         assert np.abs(a - b).max() <= 1e-8 * max(1.0, np.abs(a).max())
+        assert np.abs(a - c).max() <= 1e-8 * max(1.0, np.abs(a).max())  # fused (one potrf) == explicit Schur steps
         assert np.abs(a).max() > 0
 
 
