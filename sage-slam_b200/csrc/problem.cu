@@ -237,35 +237,33 @@ __global__ void priors_kernel(const PriorSpec *pr, int np, const float *codes, c
 {
   __shared__ double red[256];
   double cost = 0.0;
-  for (int q = 0; q < np; ++q)
+  // one (prior, component) pair per thread step; priors on the same variable may coexist, hence the atomics
+  for (int e = threadIdx.x; e < np * C; e += blockDim.x)
   {
+    const int q = e / C, c = e - q * C;
     const PriorSpec &p = pr[q];
     const int cb = 6 * K + p.kf * (C + 1);
     if (p.kind == 0)
     {
-      for (int c = threadIdx.x; c < C; c += blockDim.x)
+      const double diff = (double)p.init_code[c] - (double)codes[p.kf * C + c];
+      cost += (double)p.weight * diff * diff / (double)C;
+      if (add_to_system)
       {
-        const double diff = (double)p.init_code[c] - (double)codes[p.kf * C + c];
-        cost += (double)p.weight * diff * diff / (double)C;
-        if (add_to_system)
-        {
-          H[(size_t)(cb + c) * n + cb + c] += (double)p.weight;
-          g[cb + c] += (double)p.weight * diff;
-        }
+        atomicAdd(&H[(size_t)(cb + c) * n + cb + c], (double)p.weight);
+        atomicAdd(&g[cb + c], (double)p.weight * diff);
       }
     }
-    else if (threadIdx.x == 0)
+    else if (c == 0)
     {
       const double s = (double)scales[p.kf];
       const double d = log((double)p.init_scale) - log(s);
       cost += (double)p.weight * d * d;
       if (add_to_system)
       {
-        H[(size_t)(cb + C) * n + cb + C] += (double)p.weight / (s * s);
-        g[cb + C] += (double)p.weight / s * d;
+        atomicAdd(&H[(size_t)(cb + C) * n + cb + C], (double)p.weight / (s * s));
+        atomicAdd(&g[cb + C], (double)p.weight / s * d);
       }
     }
-    __syncthreads();
   }
   red[threadIdx.x] = cost;
   __syncthreads();

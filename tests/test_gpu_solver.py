@@ -259,3 +259,41 @@ def test_track_frame_7dof_matches_oracle_lm(sage_ctx):
     assert abs(rep["final_error"] - eo) / eo <= 1e-4
     assert np.abs(t - to).max() <= 1e-5 and np.abs(R - Ro).max() <= 1e-5 and abs(s - so) <= 1e-5
     assert rep["final_error"] < err(a["R10"], a["t10"], s0)
+
+
+def _graph(kind, K, seed=5):
+    """Ordered pairs of BASELINE configs[2] (full covisibility) and configs[4] (sparse graph, average degree ~4 here)."""
+    if kind == "full":
+        return [(i, j) for i in range(K) for j in range(K) if i != j]
+    rng = np.random.default_rng(seed)
+    und = {(i, i + 1) for i in range(K - 1)}  # connected backbone, then random long-range links (loop closures)
+    while len(und) < 2 * K:
+        i, j = sorted(rng.choice(K, 2, replace=False))
+        und.add((int(i), int(j)))
+    return [p for (i, j) in sorted(und) for p in ((i, j), (j, i))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,K", [("full", 6), ("sparse", 10)])
+def test_full_and_sparse_covisibility_graphs_match_dense_oracle(sage_ctx, kind, K):
+    """The same kernels / assembly / fused-Schur solve on the other covisibility shapes BASELINE names: every ordered pair
+    (configs[2]) and a sparse graph with long-range links (configs[4]); photometric + geometric + reprojection on every pair."""
+    kfs, _, _ = pc.build(K)
+    pairs = _graph(kind, K)
+    factors = [("photo", i, j) for i, j in pairs] + [("geo", i, j) for i, j in pairs] + [("reproj", i, j) for i, j in pairs]
+    C = pc.PRM["C"]
+    ba, _ = make_ba(sage_ctx, kfs, pairs)
+    ba.linearize()
+    H, g, cost = ba.assemble(want_matrix=True)
+    buf = pc.oracle_buffer(kfs, factors)
+    Ho, go, co = local_ba.assemble_dense(buf, factors, K, C)
+    co += pc.add_priors_dense(Ho, go, kfs)
+    assert helpers.rel_err(ba.factor_buffer(), buf) <= 1e-4
+    assert helpers.rel_err(H, Ho) <= 1e-4 and helpers.rel_err(g, go) <= 1e-4
+    assert abs(cost - co) / co <= 1e-4
+    fixed = list(range(6)) + [6 * K + C]
+    d_gpu = ba.solve(1e-3, want_delta=True)
+    d_same = pc.solve_dense(H, g, 1e-3, fixed)
+    assert np.abs(d_gpu - d_same).max() <= 1e-9 * max(1.0, np.abs(d_same).max())
+    rep = ba.lm(max_iters=4)
+    assert rep["final_cost"] < rep["initial_cost"]
