@@ -247,7 +247,7 @@ def run_ours(args):
         achieved = shard["photo"] * b_photo / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         traffic = None
         try:  # DRAM bytes of the same launch from the committed ncu --set full capture (scaled to this rank's pair count)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["photo_jac"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))["photo_jac"]
             traffic = tj["dram_bytes_per_launch"] / tj["pairs_per_launch"] * shard["photo"]
         except Exception:
             pass
@@ -274,7 +274,7 @@ def run_ours(args):
         }
         if tracker is not None:
             line["config2_tracker"] = tracker
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only: torchrun pins OMP_NUM_THREADS=1
             line["cpu_baseline"] = cpu_baseline(wl, kfs, pairs, len(pairs))
         print(json.dumps(line))
     if world > 1:
@@ -470,6 +470,12 @@ def main():
     ap.add_argument("--no-tracker", action="store_true", help="skip the configs[1] tracker latency measurement")
     ap.add_argument("--ref-samples", type=int, default=0, help="reference-gpu: sub-sample N points per keyframe (0 = dense)")
     args = ap.parse_args()
+    # stdout must carry exactly one JSON line: native libraries (NCCL's version banner, cuSOLVER notes) write to fd 1 behind
+    # Python's back, so fd 1 is pointed at stderr and Python's own sys.stdout keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_cpu(args)

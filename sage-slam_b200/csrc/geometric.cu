@@ -236,7 +236,7 @@ __global__ void geo_finalize_kernel(const GeoFactor *__restrict__ factors, int s
   __syncthreads();
   const float n = s_n;
   const int base = JAC ? D * D + D : 0;
-  if (threadIdx.x == 0)
+  if (threadIdx.x == 0 && blockIdx.y == 0)
   {
     o[base + 0] = s_e;
     o[base + 1] = n;
@@ -256,7 +256,8 @@ __global__ void geo_finalize_kernel(const GeoFactor *__restrict__ factors, int s
       }
       return c < 12 + 2 * C ? 16 + (c - 12) : 6 + (c - 12 - 2 * C);
     };
-    for (int e = threadIdx.x; e < D * D + D; e += blockDim.x)
+    // grid.y CTAs share the elements of one factor (the slice partials are 180 x slices x WP^2 floats: keep the machine busy)
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < D * D + D; e += blockDim.x * gridDim.y)
     {
       float sr, scn = 1.f;
       int r, c;
@@ -290,7 +291,7 @@ static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const
   if (jac)
   {
     geo_kernel<C, true><<<grid, GEO_CTA, 0, stream>>>(factors, cam, partH, partE);
-    geo_finalize_kernel<C, true><<<nfactors, 256, 0, stream>>>(factors, slices, partH, partE, out, out_stride);
+    geo_finalize_kernel<C, true><<<dim3(nfactors, 6), 256, 0, stream>>>(factors, slices, partH, partE, out, out_stride);
   }
   else
   {
