@@ -189,25 +189,7 @@ static void launch_response_any(int CD, const float *desc, const float *q, int K
 
 } // namespace sage
 
-#define SAGE_TRY(ctx_) \
-  sage_ba_context *ctx__ = (ctx_); \
-  try                  \
-  {
-#define SAGE_CATCH                    \
-  }                                   \
-  catch (const sage::Error &e)        \
-  {                                   \
-    if (ctx__)                        \
-      ctx__->err = e.msg;             \
-    return 1;                         \
-  }                                   \
-  catch (const std::exception &e)     \
-  {                                   \
-    if (ctx__)                        \
-      ctx__->err = e.what();          \
-    return 1;                         \
-  }                                   \
-  return 0;
+
 
 using namespace sage;
 

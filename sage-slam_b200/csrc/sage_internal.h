@@ -141,3 +141,25 @@ struct sage_ba_keyframe
   float4 *dgm = nullptr;  // [HW] (D, dx, dy, mask) for the geometric factor, state dependent
   float *dscr = nullptr;  // [HW] scratch
 };
+
+// Every extern "C" entry point wraps its body in SAGE_TRY(ctx) ... SAGE_CATCH: exceptions become a non-zero return code
+// and the message is kept in the context for sage_ba_last_error().
+#define SAGE_TRY(ctx_) \
+  sage_ba_context *ctx__ = (ctx_); \
+  try                  \
+  {
+#define SAGE_CATCH                                   \
+  }                                                  \
+  catch (const sage::Error &e)                       \
+  {                                                  \
+    if (ctx__)                                       \
+      ctx__->err = e.msg;                            \
+    return 1;                                        \
+  }                                                  \
+  catch (const std::exception &e)                    \
+  {                                                  \
+    if (ctx__)                                       \
+      ctx__->err = e.what();                         \
+    return 1;                                        \
+  }                                                  \
+  return 0;
