@@ -37,9 +37,6 @@ namespace sage
 #ifndef PH_HALF
 #define PH_HALF 0
 #endif
-#ifndef PH_REUSE
-#define PH_REUSE 0
-#endif
 constexpr int PH_WARPS = PH_NWARPS;
 constexpr int PH_CTA = PH_WARPS * 32;
 
@@ -249,97 +246,24 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
                  (selB[k] == 1 ? cam.fx[l] : selB[k] == 2 ? cam.fy[l] : 1.f);
 
       // -------------------------------------------------------------- lane == channel quad: gathers
-#if PH_REUSE
-      // Tap window.  A group walks LPG consecutive samples whose warped positions advance by ~2^-l pixels at level l, so a
-      // sample's 2x2 cell is usually the previous sample's cell or its right-hand neighbour.  The group keeps two pixel
-      // columns (top, bottom) x (feature, d/dx, d/dy) in registers, A and B; when the cell moves one pixel to the right only
-      // the column that fell out is re-fetched and the roles of A and B swap (the swap is applied to the four weights, not
-      // to the data).  Which column to fetch is decided once per sample with lane == sample (below); the fetches are
-      // predicated loads, so the four groups of a warp never diverge.  Lines per sample-level drop from 12 to about
-      // 6.8 / 4.1 / 2.8 / 2.2 at levels 0..3 for raster-ordered samples; any other order just re-fetches (still correct).
-      int pkA, offB;
-      float wq[4];
-      {
-        const int ci = lane % LPG;
-        const int ppk = __shfl_up_sync(0xffffffffu, t1.pk, 1);
-        const bool same = ci != 0 && t1.pk == ppk;
-        const bool shift = ci != 0 && !same && ((t1.pk ^ ppk) & 3) == 0 && (t1.pk & 2) != 0 && ((t1.pk & ~3) - (ppk & ~3)) == 3 * F;
-        const bool fullld = !same && !shift;
-        int par = 0; // 0: A = west column, B = east column ; 1: swapped
-#pragma unroll
-        for (int k = 1; k < LPG; ++k)
-        {
-          const int pp = __shfl_up_sync(0xffffffffu, par, 1);
-          if (ci == k)
-            par = fullld ? 0 : (pp ^ (shift ? 1 : 0));
-        }
-        const int base = t1.pk & ~3, east = base + ((t1.pk & 2) ? 3 * F : 0);
-        const bool needA = fullld || (shift && par != 0), needB = fullld || (shift && par == 0);
-        pkA = (par ? east : base) | (t1.pk & 1) | (needA ? 2 : 0) | (needB ? 4 : 0);
-        offB = par ? base : east;
-        // combine order (A top, B bottom, A bottom, B top) = (nw, se, sw, ne) or, swapped, (ne, sw, se, nw)
-        wq[0] = par ? t1.w[3] : t1.w[0];
-        wq[1] = par ? t1.w[2] : t1.w[1];
-        wq[2] = par ? t1.w[1] : t1.w[2];
-        wq[3] = par ? t1.w[0] : t1.w[3];
-      }
-      float4 wF[4], wX[4], wY[4]; // (A top, B bottom, A bottom, B top)
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        wF[k] = wX[k] = wY[k] = f4zero();
-#endif
 #pragma unroll kUnroll
       for (int i = 0; i < LPG; ++i)
       {
         const int src = q * LPG + i;
-#if PH_REUSE
-        TapSet s1;
-        const int spk = __shfl_sync(0xffffffffu, pkA, src);
-        const int sob = __shfl_sync(0xffffffffu, offB, src);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          s1.w[k] = __shfl_sync(0xffffffffu, wq[k], src);
-        const float *pAt = fg1 + (spk & ~7), *pBt = fg1 + sob;
-        const int dyo = (spk & 1) ? rowo : 0;
-        const float *pAb = pAt + dyo, *pBb = pBt + dyo;
-        const int nA = spk & 2, nB = spk & 4;
-        ldg4_if(wF[0], pAt, nA);
-        ldg4_if(wF[2], pAb, nA);
-        ldg4_if(wF[3], pBt, nB);
-        ldg4_if(wF[1], pBb, nB);
-        if constexpr (T::kJac)
-        {
-          ldg4_if(wX[0], pAt + F, nA);
-          ldg4_if(wX[2], pAb + F, nA);
-          ldg4_if(wX[3], pBt + F, nB);
-          ldg4_if(wX[1], pBb + F, nB);
-          ldg4_if(wY[0], pAt + 2 * F, nA);
-          ldg4_if(wY[2], pAb + 2 * F, nA);
-          ldg4_if(wY[3], pBt + 2 * F, nB);
-          ldg4_if(wY[1], pBb + 2 * F, nB);
-        }
-        const float4 f1 = combine4(wF, s1.w);
-#else
         const TapSet s1 = shfl_tapset(t1, src);
         const float *pnw = fg1 + (s1.pk & ~3);
         const float *pne = pnw + ((s1.pk & 2) ? 3 * F : 0);
         const float *psw = pnw + ((s1.pk & 1) ? rowo : 0);
         const float *pse = psw + ((s1.pk & 2) ? 3 * F : 0);
         const float4 f1 = gather4(pnw, pse, psw, pne, s1.w);
-#endif
         const int ns = min(batch * 32 + src, N - 1);
         const float4 f0 = ldg4(sf0 + (size_t)ns * F);
         const float dfx = f0.x - f1.x, dfy = f0.y - f1.y, dfz = f0.z - f1.z, dfw = f0.w - f1.w;
         const float e = dfx * dfx + dfy * dfy + dfz * dfz + dfw * dfw;
         if constexpr (T::kJac)
         {
-#if PH_REUSE
-          const float4 gx = combine4(wX, s1.w);
-          const float4 gy = combine4(wY, s1.w);
-#else
           const float4 gx = gather4(pnw + F, pse + F, psw + F, pne + F, s1.w);
           const float4 gy = gather4(pnw + 2 * F, pse + 2 * F, psw + 2 * F, pne + 2 * F, s1.w);
-#endif
           float v[8];
           v[0] = gx.x * gx.x + gx.y * gx.y + gx.z * gx.z + gx.w * gx.w;
           v[1] = gx.x * gy.x + gx.y * gy.y + gx.z * gy.z + gx.w * gy.w;

@@ -209,25 +209,6 @@ __device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
   return r;
 }
 
-// predicated 16-byte read-only load: v is left untouched when pred == 0 (no branch, so sub-warp groups never diverge)
-__device__ __forceinline__ void ldg4_if(float4 &v, const float *p, int pred)
-{
-  asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(p), "r"(pred));
-}
-
-// weighted sum of four already-fetched taps v[] = (nw, se, sw, ne), same operation order as gather4
-__device__ __forceinline__ float4 combine4(const float4 (&v)[4], const float *w)
-{
-  float4 r;
-  r.x = v[0].x * w[0] + v[1].x * w[1] + v[2].x * w[2] + v[3].x * w[3];
-  r.y = v[0].y * w[0] + v[1].y * w[1] + v[2].y * w[2] + v[3].y * w[3];
-  r.z = v[0].z * w[0] + v[1].z * w[1] + v[2].z * w[2] + v[3].z * w[3];
-  r.w = v[0].w * w[0] + v[1].w * w[1] + v[2].w * w[2] + v[3].w * w[3];
-  return r;
-}
-
 // 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
 __device__ __forceinline__ float4 gather4(const float *pnw, const float *pse, const float *psw, const float *pne, const float *w)
 {
