@@ -1,0 +1,589 @@
+// df_sage_shim.cpp -- the reference's `df::*_calculate` symbols implemented on top of the C ABI of include/sage_ba.h.
+//
+// This is the binding INTEGRATION.md describes: a maintainer of the reference replaces the four translation units of the
+// static library df_cuda (system/sources/cuda/CMakeLists.txt:37-46) by this file and links libsage_ba.so; the reference's
+// headers (cuda/*_factor_kernels.h) stay untouched, so core/gtsam/*_factor.cpp and core/system/camera_tracker.cpp compile
+// and link unchanged.  It is compiled here against those headers (oracle/build_ref.py, only where /root/reference exists)
+// together with the same pybind front that drives the reference's own kernels, and tests/test_shim_dropin.py holds its
+// outputs to the reference goldens -- the df:: boundary itself is under test, not only the C ABI below it.
+//
+// Every reference operator receives only a PART of each frame (the photometric one sees KF0's features, depth and samples
+// and KF1's features, gradients and mask), so the shim builds partial sage_ba keyframes from the tensors of the call and
+// caches them by the identity (data pointers) of those tensors; in the live system the cache is filled once per frame
+// (INTEGRATION.md section 2).  CUDA errors keep the reference's behaviour: message on stderr and exit()
+// (cuda/photometric_factor_kernels.cpp:23-31).
+#include <c10/cuda/CUDAStream.h>
+#include <torch/torch.h>
+
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "geometric_factor_kernels.h"
+#include "match_geometry_factor_kernels.h"
+#include "photometric_factor_kernels.h"
+#include "reprojection_factor_kernels.h"
+#include "sage_ba.h"
+
+namespace
+{
+
+sage_ba_context *ctx()
+{
+  // one context per calling thread (the reference is entered from up to four, core/deepfactors.cpp:1497-1505),
+  // running on torch's current stream so that the call is ordered after the producers of its input tensors
+  thread_local sage_ba_context *c = nullptr;
+  if (!c)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sage_ba_create(&c, dev, c10::cuda::getCurrentCUDAStream(dev).stream()) != 0)
+    {
+      fprintf(stderr, "sage_ba_create failed\n");
+      exit(1);
+    }
+  }
+  // the reference's operators are synchronous; when torch's current stream is the legacy default stream the context runs
+  // on a private stream, so wait here for whatever produced the input tensors
+  cudaStreamSynchronize(c10::cuda::getCurrentCUDAStream().stream());
+  return c;
+}
+
+#define SAGE_OK(call)                                                         \
+  do                                                                          \
+  {                                                                           \
+    if ((call) != 0)                                                          \
+    {                                                                         \
+      fprintf(stderr, "sage_ba: %s (%s)\n", sage_ba_last_error(ctx()), #call); \
+      exit(1);                                                                \
+    }                                                                         \
+  } while (0)
+
+// small state tensors (poses, codes, weights, match arrays) -> contiguous host float / int32
+std::vector<float> hostf(const at::Tensor &t)
+{
+  const at::Tensor c = t.to(at::kCPU, at::kFloat).contiguous();
+  return std::vector<float>(c.data_ptr<float>(), c.data_ptr<float>() + c.numel());
+}
+std::vector<int32_t> hosti(const at::Tensor &t)
+{
+  const at::Tensor c = t.to(at::kCPU, at::kInt).contiguous();
+  return std::vector<int32_t>(c.data_ptr<int32_t>(), c.data_ptr<int32_t>() + c.numel());
+}
+
+struct KfDeleter
+{
+  sage_ba_context *c;
+  void operator()(sage_ba_keyframe *k) const { sage_ba_keyframe_destroy(c, k); }
+};
+using KfPtr = std::shared_ptr<sage_ba_keyframe>;
+using KfKey = std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, long>;
+// Heap objects that are never destroyed: at process exit torch and the CUDA context may already be gone.
+std::map<KfKey, KfPtr> &g_cache = *new std::map<KfKey, KfPtr>();
+std::vector<at::Tensor> &g_keep = *new std::vector<at::Tensor>(); // source tensors stay alive, so a pointer is never reused
+std::mutex g_mutex;
+
+struct FrameView
+{
+  // any subset of a frame's tensors, as the reference operators receive them
+  at::Tensor feat_pyramid, grad_pyramid, bias, jac, mask, loc1d, homo;
+};
+
+KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int levels, int F, int C, bool cache = true)
+{
+  auto ptr = [](const at::Tensor &t) -> const void * { return t.defined() ? t.data_ptr() : nullptr; };
+  const KfKey key{ptr(v.feat_pyramid), ptr(v.grad_pyramid), ptr(v.bias), ptr(v.jac), ptr(v.mask), ptr(v.loc1d),
+                  v.homo.defined() ? (long)v.homo.size(0) : 0};
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (cache)
+  {
+    auto it = g_cache.find(key);
+    if (it != g_cache.end())
+      return it->second;
+  }
+  sage_ba_keyframe_desc d{};
+  d.memory = SAGE_BA_DEVICE;
+  d.height = (int)cam0.height();
+  d.width = (int)cam0.width();
+  d.levels = levels;
+  d.feat_channels = F;
+  d.code_size = C;
+  d.camera = {cam0.fx(), cam0.fy(), cam0.u0(), cam0.v0(), cam0.width(), cam0.height()};
+  std::vector<at::Tensor> keep;
+  auto cf = [&](const at::Tensor &t) -> const float * {
+    if (!t.defined())
+      return nullptr;
+    keep.push_back(t.to(at::kFloat).contiguous());
+    return keep.back().data_ptr<float>();
+  };
+  d.feat_map_pyramid = cf(v.feat_pyramid);
+  d.feat_map_grad_pyramid = cf(v.grad_pyramid);
+  d.dpt_map_bias = cf(v.bias);
+  d.video_mask = cf(v.mask);
+  if (v.jac.defined())
+  {
+    // the depth basis arrives as a strided [HW, C] view of the network's [C, H, W] output (code_depth_network.cpp:38-39)
+    keep.push_back(v.jac);
+    d.dpt_jac_code = v.jac.data_ptr<float>();
+    d.jac_stride_row = v.jac.stride(0);
+    d.jac_stride_col = v.jac.stride(1);
+  }
+  if (v.homo.defined())
+  {
+    d.sampled_locations_homo = cf(v.homo);
+    d.num_samples = (int)v.homo.size(0);
+    if (v.loc1d.defined())
+    {
+      // int64 in the photometric path, already cast to int32 by the geometric / reprojection callers (geometric_factor.cpp:344)
+      keep.push_back(v.loc1d.to(at::kLong).contiguous());
+      d.sampled_locations_1d = keep.back().data_ptr<int64_t>();
+    }
+  }
+  sage_ba_keyframe *kf = nullptr;
+  sage_ba_context *c = ctx();
+  SAGE_OK(sage_ba_keyframe_create(c, &d, &kf));
+  KfPtr out(kf, KfDeleter{c});
+  if (cache)
+  {
+    g_cache[key] = out;
+    for (const at::Tensor *t : {&v.feat_pyramid, &v.grad_pyramid, &v.bias, &v.jac, &v.mask, &v.loc1d, &v.homo})
+      if (t->defined())
+        g_keep.push_back(*t);
+  }
+  return out;
+}
+
+at::Tensor to_dev(const float *p, std::vector<int64_t> shape, const at::Tensor &like)
+{
+  return torch::from_blob(const_cast<float *>(p), shape, at::kFloat).clone().to(like.device());
+}
+
+int loss_type(const std::string &s)
+{
+  if (s == "fair")
+    return SAGE_BA_LOSS_FAIR;
+  if (s == "L2")
+    return SAGE_BA_LOSS_L2;
+  if (s == "huber")
+    return SAGE_BA_LOSS_HUBER;
+  if (s == "unbiased")
+    return SAGE_BA_LOSS_UNBIASED;
+  fprintf(stderr, "sage_ba: unknown robust loss type %s\n", s.c_str());
+  exit(1);
+}
+
+sage_ba_camera cam_of(const df::PinholeCamera<float> &c) { return {c.fx(), c.fy(), c.u0(), c.v0(), c.width(), c.height()}; }
+
+} // namespace
+
+namespace df
+{
+
+// ------------------------------------------------------------------------------------------------ photometric
+template <int FS>
+float photometric_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor flatten_dpt_map_bias_0,
+                                  const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0, const at::Tensor valid_mask_1,
+                                  const at::Tensor sampled_locations_1d_0, const at::Tensor sampled_locations_homo_0,
+                                  const at::Tensor feat_map_pyramid_0, const at::Tensor feat_map_pyramid_1, const at::Tensor level_offsets,
+                                  const float scale_0, const CameraPyramid<float> &camera_pyramid, const float eps,
+                                  const at::Tensor weights_tensor)
+{
+  const int L = (int)level_offsets.size(0), C = (int)code_0.numel();
+  KfPtr kf0 = keyframe({feat_map_pyramid_0, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0,
+                        sampled_locations_homo_0},
+                       camera_pyramid[0], L, FS, C);
+  KfPtr kf1 = keyframe({feat_map_pyramid_1, {}, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, C);
+  const auto R = hostf(rotation), t = hostf(translation), code = hostf(code_0), w = hostf(weights_tensor);
+  float err = 0.f;
+  SAGE_OK(sage_ba_photometric_error(ctx(), kf0.get(), kf1.get(), R.data(), t.data(), code.data(), scale_0, eps, w.data(), &err, nullptr));
+  return err;
+}
+
+template <int CS, int FS>
+void photometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation10,
+                                     const at::Tensor translation10, const at::Tensor rotation0, const at::Tensor translation0,
+                                     const at::Tensor rotation1, const at::Tensor translation1, const at::Tensor flatten_dpt_map_bias_0,
+                                     const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0, const at::Tensor valid_mask_1,
+                                     const at::Tensor sampled_locations_1d_0, const at::Tensor sampled_locations_homo_0,
+                                     const at::Tensor feat_map_pyramid_0, const at::Tensor feat_map_pyramid_1,
+                                     const at::Tensor feat_map_grad_pyramid_1, const at::Tensor level_offsets, const float scale_0,
+                                     const CameraPyramid<float> &camera_pyramid, const float eps, const at::Tensor weights_tensor)
+{
+  const int L = (int)level_offsets.size(0);
+  KfPtr kf0 = keyframe({feat_map_pyramid_0, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0,
+                        sampled_locations_homo_0},
+                       camera_pyramid[0], L, FS, CS);
+  KfPtr kf1 = keyframe({feat_map_pyramid_1, feat_map_grad_pyramid_1, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, CS);
+  constexpr int D = 13 + CS;
+  std::vector<float> A(D * D), b(D);
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
+             t1 = hostf(translation1), code = hostf(code_0), w = hostf(weights_tensor);
+  SAGE_OK(sage_ba_photometric_jac_error(ctx(), kf0.get(), kf1.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(),
+                                        code.data(), scale_0, eps, w.data(), A.data(), b.data(), &error, nullptr));
+  AtA = to_dev(A.data(), {D, D}, rotation10);
+  Atb = to_dev(b.data(), {D, 1}, rotation10);
+}
+
+template <int FS>
+static void tracker_photo_jac(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor &rotation, const at::Tensor &translation,
+                              const at::Tensor &valid_mask_1, const at::Tensor &sampled_dpts_0, const at::Tensor &sampled_locations_homo_0,
+                              const at::Tensor &sampled_features_0, const at::Tensor &feat_map_pyramid_1,
+                              const at::Tensor &feat_map_grad_pyramid_1, const at::Tensor &level_offsets,
+                              const CameraPyramid<float> &camera_pyramid, int with_scale, float scale_0, float eps,
+                              const at::Tensor &weights_tensor)
+{
+  const int L = (int)level_offsets.size(0), D = with_scale ? 7 : 6;
+  KfPtr fr1 = keyframe({feat_map_pyramid_1, feat_map_grad_pyramid_1, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, 8);
+  const at::Tensor dp = sampled_dpts_0.to(at::kFloat).contiguous(), hm = sampled_locations_homo_0.to(at::kFloat).contiguous(),
+                   sf = sampled_features_0.to(at::kFloat).contiguous();
+  const auto R = hostf(rotation), t = hostf(translation), w = hostf(weights_tensor);
+  std::vector<float> A(D * D), b(D);
+  SAGE_OK(sage_ba_tracker_photo_jac_error(ctx(), fr1.get(), R.data(), t.data(), dp.data_ptr<float>(), hm.data_ptr<float>(),
+                                          sf.data_ptr<float>(), (int)dp.numel(), with_scale, scale_0, eps, w.data(), A.data(), b.data(),
+                                          &error, nullptr));
+  AtA = to_dev(A.data(), {D, D}, rotation);
+  Atb = to_dev(b.data(), {D, 1}, rotation);
+}
+
+template <int FS>
+void tracker_photo_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation, const at::Tensor translation,
+                                       const at::Tensor valid_mask_1, const at::Tensor sampled_dpts_0,
+                                       const at::Tensor sampled_locations_homo_0, const at::Tensor sampled_features_0,
+                                       const at::Tensor feat_map_pyramid_1, const at::Tensor feat_map_grad_pyramid_1,
+                                       const at::Tensor level_offsets, const CameraPyramid<float> &camera_pyramid, const float eps,
+                                       const at::Tensor weights_tensor)
+{
+  tracker_photo_jac<FS>(AtA, Atb, error, rotation, translation, valid_mask_1, sampled_dpts_0, sampled_locations_homo_0, sampled_features_0,
+                        feat_map_pyramid_1, feat_map_grad_pyramid_1, level_offsets, camera_pyramid, 0, 0.f, eps, weights_tensor);
+}
+
+template <int FS>
+void tracker_photo_jac_error_calculate_with_scale(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation,
+                                                  const at::Tensor translation, const at::Tensor valid_mask_1,
+                                                  const at::Tensor sampled_dpts_0, const at::Tensor sampled_locations_homo_0,
+                                                  const at::Tensor sampled_features_0, const at::Tensor feat_map_pyramid_1,
+                                                  const at::Tensor feat_map_grad_pyramid_1, const at::Tensor level_offsets,
+                                                  const CameraPyramid<float> &camera_pyramid, const float scale_0, const float eps,
+                                                  const at::Tensor weights_tensor)
+{
+  tracker_photo_jac<FS>(AtA, Atb, error, rotation, translation, valid_mask_1, sampled_dpts_0, sampled_locations_homo_0, sampled_features_0,
+                        feat_map_pyramid_1, feat_map_grad_pyramid_1, level_offsets, camera_pyramid, 1, scale_0, eps, weights_tensor);
+}
+
+template <int FS>
+float tracker_photo_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor valid_mask_1,
+                                    const at::Tensor sampled_dpts_0, const at::Tensor sampled_locations_homo_0,
+                                    const at::Tensor sampled_features_0, const at::Tensor feat_map_pyramid_1, const at::Tensor level_offsets,
+                                    const CameraPyramid<float> &camera_pyramid, const float eps, const at::Tensor weights_tensor)
+{
+  const int L = (int)level_offsets.size(0);
+  KfPtr fr1 = keyframe({feat_map_pyramid_1, {}, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, 8);
+  const at::Tensor dp = sampled_dpts_0.to(at::kFloat).contiguous(), hm = sampled_locations_homo_0.to(at::kFloat).contiguous(),
+                   sf = sampled_features_0.to(at::kFloat).contiguous();
+  const auto R = hostf(rotation), t = hostf(translation), w = hostf(weights_tensor);
+  float err = 0.f;
+  SAGE_OK(sage_ba_tracker_photo_error(ctx(), fr1.get(), R.data(), t.data(), dp.data_ptr<float>(), hm.data_ptr<float>(), sf.data_ptr<float>(),
+                                      (int)dp.numel(), eps, w.data(), &err, nullptr));
+  return err;
+}
+
+// ------------------------------------------------------------------------------------------------ geometric
+// The reference hands over KF1's depth map, its gradient and its basis as the caller computed them for the current
+// code_1 / scale_1 (gtsam/geometric_factor.cpp:317-320,340-342).  The C ABI rebuilds the map and its central-difference
+// gradient itself from (bias, basis, code, scale); feeding it bias := dpt_map_1 / scale_1, code := 0 reproduces the caller's
+// tensors, so the call stays source-compatible.  (A caller that adopts the C ABI directly passes code_1 and drops those lines.)
+template <int CS>
+float geometric_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor flatten_dpt_map_bias_0,
+                                const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0, const at::Tensor dpt_map_1,
+                                const at::Tensor valid_mask_1, const at::Tensor sampled_locations_1d_0,
+                                const at::Tensor sampled_locations_homo_0, const float scale_0, const PinholeCamera<float> &camera,
+                                const float eps, const float loss_param, const float weight)
+{
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0, sampled_locations_homo_0}, camera,
+                       1, 16, CS);
+  const long HW = dpt_map_1.numel();
+  const at::Tensor zero_basis = torch::zeros({HW, (long)CS}, dpt_map_1.options());
+  KfPtr kf1 = keyframe({{}, {}, dpt_map_1.reshape({-1}), zero_basis, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*cache=*/false);
+  const auto R = hostf(rotation), t = hostf(translation), code = hostf(code_0);
+  const std::vector<float> code1(CS, 0.f);
+  float err = 0.f;
+  SAGE_OK(sage_ba_geometric_error(ctx(), kf0.get(), kf1.get(), R.data(), t.data(), code.data(), code1.data(), scale_0, 1.0f, eps, loss_param,
+                                  weight, &err, nullptr));
+  return err;
+}
+
+template <int CS>
+void geometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation10, const at::Tensor translation10,
+                                   const at::Tensor rotation0, const at::Tensor translation0, const at::Tensor rotation1,
+                                   const at::Tensor translation1, const at::Tensor flatten_dpt_map_bias_0,
+                                   const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0, const at::Tensor dpt_map_1,
+                                   const at::Tensor /*dpt_map_grad_1: rebuilt inside by the same central differences*/,
+                                   const at::Tensor dpt_jac_code_1, const at::Tensor valid_mask_1, const at::Tensor sampled_locations_1d_0,
+                                   const at::Tensor sampled_locations_homo_0, const float scale_0, const float scale_1,
+                                   const PinholeCamera<float> &camera, const float eps, const float loss_param, const float weight)
+{
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0, sampled_locations_homo_0}, camera,
+                       1, 16, CS);
+  const at::Tensor unscaled = (dpt_map_1 / scale_1).reshape({-1}).contiguous();
+  const at::Tensor basis1 = dpt_jac_code_1.reshape({-1, (long)CS}); // [H, W, C] -> [HW, C]
+  KfPtr kf1 = keyframe({{}, {}, unscaled, basis1, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*cache=*/false);
+  constexpr int D = 14 + 2 * CS;
+  std::vector<float> A(D * D), b(D);
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
+             t1 = hostf(translation1), code = hostf(code_0);
+  const std::vector<float> code1(CS, 0.f);
+  SAGE_OK(sage_ba_geometric_jac_error(ctx(), kf0.get(), kf1.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(),
+                                      code.data(), code1.data(), scale_0, scale_1, eps, loss_param, weight, A.data(), b.data(), &error,
+                                      nullptr));
+  AtA = to_dev(A.data(), {D, D}, rotation10);
+  Atb = to_dev(b.data(), {D, 1}, rotation10);
+}
+
+// ------------------------------------------------------------------------------------------------ reprojection
+void tracker_reproj_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation, const at::Tensor translation,
+                                        const at::Tensor sampled_dpts_0, const at::Tensor sampled_locations_homo_0,
+                                        const at::Tensor matched_locations_2d_1, const PinholeCamera<float> &camera, const float eps,
+                                        const float loss_param, const float weight)
+{
+  const auto R = hostf(rotation), t = hostf(translation), dp = hostf(sampled_dpts_0), hm = hostf(sampled_locations_homo_0),
+             uv = hostf(matched_locations_2d_1);
+  const sage_ba_camera cam = cam_of(camera);
+  std::vector<float> A(36), b(6);
+  SAGE_OK(sage_ba_tracker_reproj_jac_error(ctx(), &cam, R.data(), t.data(), dp.data(), hm.data(), uv.data(), (int)dp.size(), eps, loss_param,
+                                           weight, A.data(), b.data(), &error, nullptr));
+  AtA = to_dev(A.data(), {6, 6}, rotation);
+  Atb = to_dev(b.data(), {6, 1}, rotation);
+}
+
+float tracker_reproj_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor sampled_dpts_0,
+                                     const at::Tensor sampled_locations_homo_0, const at::Tensor matched_locations_2d_1,
+                                     const PinholeCamera<float> &camera, const float eps, const float loss_param, const float weight)
+{
+  const auto R = hostf(rotation), t = hostf(translation), dp = hostf(sampled_dpts_0), hm = hostf(sampled_locations_homo_0),
+             uv = hostf(matched_locations_2d_1);
+  const sage_ba_camera cam = cam_of(camera);
+  float err = 0.f;
+  SAGE_OK(sage_ba_tracker_reproj_error(ctx(), &cam, R.data(), t.data(), dp.data(), hm.data(), uv.data(), (int)dp.size(), eps, loss_param,
+                                       weight, &err, nullptr));
+  return err;
+}
+
+template <int CS>
+void reprojection_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation10,
+                                      const at::Tensor translation10, const at::Tensor rotation0, const at::Tensor translation0,
+                                      const at::Tensor rotation1, const at::Tensor translation1, const at::Tensor flatten_dpt_map_bias_0,
+                                      const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0,
+                                      const at::Tensor sampled_locations_1d_0, const at::Tensor sampled_locations_homo_0,
+                                      const at::Tensor matched_locations_2d_1, const float scale_0, const PinholeCamera<float> &camera,
+                                      const float eps, const float loss_param, const float weight)
+{
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, {}, {}}, camera, 1, 16, CS);
+  constexpr int D = 13 + CS;
+  std::vector<float> A(D * D), b(D);
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
+             t1 = hostf(translation1), code = hostf(code_0), hm = hostf(sampled_locations_homo_0), uv = hostf(matched_locations_2d_1);
+  const auto loc = hosti(sampled_locations_1d_0);
+  SAGE_OK(sage_ba_reprojection_jac_error(ctx(), kf0.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(), code.data(),
+                                         scale_0, loc.data(), hm.data(), uv.data(), (int)loc.size(), eps, loss_param, weight, A.data(),
+                                         b.data(), &error, nullptr));
+  AtA = to_dev(A.data(), {D, D}, rotation10);
+  Atb = to_dev(b.data(), {D, 1}, rotation10);
+}
+
+template <int CS>
+float reprojection_error_calculate(const at::Tensor rotation10, const at::Tensor translation10, const at::Tensor flatten_dpt_map_bias_0,
+                                   const at::Tensor flatten_dpt_jac_code_0, const at::Tensor code_0, const at::Tensor sampled_locations_1d_0,
+                                   const at::Tensor sampled_locations_homo_0, const at::Tensor matched_locations_2d_1, const float scale_0,
+                                   const PinholeCamera<float> &camera, const float eps, const float loss_param, const float weight)
+{
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, {}, {}}, camera, 1, 16, CS);
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), code = hostf(code_0), hm = hostf(sampled_locations_homo_0),
+             uv = hostf(matched_locations_2d_1);
+  const auto loc = hosti(sampled_locations_1d_0);
+  float err = 0.f;
+  SAGE_OK(sage_ba_reprojection_error(ctx(), kf0.get(), R10.data(), t10.data(), code.data(), scale_0, loc.data(), hm.data(), uv.data(),
+                                     (int)loc.size(), eps, loss_param, weight, &err, nullptr));
+  return err;
+}
+
+// ------------------------------------------------------------------------------------------------ match geometry
+float tracker_match_geom_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor sampled_dpts_0,
+                                         const at::Tensor matched_dpts_1, const at::Tensor sampled_locations_homo_0,
+                                         const at::Tensor matched_locations_homo_1, const float loss_param, const float weight)
+{
+  const auto R = hostf(rotation), t = hostf(translation), d0 = hostf(sampled_dpts_0), d1 = hostf(matched_dpts_1),
+             h0 = hostf(sampled_locations_homo_0), h1 = hostf(matched_locations_homo_1);
+  float err = 0.f;
+  SAGE_OK(sage_ba_tracker_match_geom_error(ctx(), R.data(), t.data(), d0.data(), d1.data(), h0.data(), h1.data(), (int)d0.size(), loss_param,
+                                           weight, &err));
+  return err;
+}
+
+static void tracker_mg_jac(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor &rotation, const at::Tensor &translation,
+                           const at::Tensor &sampled_dpts_0, const at::Tensor &matched_dpts_1, const at::Tensor &sampled_locations_homo_0,
+                           const at::Tensor &matched_locations_homo_1, int with_scale, float scale_0, float loss_param, float weight)
+{
+  const int D = with_scale ? 7 : 6;
+  const auto R = hostf(rotation), t = hostf(translation), d0 = hostf(sampled_dpts_0), d1 = hostf(matched_dpts_1),
+             h0 = hostf(sampled_locations_homo_0), h1 = hostf(matched_locations_homo_1);
+  std::vector<float> A(D * D), b(D);
+  SAGE_OK(sage_ba_tracker_match_geom_jac_error(ctx(), R.data(), t.data(), d0.data(), d1.data(), h0.data(), h1.data(), (int)d0.size(),
+                                               with_scale, scale_0, loss_param, weight, A.data(), b.data(), &error));
+  AtA = to_dev(A.data(), {D, D}, rotation);
+  Atb = to_dev(b.data(), {D, 1}, rotation);
+}
+
+void tracker_match_geom_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation,
+                                            const at::Tensor translation, const at::Tensor sampled_dpts_0, const at::Tensor matched_dpts_1,
+                                            const at::Tensor sampled_locations_homo_0, const at::Tensor matched_locations_homo_1,
+                                            const float loss_param, const float weight)
+{
+  tracker_mg_jac(AtA, Atb, error, rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0, matched_locations_homo_1, 0,
+                 0.f, loss_param, weight);
+}
+
+void tracker_match_geom_jac_error_calculate_with_scale(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation,
+                                                       const at::Tensor translation, const at::Tensor sampled_dpts_0,
+                                                       const at::Tensor matched_dpts_1, const at::Tensor sampled_locations_homo_0,
+                                                       const at::Tensor matched_locations_homo_1, const float scale_0,
+                                                       const float loss_param, const float weight)
+{
+  tracker_mg_jac(AtA, Atb, error, rotation, translation, sampled_dpts_0, matched_dpts_1, sampled_locations_homo_0, matched_locations_homo_1, 1,
+                 scale_0, loss_param, weight);
+}
+
+template <int CS>
+float match_geometry_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor flatten_dpt_map_bias_0,
+                                     const at::Tensor flatten_dpt_map_bias_1, const at::Tensor flatten_dpt_jac_code_0,
+                                     const at::Tensor flatten_dpt_jac_code_1, const at::Tensor code_0, const at::Tensor code_1,
+                                     const at::Tensor sampled_locations_homo_0, const at::Tensor matched_locations_homo_1,
+                                     const at::Tensor sampled_locations_1d_0, const at::Tensor matched_locations_1d_1, const float scale_0,
+                                     const float scale_1, const float loss_param, const float weight, const std::string robust_loss_type)
+{
+  const long HW = flatten_dpt_map_bias_0.numel();
+  const PinholeCamera<float> cam(1.f, 1.f, 0.f, 0.f, (float)HW, 1.f); // only the pixel count matters for depth-only keyframes
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, {}, {}}, cam, 1, 16, CS);
+  KfPtr kf1 = keyframe({{}, {}, flatten_dpt_map_bias_1, flatten_dpt_jac_code_1, {}, {}, {}}, cam, 1, 16, CS);
+  const auto R = hostf(rotation), t = hostf(translation), c0 = hostf(code_0), c1 = hostf(code_1), h0 = hostf(sampled_locations_homo_0),
+             h1 = hostf(matched_locations_homo_1);
+  const auto l0 = hosti(sampled_locations_1d_0), l1 = hosti(matched_locations_1d_1);
+  float err = 0.f;
+  SAGE_OK(sage_ba_match_geometry_error(ctx(), kf0.get(), kf1.get(), R.data(), t.data(), c0.data(), c1.data(), scale_0, scale_1, l0.data(),
+                                       l1.data(), h0.data(), h1.data(), (int)l0.size(), loss_param, weight, loss_type(robust_loss_type), &err));
+  return err;
+}
+
+template <int CS>
+void match_geometry_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation10,
+                                        const at::Tensor translation10, const at::Tensor rotation0, const at::Tensor translation0,
+                                        const at::Tensor rotation1, const at::Tensor translation1, const at::Tensor flatten_dpt_map_bias_0,
+                                        const at::Tensor flatten_dpt_map_bias_1, const at::Tensor flatten_dpt_jac_code_0,
+                                        const at::Tensor flatten_dpt_jac_code_1, const at::Tensor code_0, const at::Tensor code_1,
+                                        const at::Tensor sampled_locations_homo_0, const at::Tensor matched_locations_homo_1,
+                                        const at::Tensor sampled_locations_1d_0, const at::Tensor matched_locations_1d_1, const float scale_0,
+                                        const float scale_1, const float loss_param, const float weight, const std::string robust_loss_type)
+{
+  const long HW = flatten_dpt_map_bias_0.numel();
+  const PinholeCamera<float> cam(1.f, 1.f, 0.f, 0.f, (float)HW, 1.f);
+  KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, {}, {}}, cam, 1, 16, CS);
+  KfPtr kf1 = keyframe({{}, {}, flatten_dpt_map_bias_1, flatten_dpt_jac_code_1, {}, {}, {}}, cam, 1, 16, CS);
+  constexpr int D = 14 + 2 * CS;
+  std::vector<float> A(D * D), b(D);
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
+             t1 = hostf(translation1), c0 = hostf(code_0), c1 = hostf(code_1), h0 = hostf(sampled_locations_homo_0),
+             h1 = hostf(matched_locations_homo_1);
+  const auto l0 = hosti(sampled_locations_1d_0), l1 = hosti(matched_locations_1d_1);
+  SAGE_OK(sage_ba_match_geometry_jac_error(ctx(), kf0.get(), kf1.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(),
+                                           c0.data(), c1.data(), scale_0, scale_1, l0.data(), l1.data(), h0.data(), h1.data(), (int)l0.size(),
+                                           loss_param, weight, loss_type(robust_loss_type), A.data(), b.data(), &error));
+  AtA = to_dev(A.data(), {D, D}, rotation10);
+  Atb = to_dev(b.data(), {D, 1}, rotation10);
+}
+
+float loop_mg_error_calculate(const at::Tensor rotation, const at::Tensor translation, const at::Tensor sampled_unscaled_dpts_0,
+                              const at::Tensor matched_unscaled_dpts_1, const at::Tensor sampled_locations_homo_0,
+                              const at::Tensor matched_locations_homo_1, const float scale_0, const float scale_1, const float loss_param,
+                              const float weight)
+{
+  const auto R = hostf(rotation), t = hostf(translation), d0 = hostf(sampled_unscaled_dpts_0), d1 = hostf(matched_unscaled_dpts_1),
+             h0 = hostf(sampled_locations_homo_0), h1 = hostf(matched_locations_homo_1);
+  float err = 0.f;
+  SAGE_OK(sage_ba_loop_mg_error(ctx(), R.data(), t.data(), d0.data(), d1.data(), h0.data(), h1.data(), (int)d0.size(), scale_0, scale_1,
+                                loss_param, weight, &err));
+  return err;
+}
+
+void loop_mg_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &error, const at::Tensor rotation10, const at::Tensor translation10,
+                                 const at::Tensor rotation0, const at::Tensor translation0, const at::Tensor rotation1,
+                                 const at::Tensor translation1, const at::Tensor sampled_unscaled_dpts_0,
+                                 const at::Tensor matched_unscaled_dpts_1, const at::Tensor sampled_locations_homo_0,
+                                 const at::Tensor matched_locations_homo_1, const float scale_0, const float scale_1, const float loss_param,
+                                 const float weight)
+{
+  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
+             t1 = hostf(translation1), d0 = hostf(sampled_unscaled_dpts_0), d1 = hostf(matched_unscaled_dpts_1),
+             h0 = hostf(sampled_locations_homo_0), h1 = hostf(matched_locations_homo_1);
+  std::vector<float> A(14 * 14), b(14);
+  SAGE_OK(sage_ba_loop_mg_jac_error(ctx(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(), d0.data(), d1.data(), h0.data(),
+                                    h1.data(), (int)d0.size(), scale_0, scale_1, loss_param, weight, A.data(), b.data(), &error));
+  AtA = to_dev(A.data(), {14, 14}, rotation10);
+  Atb = to_dev(b.data(), {14, 1}, rotation10);
+}
+
+// explicit instantiations, as the reference's translation units end (cuda/photometric_factor_kernels.cpp:1388-1449 etc.)
+template float photometric_error_calculate<DF_FEAT_SIZE>(const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                         const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                         const at::Tensor, const float, const CameraPyramid<float> &, const float,
+                                                         const at::Tensor);
+template void photometric_jac_error_calculate<DF_CODE_SIZE, DF_FEAT_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor,
+                                                                          const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                                          const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                                          const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                                          const at::Tensor, const at::Tensor, const float,
+                                                                          const CameraPyramid<float> &, const float, const at::Tensor);
+template void tracker_photo_jac_error_calculate<DF_FEAT_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor,
+                                                              const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                              const at::Tensor, const at::Tensor, const at::Tensor, const CameraPyramid<float> &,
+                                                              const float, const at::Tensor);
+template void tracker_photo_jac_error_calculate_with_scale<DF_FEAT_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor,
+                                                                         const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                                         const at::Tensor, const at::Tensor, const at::Tensor,
+                                                                         const CameraPyramid<float> &, const float, const float,
+                                                                         const at::Tensor);
+template float tracker_photo_error_calculate<DF_FEAT_SIZE>(const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                           const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                           const CameraPyramid<float> &, const float, const at::Tensor);
+template float geometric_error_calculate<DF_CODE_SIZE>(const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                       const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const float,
+                                                       const PinholeCamera<float> &, const float, const float, const float);
+template void geometric_jac_error_calculate<DF_CODE_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                          const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                          const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                          const at::Tensor, const at::Tensor, const float, const float,
+                                                          const PinholeCamera<float> &, const float, const float, const float);
+template void reprojection_jac_error_calculate<DF_CODE_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor,
+                                                             const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                             const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                             const at::Tensor, const at::Tensor, const float, const PinholeCamera<float> &,
+                                                             const float, const float, const float);
+template float reprojection_error_calculate<DF_CODE_SIZE>(const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                          const at::Tensor, const at::Tensor, const at::Tensor, const float,
+                                                          const PinholeCamera<float> &, const float, const float, const float);
+template float match_geometry_error_calculate<DF_CODE_SIZE>(const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                            const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                            const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor, const float,
+                                                            const float, const float, const float, const std::string);
+template void match_geometry_jac_error_calculate<DF_CODE_SIZE>(at::Tensor &, at::Tensor &, float &, const at::Tensor, const at::Tensor,
+                                                               const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                               const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                               const at::Tensor, const at::Tensor, const at::Tensor, const at::Tensor,
+                                                               const at::Tensor, const at::Tensor, const float, const float, const float,
+                                                               const float, const std::string);
+
+} // namespace df

@@ -90,6 +90,76 @@ def build(configs=CONFIGS, force=False, jobs=8):
     return True
 
 
+def shim_path(cs, fs):
+    return os.path.join(OUT, f"sage_shim_c{cs}_f{fs}.so")
+
+
+def build_shim(configs=CONFIGS, force=False, jobs=8):
+    """The drop-in check of the df:: boundary: integration/df_sage_shim.cpp (the reference's df::*_calculate symbols on top
+    of the C ABI) compiled against the reference's own headers and linked with the SAME pybind front (ref_ext.cpp) that
+    drives the reference kernels, plus libsage_ba.so -- no reference kernel source is part of this module."""
+    if not available():
+        return False
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(OUT, exist_ok=True)
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "sage-slam_b200", "lib")
+    inc = []
+    for p in ce.include_paths("cuda") if hasattr(ce, "include_paths") else ce.include_paths(True):
+        inc += ["-isystem", p]
+    inc += ["-isystem", sysconfig.get_paths()["include"]]
+    inc += ["-I", os.path.join(HERE, "ref_shims"), "-I", os.path.join(REF, "sources", "cuda"),
+            "-I", os.path.join(REF, "sources", "common"), "-I", os.path.join(REF, "thirdparty", "eigen"),
+            "-I", os.path.join(root, "include")]
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    tasks, links = [], []
+    for cs, fs in configs:
+        so = shim_path(cs, fs)
+        shim_src = os.path.join(root, "integration", "df_sage_shim.cpp")
+        if os.path.exists(so) and not force and os.path.getmtime(so) > os.path.getmtime(shim_src):
+            continue
+        name = f"sage_shim_c{cs}_f{fs}"
+        common = ["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a", "-x", "cu",
+                  "-Xcompiler", "-fPIC", "-w", "--expt-relaxed-constexpr",
+                  "-include", os.path.join(HERE, "ref_shims", "sage_ref_compat.h"),
+                  f"-DDF_CODE_SIZE={cs}", f"-DDF_FEAT_SIZE={fs}", f"-DTORCH_EXTENSION_NAME={name}",
+                  "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI))] + inc
+        objs = []
+        for src in (shim_src, os.path.join(HERE, "ref_ext.cpp")):
+            obj = os.path.join(OUT, f"{name}_{os.path.basename(src)[:-4]}.o")
+            tasks.append(common + ["-c", src, "-o", obj])
+            objs.append(obj)
+        links.append(["nvcc", "-shared", "-o", so] + objs +
+                     ["-L", torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
+                      "-L", libdir, "-lsage_ba", "-Xlinker", "-rpath", "-Xlinker", torch_lib,
+                      "-Xlinker", "-rpath", "-Xlinker", "/root/repo/sage-slam_b200/lib"])
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        list(ex.map(_run, tasks))
+    for l in links:
+        _run(l)
+    for f in os.listdir(OUT):
+        if f.endswith(".o"):
+            os.remove(os.path.join(OUT, f))
+    return True
+
+
+def load_shim(cs, fs):
+    """Import the shim module (df:: symbols implemented by libsage_ba.so); needs a CUDA device to do anything."""
+    import importlib.util
+    import torch  # noqa: F401
+
+    path = shim_path(cs, fs)
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    name = f"sage_shim_c{cs}_f{fs}"
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load(cs, fs):
     """Import the compiled reference module for (CS, FS); needs a CUDA device to do anything."""
     import importlib.util
@@ -107,4 +177,5 @@ def load(cs, fs):
 
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    build_shim(force="--force" in sys.argv)
     print("reference modules:", sorted(os.listdir(OUT)) if ok else "reference sources not present")

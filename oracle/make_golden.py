@@ -22,14 +22,14 @@ def T(a, dev, dtype=torch.float32):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dtype)
 
 
-def run_case(name, far):
+def run_case(name, far, mod=None):
     dev = torch.device("cuda:0")
     assert torch.backends.cuda.matmul.allow_tf32 is False
     kfs = helpers.build_case(name, far=far)
     a = helpers.case_args(kfs)
     ta = helpers.tracker_args(kfs, a)
     ma = helpers.match_args(kfs)
-    mod = build_ref.load(a["C"], a["F"])
+    mod = mod or build_ref.load(a["C"], a["F"])
     cam = [float(x) for x in a["cam"]]
     L = a["L"]
     # the depth basis as the reference hands it over: [HW, C] view with strides (1, HW)

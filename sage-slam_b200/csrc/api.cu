@@ -212,9 +212,14 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
   };
   try
   {
-    SAGE_CHECK((d->feat_map_pyramid || d->feat_map) && d->video_mask, "feat_map (or feat_map_pyramid) and video_mask are required");
-    SAGE_CUDA(cudaMalloc(&kf->fg, sizeof(float) * SP * 3 * F));
-    SAGE_CUDA(cudaMalloc(&kf->mask, sizeof(float) * HW));
+    // every group of tensors is optional (the reference's operators each see only part of a frame, and the df:: shim of
+    // INTEGRATION.md builds partial keyframes from what one call is given); the entry points check for what they need
+    SAGE_CHECK(d->feat_map_pyramid || d->feat_map || d->dpt_map_bias, "a keyframe needs feature maps or depth data");
+    SAGE_CHECK(!d->feat_map || d->video_mask, "building the pyramid on the device needs video_mask");
+    if (d->feat_map_pyramid || d->feat_map)
+      SAGE_CUDA(cudaMalloc(&kf->fg, sizeof(float) * SP * 3 * F));
+    if (d->video_mask)
+      SAGE_CUDA(cudaMalloc(&kf->mask, sizeof(float) * HW));
     if (d->feat_map)
     {
       // device-side input builder: masked Gaussian pyramid + gradients straight into the channel-last layout
@@ -225,7 +230,7 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
       temps.push_back(mscr);
       ctx->launches += launch_build_pyramid(feat0, mask0, kf->fg, (float *)mscr, kf->pyr, F, s);
     }
-    else
+    else if (d->feat_map_pyramid)
     {
       const float *feat = (const float *)stage(d->feat_map_pyramid, sizeof(float) * F * SP);
       if (d->feat_map_grad_pyramid)
@@ -241,7 +246,8 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
         ctx->launches += 1;
       }
     }
-    SAGE_CUDA(cudaMemcpyAsync(kf->mask, d->video_mask, sizeof(float) * HW, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    if (d->video_mask)
+      SAGE_CUDA(cudaMemcpyAsync(kf->mask, d->video_mask, sizeof(float) * HW, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     if (d->dpt_map_bias)
     {
       SAGE_CHECK(d->dpt_jac_code, "dpt_jac_code is required with dpt_map_bias");
@@ -268,10 +274,13 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
         const int64_t *l64 = (const int64_t *)stage(d->sampled_locations_1d, sizeof(int64_t) * N);
         launch_convert_loc(l64, kf->loc1d, N, s);
         ctx->launches += 1;
-        // features of this keyframe at its own sample points, every level: what the mapping kernels read as "feat_0"
-        SAGE_CUDA(cudaMalloc(&kf->sfeat, sizeof(float) * (size_t)kf->L * N * F));
-        launch_presample(kf->fg, nullptr, nullptr, kf->loc1d, kf->homo, nullptr, 1.f, kf->pyr, F, C, N, nullptr, nullptr, kf->sfeat, s);
-        ctx->launches += 1;
+        if (kf->fg)
+        {
+          // features of this keyframe at its own sample points, every level: what the mapping kernels read as "feat_0"
+          SAGE_CUDA(cudaMalloc(&kf->sfeat, sizeof(float) * (size_t)kf->L * N * F));
+          launch_presample(kf->fg, nullptr, nullptr, kf->loc1d, kf->homo, nullptr, 1.f, kf->pyr, F, C, N, nullptr, nullptr, kf->sfeat, s);
+          ctx->launches += 1;
+        }
       }
     }
     SAGE_CUDA(cudaGetLastError());
@@ -331,6 +340,7 @@ static PhotoFactor photo_map_factor(const sage_ba_keyframe *kf0, const sage_ba_k
 {
   check_pair(kf0, kf1);
   SAGE_CHECK(kf0->bias && kf0->basis && kf0->loc1d && kf0->homo && kf0->sfeat, "kf0 lacks depth / sample data");
+  SAGE_CHECK(kf1->fg && kf1->mask, "kf1 lacks feature maps / mask");
   PhotoFactor f;
   memset(&f, 0, sizeof(f));
   f.fg0 = kf0->fg;
@@ -381,7 +391,7 @@ int sage_ba_photometric_error(sage_ba_context *ctx, const sage_ba_keyframe *kf0,
 static PhotoFactor photo_trk_factor(const sage_ba_keyframe *fr1, const float *R, const float *t, const float *dpts, const float *homo4,
                                     const float *feats, int N, float scale0, float eps, const float *weights)
 {
-  SAGE_CHECK(fr1, "null frame");
+  SAGE_CHECK(fr1 && fr1->fg && fr1->mask, "frame lacks feature maps / mask");
   PhotoFactor f;
   memset(&f, 0, sizeof(f));
   f.fg1 = fr1->fg;
@@ -456,7 +466,7 @@ int sage_ba_tracker_presample(sage_ba_context *ctx, const sage_ba_keyframe *kf0,
 {
   SAGE_TRY(ctx)
   SAGE_CUDA(cudaSetDevice(ctx->device));
-  SAGE_CHECK(kf0 && kf0->bias && kf0->loc1d, "kf0 lacks depth / sample data");
+  SAGE_CHECK(kf0 && kf0->bias && kf0->loc1d && kf0->fg, "kf0 lacks depth / sample / feature data");
   float *dcode = ctx->tmp_code.ensure(SAGE_MAX_CODE);
   float *hc = reinterpret_cast<float *>(ctx->hfactor.ensure(1024));
   memcpy(hc, code0, sizeof(float) * kf0->C);
@@ -476,7 +486,7 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
                            float *n_inl)
 {
   check_pair(kf0, kf1);
-  SAGE_CHECK(kf0->bias && kf0->loc1d && kf1->bias, "keyframes lack depth / sample data");
+  SAGE_CHECK(kf0->bias && kf0->loc1d && kf1->bias && kf1->mask, "keyframes lack depth / sample / mask data");
   const int C = kf0->C, D = 14 + 2 * C;
   cudaStream_t s = ctx->stream;
   // KF1's depth map + gradient from (code1) -- gtsam/geometric_factor.cpp:317-320 moved inside

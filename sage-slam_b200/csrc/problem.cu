@@ -762,7 +762,8 @@ int sage_ba_problem_create(sage_ba_context *ctx, int num_keyframes, sage_ba_keyf
     p->K = num_keyframes;
     for (int k = 0; k < num_keyframes; ++k)
     {
-      SAGE_CHECK(kfs[k] && kfs[k]->bias && kfs[k]->loc1d, "keyframes of a problem need depth and sample data");
+      SAGE_CHECK(kfs[k] && kfs[k]->bias && kfs[k]->loc1d && kfs[k]->fg && kfs[k]->mask && kfs[k]->sfeat,
+                 "keyframes of a problem need feature maps, mask, depth and sample data");
       if (k)
         SAGE_CHECK(kfs[k]->H == kfs[0]->H && kfs[k]->W == kfs[0]->W && kfs[k]->F == kfs[0]->F && kfs[k]->C == kfs[0]->C &&
                        kfs[k]->L == kfs[0]->L,
