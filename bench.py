@@ -20,6 +20,8 @@ roofline: the photometric linearisation kernel (the dominant launch), algorithmi
 --impl reference: the reference has NO CPU implementation of this path, so the reference arm
           times the CPU restatement of its kernels (oracle/, all host threads) on a bounded sample (one ordered
           pair: photometric + geometric linearisation and error evaluation) and extrapolates to the 180 pairs.
+--impl shim: the same pair-by-pair call sequence as reference-gpu, but through integration/df_sage_shim.cpp (the
+reference's df:: symbols implemented by libsage_ba.so) -- what an unmodified caller of the reference gets.
 --impl reference-gpu: the reference's OWN CUDA kernels (oracle/_ref, compiled unmodified from /root/reference),
           called pair by pair as core/gtsam/*_factor.cpp does, on the same B200 (bounded sample of pairs).
 """
@@ -433,7 +435,7 @@ def run_reference_gpu(args):
                                     num_samples=args.ref_samples or None)
     pairs = sage.synthetic.ordered_pairs(kfs)
     npairs = 180 if not args.small else len(pairs)
-    mod = build_ref.load(wl["C"], wl["F"])
+    mod = build_ref.load_shim(wl["C"], wl["F"]) if args.impl == "shim" else build_ref.load(wl["C"], wl["F"])
     dev = torch.device("cuda:0")
 
     def T(a, dtype=torch.float32):
@@ -483,10 +485,11 @@ def run_reference_gpu(args):
     torch.cuda.synchronize()
     t_pair = (time.perf_counter() - t0) / args.steps
     value = 1.0 / (t_pair * npairs)
-    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": value, "unit": "LM iters/s", "n_gpus": 1, "steps": args.steps,
+    print(json.dumps({"impl": args.impl, "metric": METRIC, "value": value, "unit": "LM iters/s", "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": t_pair * npairs * 1e3, "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "reference CUDA kernels (oracle/_ref), pair by pair; each step = 1 ordered pair "
+                      "config": {"workload": ("df:: shim over libsage_ba.so" if args.impl == "shim" else "reference CUDA kernels (oracle/_ref)") +
+                                             ", pair by pair; each step = 1 ordered pair "
                                              f"(photo+geo linearisation + error evaluation), extrapolated x{npairs}",
                                  "num_samples": args.ref_samples or wl["W"] * wl["H"]},
                       "ms_per_pair": t_pair * 1e3}))
@@ -497,7 +500,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "shim"])
     ap.add_argument("--small", action="store_true", help="tiny debug workload (not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tracker", action="store_true", help="skip the configs[1] tracker latency measurement")
@@ -512,7 +515,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_cpu(args)
-    elif args.impl == "reference-gpu":
+    elif args.impl in ("reference-gpu", "shim"):
         run_reference_gpu(args)
     else:
         run_ours(args)

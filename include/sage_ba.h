@@ -87,6 +87,9 @@ typedef struct sage_ba_keyframe_desc
 
 int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *desc, sage_ba_keyframe **kf);
 void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf);
+/* Replace the keyframe's dpt_map_bias ([H*W], HOST or DEVICE per `memory`) in place.  Used by the df:: shim, which receives
+ * KF1's state-dependent depth map instead of (bias, code) from the reference's geometric operators. */
+int sage_ba_keyframe_set_bias(sage_ba_context *ctx, sage_ba_keyframe *kf, const float *dpt_map_bias, int memory);
 /* the CameraPyramid<float> derived for this keyframe (common/camera_pyramid.h:18-32) */
 int sage_ba_keyframe_cameras(const sage_ba_keyframe *kf, sage_ba_camera *cams /* [levels] */, int *level_offsets);
 

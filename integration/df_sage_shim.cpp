@@ -83,7 +83,7 @@ struct KfDeleter
   void operator()(sage_ba_keyframe *k) const { sage_ba_keyframe_destroy(c, k); }
 };
 using KfPtr = std::shared_ptr<sage_ba_keyframe>;
-using KfKey = std::tuple<const void *, const void *, const void *, const void *, const void *, const void *, long>;
+using KfKey = std::tuple<const void *, const void *, const void *, const void *, const void *, long, long, long, long>;
 // Heap objects that are never destroyed: at process exit torch and the CUDA context may already be gone.
 std::map<KfKey, KfPtr> &g_cache = *new std::map<KfKey, KfPtr>();
 std::vector<at::Tensor> &g_keep = *new std::vector<at::Tensor>(); // source tensors stay alive, so a pointer is never reused
@@ -95,17 +95,23 @@ struct FrameView
   at::Tensor feat_pyramid, grad_pyramid, bias, jac, mask, loc1d, homo;
 };
 
-KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int levels, int F, int C, bool cache = true)
+KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int levels, int F, int C, bool key_bias = true)
 {
   auto ptr = [](const at::Tensor &t) -> const void * { return t.defined() ? t.data_ptr() : nullptr; };
-  const KfKey key{ptr(v.feat_pyramid), ptr(v.grad_pyramid), ptr(v.bias), ptr(v.jac), ptr(v.mask), ptr(v.loc1d),
-                  v.homo.defined() ? (long)v.homo.size(0) : 0};
+  // identity = the frame's persistent tensors; the sample locations are a frame member too, but callers hand over per-call
+  // casts of them (geometric_factor.cpp:344), so only their count takes part.  key_bias lets a caller key a keyframe whose
+  // bias is state dependent (KF1 of the geometric operators) on its other tensors only.
+  const KfKey key{ptr(v.feat_pyramid), ptr(v.grad_pyramid), key_bias ? ptr(v.bias) : nullptr, ptr(v.jac), ptr(v.mask),
+                  v.homo.defined() ? (long)v.homo.size(0) : 0, (long)cam0.width(), (long)cam0.height(), (long)levels};
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (cache)
   {
     auto it = g_cache.find(key);
     if (it != g_cache.end())
+    {
+      if (!key_bias) // same frame, new state: refresh the depth map in place
+        SAGE_OK(sage_ba_keyframe_set_bias(ctx(), it->second.get(), v.bias.to(at::kFloat).contiguous().data_ptr<float>(), SAGE_BA_DEVICE));
       return it->second;
+    }
   }
   sage_ba_keyframe_desc d{};
   d.memory = SAGE_BA_DEVICE;
@@ -149,13 +155,12 @@ KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int lev
   sage_ba_context *c = ctx();
   SAGE_OK(sage_ba_keyframe_create(c, &d, &kf));
   KfPtr out(kf, KfDeleter{c});
-  if (cache)
-  {
-    g_cache[key] = out;
-    for (const at::Tensor *t : {&v.feat_pyramid, &v.grad_pyramid, &v.bias, &v.jac, &v.mask, &v.loc1d, &v.homo})
-      if (t->defined())
-        g_keep.push_back(*t);
-  }
+  g_cache[key] = out;
+  for (const at::Tensor *t : {&v.feat_pyramid, &v.grad_pyramid, &v.jac, &v.mask})
+    if (t->defined())
+      g_keep.push_back(*t);
+  if (key_bias && v.bias.defined())
+    g_keep.push_back(v.bias);
   return out;
 }
 
@@ -308,8 +313,10 @@ float geometric_error_calculate(const at::Tensor rotation, const at::Tensor tran
   KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0, sampled_locations_homo_0}, camera,
                        1, 16, CS);
   const long HW = dpt_map_1.numel();
-  const at::Tensor zero_basis = torch::zeros({HW, (long)CS}, dpt_map_1.options());
-  KfPtr kf1 = keyframe({{}, {}, dpt_map_1.reshape({-1}), zero_basis, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*cache=*/false);
+  static thread_local at::Tensor zero_basis; // the error-only operator needs no basis of KF1
+  if (!zero_basis.defined() || zero_basis.size(0) != HW || zero_basis.device() != dpt_map_1.device())
+    zero_basis = torch::zeros({HW, (long)CS}, dpt_map_1.options());
+  KfPtr kf1 = keyframe({{}, {}, dpt_map_1.reshape({-1}), zero_basis, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*key_bias=*/false);
   const auto R = hostf(rotation), t = hostf(translation), code = hostf(code_0);
   const std::vector<float> code1(CS, 0.f);
   float err = 0.f;
@@ -332,7 +339,7 @@ void geometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &erro
                        1, 16, CS);
   const at::Tensor unscaled = (dpt_map_1 / scale_1).reshape({-1}).contiguous();
   const at::Tensor basis1 = dpt_jac_code_1.reshape({-1, (long)CS}); // [H, W, C] -> [HW, C]
-  KfPtr kf1 = keyframe({{}, {}, unscaled, basis1, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*cache=*/false);
+  KfPtr kf1 = keyframe({{}, {}, unscaled, basis1, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*key_bias=*/false);
   constexpr int D = 14 + 2 * CS;
   std::vector<float> A(D * D), b(D);
   const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sage_ba_synchronize": (C.c_int, [vp]),
     "sage_ba_keyframe_create": (C.c_int, [vp, C.POINTER(KeyframeDesc), C.POINTER(vp)]),
     "sage_ba_keyframe_destroy": (None, [vp, vp]),
+    "sage_ba_keyframe_set_bias": (C.c_int, [vp, vp, vp, C.c_int]),
     "sage_ba_keyframe_cameras": (C.c_int, [vp, C.POINTER(Camera), c_int_p]),
     "sage_ba_photometric_jac_error": (C.c_int, [vp, vp, vp] + [vp] * 7 + [F, F, vp, vp, vp, vp, vp]),
     "sage_ba_photometric_error": (C.c_int, [vp, vp, vp, vp, vp, vp, F, F, vp, vp, vp]),

@@ -299,6 +299,18 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
   SAGE_CATCH
 }
 
+int sage_ba_keyframe_set_bias(sage_ba_context *ctx, sage_ba_keyframe *kf, const float *dpt_map_bias, int memory)
+{
+  SAGE_TRY(ctx)
+  SAGE_CHECK(kf && kf->bias && dpt_map_bias, "keyframe has no depth data");
+  SAGE_CHECK(memory == SAGE_BA_HOST || memory == SAGE_BA_DEVICE, "memory must be SAGE_BA_HOST or SAGE_BA_DEVICE");
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  SAGE_CUDA(cudaMemcpyAsync(kf->bias, dpt_map_bias, sizeof(float) * kf->H * kf->W,
+                            memory == SAGE_BA_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  SAGE_CUDA(cudaStreamSynchronize(ctx->stream));
+  SAGE_CATCH
+}
+
 void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf)
 {
   if (!kf)
