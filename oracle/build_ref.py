@@ -85,7 +85,7 @@ def build(configs=CONFIGS, force=False, jobs=8):
     for l in links:
         _run(l)
     for f in os.listdir(OUT):
-        if f.endswith(".o"):
+        if f.endswith(".o") and not f.endswith("_ref_ext.o"):  # the pybind front's object is reused by build_shim()
             os.remove(os.path.join(OUT, f))
     return True
 
@@ -126,11 +126,16 @@ def build_shim(configs=CONFIGS, force=False, jobs=8):
                   "-include", os.path.join(HERE, "ref_shims", "sage_ref_compat.h"),
                   f"-DDF_CODE_SIZE={cs}", f"-DDF_FEAT_SIZE={fs}", f"-DTORCH_EXTENSION_NAME={name}",
                   "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI))] + inc
-        objs = []
-        for src in (shim_src, os.path.join(HERE, "ref_ext.cpp")):
-            obj = os.path.join(OUT, f"{name}_{os.path.basename(src)[:-4]}.o")
-            tasks.append(common + ["-c", src, "-o", obj])
-            objs.append(obj)
+        obj = os.path.join(OUT, f"{name}_df_sage_shim.o")
+        tasks.append(common + ["-c", shim_src, "-o", obj])
+        # the pybind front is the reference module's object, module name included (load_shim imports the file under that
+        # name): build() leaves it behind; compile it here only if it is missing
+        ref_name = f"sage_ref_c{cs}_f{fs}"
+        front = os.path.join(OUT, f"{ref_name}_ref_ext.o")
+        if not os.path.exists(front):
+            tasks.append([c if not c.startswith("-DTORCH_EXTENSION_NAME=") else f"-DTORCH_EXTENSION_NAME={ref_name}" for c in common] +
+                         ["-c", os.path.join(HERE, "ref_ext.cpp"), "-o", front])
+        objs = [obj, front]
         links.append(["nvcc", "-shared", "-o", so] + objs +
                      ["-L", torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-ltorch_python",
                       "-L", libdir, "-lsage_ba", "-Xlinker", "-rpath", "-Xlinker", torch_lib,
@@ -153,7 +158,7 @@ def load_shim(cs, fs):
     path = shim_path(cs, fs)
     if not os.path.exists(path):
         raise FileNotFoundError(path)
-    name = f"sage_shim_c{cs}_f{fs}"
+    name = f"sage_ref_c{cs}_f{fs}"  # the pybind front object is shared with the reference module, so is its init symbol
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

@@ -506,7 +506,12 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
   float *hc = reinterpret_cast<float *>(ctx->hfactor.ensure(1024));
   memcpy(hc + 512 / 4, code1, sizeof(float) * C);
   SAGE_CUDA(cudaMemcpyAsync(dcode, hc + 512 / 4, sizeof(float) * C, cudaMemcpyHostToDevice, s));
-  launch_depth_maps(kf1->bias, kf1->basis, dcode, kf1->mask, kf1->dgm, kf1->dscr, kf1->H, kf1->W, C, s);
+  // KF1's state-dependent depth map lives in the CONTEXT, not in the keyframe: the reference calls this operator from several
+  // threads that may share kf1 (TBB workers linearising new factors, NonlinearFactorGraph.cpp:329-335)
+  const size_t HW1 = (size_t)kf1->H * kf1->W;
+  float4 *dgm = reinterpret_cast<float4 *>(ctx->geo_dgm.ensure(4 * HW1));
+  float *dscr = ctx->geo_dscr.ensure(HW1);
+  launch_depth_maps(kf1->bias, kf1->basis, dcode, kf1->mask, dgm, dscr, kf1->H, kf1->W, C, s);
   ctx->launches += 2;
 
   GeoFactor f;
@@ -515,7 +520,7 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
   f.basis0 = kf0->basis;
   f.loc1d = kf0->loc1d;
   f.homo = kf0->homo;
-  f.dgm1 = kf1->dgm;
+  f.dgm1 = dgm;
   f.basis1 = kf1->basis;
   f.N = kf0->N;
   fill_pose(f.R10, f.t10, R10, t10);

@@ -117,6 +117,7 @@ struct sage_ba_context
   sage::PinBuf<float> hout;
   sage::PinBuf<unsigned char> hfactor;
   sage::DevBuf<float> tmp_code;
+  sage::DevBuf<float> geo_dgm, geo_dscr; // KF1 depth map (D, dx, dy, mask) of the single-factor geometric operator
   // tracker scratch
   sage::DevBuf<float> trk_dpts, trk_homo, trk_feats, trk_m_dpts, trk_m_homo, trk_m_2d;
   // descriptor cycle-matching scratch (descriptor.cu)

@@ -89,3 +89,47 @@ def test_device_pyramid_builder_matches_host_builder(sage_ctx, name):
                                                         a["code0"], a["scale0"], a["eps"], a["weights"]))
     (A0, b0, e0, n0), (A1, b1, e1, n1) = outs
     assert n0 == n1 and helpers.rel_err(A1, A0) <= 1e-5 and helpers.rel_err(b1, b0) <= 1e-5 and abs(e1 - e0) <= 1e-5 * e0
+
+
+@pytest.mark.gpu
+def test_operators_are_reentrant_from_four_threads(sage_ctx):
+    """The reference's operators are entered from up to four host threads on shared frames (core/deepfactors.cpp:1497-1505;
+    TBB workers linearising new factors): one context per thread, the SAME device keyframes, different states per thread --
+    every thread must get exactly what it gets alone."""
+    import threading
+
+    import sage_slam_b200 as sage
+    from sage_slam_b200 import ops
+
+    kfs = helpers.build_case("small_c8_f16")
+    a = helpers.case_args(kfs)
+    d0, d1 = sage.DeviceKeyframe(sage_ctx, kfs[0]), sage.DeviceKeyframe(sage_ctx, kfs[1])
+    rng = np.random.default_rng(3)
+    states = [(a["code0"] + 0.05 * rng.standard_normal(a["code0"].shape).astype(np.float32),
+               a["code1"] + 0.05 * rng.standard_normal(a["code1"].shape).astype(np.float32), float(a["scale1"] * (1 + 0.02 * t)))
+              for t in range(4)]
+
+    def work(ctx, st):
+        c0, c1, s1 = st
+        p = ops.photometric_jac_error_calculate(ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], c0, a["scale0"],
+                                                a["eps"], a["weights"])
+        g = ops.geometric_jac_error_calculate(ctx, d0, d1, a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], c0, c1, a["scale0"],
+                                              s1, a["eps"], a["geo_loss"], a["geo_weight"])
+        return [np.asarray(x).copy() for x in (p[0], p[1], p[2], g[0], g[1], g[2])]
+
+    alone = [work(sage_ctx, st) for st in states]
+    got = [None] * 4
+    ctxs = [sage.Context(0) for _ in range(4)]
+
+    def run(t):
+        for _ in range(8):
+            got[t] = work(ctxs[t], states[t])
+
+    th = [threading.Thread(target=run, args=(t,)) for t in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for t in range(4):
+        for x, y in zip(got[t], alone[t]):
+            np.testing.assert_array_equal(x, y)
