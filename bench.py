@@ -302,7 +302,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "photo_kernel<32,32,MAP_JAC> (photometric linearisation, all owned pairs per launch)",
                          "achieved": achieved, "peak": hbm, "peak_source": src, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": shard["photo"] * b_photo},
+                         "traffic": traffic, "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": shard["photo"] * b_photo,
+                         "note": "bound is HBM by algorithmic bytes; the measured limiter is the L1 data pipe (61 % busy, DRAM 8 %: "
+                                 "profiles/r1c_ncu_full_summary.json), see profiles/README.md"},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "clocks": clocks,
             "lm_trace": [(float(a), float(b)) for a, b in costs[-args.steps:]][:6],

@@ -27,6 +27,9 @@ namespace sage
 {
 
 constexpr int DM_THREADS = 256; // keypoints per CTA
+#ifndef DM_PIX_UNROLL
+#define DM_PIX_UNROLL 4 // independent pixels in flight per thread: the channel sum of one pixel is a dependent chain
+#endif
 
 // q[k][c] = desc[c][loc[k]]
 __global__ void desc_gather_kernel(const float *__restrict__ desc, const int *__restrict__ loc, int K, int CD, int HW, float *__restrict__ q)
@@ -44,6 +47,7 @@ desc_response_kernel(const float *__restrict__ desc /* [CD][HW] */, const float 
                      float *__restrict__ pbest /* [nchunks][K] */, int *__restrict__ pidx)
 {
   constexpr int DM_TILE = CD <= 32 ? 256 : 128; // pixels staged per pass (<= 37 KB of shared memory)
+  constexpr int kPixUnroll = DM_PIX_UNROLL;
   constexpr int ST = CD + 4; // padded pixel stride: 16-byte aligned rows, 4-way instead of 16-way conflicts on the transposing store
   __shared__ __align__(16) float tile[DM_TILE * ST];
   const int k = blockIdx.y * DM_THREADS + threadIdx.x;
@@ -69,7 +73,7 @@ desc_response_kernel(const float *__restrict__ desc /* [CD][HW] */, const float 
         tile[p * ST + c] = __ldg(desc + (size_t)c * HW + p0 + p);
     }
     __syncthreads();
-#pragma unroll 2
+#pragma unroll kPixUnroll
     for (int p = 0; p < np; ++p)
     {
       const float *b = tile + p * ST;

@@ -3,6 +3,8 @@
     PhotometricFactor   core/gtsam/photometric_factor.cpp:72 (error), :106-219 (linearize), :264-311
     GeometricFactor     core/gtsam/geometric_factor.cpp:41, :67-233, :300-356
     ReprojectionFactor  core/gtsam/reprojection_factor.cpp:201, :227-317, :332-396
+    MatchGeometryFactor core/gtsam/match_geometry_factor.cpp (same structure; 3-D point-to-point term of loop closure / scale init)
+    cycle_matches       the matching part of both constructors (reprojection_factor.cpp:36-112, match_geometry_factor.cpp:40-118)
 
 Same responsibilities as the reference classes: unpack `Values` (pose_wk as (R, t), code, scale), build the
 relative pose T10 = T1^-1 T0 in fp32 (photometric_factor.cpp:280-281), call the operator (here: the C ABI),
@@ -193,3 +195,61 @@ class ReprojectionFactor:
                                                               np.asarray(c[self.keys[2]], F32), float(c[self.keys[3]]), self.loc,
                                                               self.homo, self.m2d, self.eps, self.loss_param, self.weight)
         return _partition(AtA, Atb, self.keys, [6, 6, self.kf.C, 1], e, self.psd)
+
+
+def cycle_matches(ctx, kf_rec, fr_rec, num_keypoints, cyc_consis_thresh, seed=None):
+    """The descriptor-matching part of the ReprojectionFactor / MatchGeometryFactor constructors
+    (reprojection_factor.cpp:36-112): draw `num_keypoints` of kf's valid locations, cycle-match their descriptors against fr
+    (ops.cycle_feature_matching = row f3 on the device), keep the cycle-consistent ones.
+
+    kf_rec / fr_rec are frames.Keyframe records with feat_desc.  Returns None without inliers, else a dict with the
+    reference's member names: matched_locations_1d_0 [M] int32, matched_locations_homo_0 [M,3], matched_locations_1d_1 [M] int32,
+    matched_locations_2d_1 [M,2], matched_locations_homo_1 [M,3], desc_inlier_ratio.
+    Not reproduced: libstdc++'s std::shuffle (a numpy MT19937 permutation seeded kf.id * fr.id like the reference is used)
+    and the TEASER++ filtering that follows (reprojection_factor.cpp:136-186, third-party)."""
+    n = len(kf_rec.sampled_locations_1d)
+    K = min(int(num_keypoints), n)
+    rs = np.random.RandomState(kf_rec.id * fr_rec.id if seed is None else seed)
+    idx = rs.permutation(n)[:K]
+    kp = np.asarray(kf_rec.sampled_locations_1d)[idx]
+    r = ops.cycle_feature_matching(ctx, kf_rec.feat_desc, fr_rec.feat_desc, kp, cyc_consis_thresh)
+    sel = r["inlier_within_keypoint_indexes"]
+    if len(sel) == 0:
+        return None
+    cam = fr_rec.camera_pyramid[0]
+    uv = r["matched_locations_2d_1"].astype(F32)
+    homo1 = np.stack([(uv[:, 0] - F32(cam[2])) / F32(cam[0]), (uv[:, 1] - F32(cam[3])) / F32(cam[1]), np.ones(len(uv), F32)], 1)
+    return {"matched_locations_1d_0": kp[sel].astype(np.int32),
+            "matched_locations_homo_0": np.asarray(kf_rec.sampled_locations_homo)[idx[sel]].astype(F32),
+            "matched_locations_1d_1": r["matched_locations_1d_1"].astype(np.int32), "matched_locations_2d_1": uv,
+            "matched_locations_homo_1": homo1.astype(F32), "desc_inlier_ratio": len(sel) / float(K)}
+
+
+class MatchGeometryFactor:
+    """keys (pose0, pose1, code0, code1, scale0, scale1); 3-D point-to-point term between matched keypoints with the depths of
+    both keyframes (core/gtsam/match_geometry_factor.cpp; kernels cuda/match_geometry_factor_kernels.cpp:1567-1823)."""
+
+    def __init__(self, ctx, kf0, kf1, matches, factor_weight, loss_param, robust_loss_type="fair", inlier_multiplier=1.0, psd="reference"):
+        self.ctx, self.kf0, self.kf1, self.m = ctx, kf0, kf1, matches
+        self.weight, self.loss_param, self.loss_type, self.psd = inlier_multiplier * factor_weight, loss_param, robust_loss_type, psd
+        i, j = kf0.kf.id, kf1.kf.id
+        self.keys = [pose_key(i), pose_key(j), code_key(i), code_key(j), scale_key(i), scale_key(j)]
+
+    def dim(self):
+        return 14 + 2 * self.kf0.C
+
+    def _args(self, c):
+        m = self.m
+        return (np.asarray(c[self.keys[2]], F32), np.asarray(c[self.keys[3]], F32), m["matched_locations_homo_0"],
+                m["matched_locations_homo_1"], m["matched_locations_1d_0"], m["matched_locations_1d_1"], float(c[self.keys[4]]),
+                float(c[self.keys[5]]), self.loss_param, self.weight, self.loss_type)
+
+    def error(self, c):
+        R10, t10, *_ = _rel(c[self.keys[0]], c[self.keys[1]])
+        return float(ops.match_geometry_error_calculate(self.ctx, self.kf0, self.kf1, R10, t10, *self._args(c)))
+
+    def linearize(self, c):
+        R10, t10, R0, t0, R1, t1 = _rel(c[self.keys[0]], c[self.keys[1]])
+        AtA, Atb, e = ops.match_geometry_jac_error_calculate(self.ctx, self.kf0, self.kf1, R10, t10, R0, t0, R1, t1, *self._args(c))
+        C = self.kf0.C
+        return _partition(AtA, Atb, self.keys, [6, 6, C, C, 1, 1], e, self.psd)

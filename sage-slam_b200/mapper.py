@@ -16,7 +16,7 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-from . import capi, ops
+from . import capi, factors, ops
 from .frames import Keyframe
 from .local_ba import LocalBA
 
@@ -114,16 +114,12 @@ class BatchedMapper:
         kf, fr = self.map.keyframes[i], self.map.keyframes[j]
         if kf.feat_desc is None or fr.feat_desc is None:
             return None
-        n = len(kf.sampled_locations_1d)
-        K = min(self.opts.desc_num_keypoints, n)
-        idx = np.random.RandomState(kf.id * fr.id).permutation(n)[:K]
-        kp = kf.sampled_locations_1d[idx]
-        r = ops.cycle_feature_matching(self.ctx, kf.feat_desc, fr.feat_desc, kp, self.opts.desc_cyc_consis_thresh)
-        sel = r["inlier_within_keypoint_indexes"]
-        self.match_stats[(i, j)] = (len(sel), K)
-        if len(sel) == 0:
+        r = factors.cycle_matches(self.ctx, kf, fr, self.opts.desc_num_keypoints, self.opts.desc_cyc_consis_thresh)
+        K = min(self.opts.desc_num_keypoints, len(kf.sampled_locations_1d))
+        self.match_stats[(i, j)] = (0 if r is None else len(r["matched_locations_1d_0"]), K)
+        if r is None:
             return None
-        return (kp[sel].astype(np.int32), kf.sampled_locations_homo[idx[sel]].astype(F32), r["matched_locations_2d_1"].astype(F32))
+        return (r["matched_locations_1d_0"], r["matched_locations_homo_0"], r["matched_locations_2d_1"])
 
     # ------------------------------------------------------------------------------------------ MappingStep
     def mapping_step(self, iters=None):

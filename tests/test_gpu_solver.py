@@ -172,6 +172,49 @@ def test_factor_classes_error_linearize(sage_ctx):
     rf = factors.ReprojectionFactor(sage_ctx, d0, d1, ma["mloc"], ma["mhomo"], ma["m2d"], a["rep_weight"], a["rep_loss"])
     hr = rf.linearize(vals)
     assert len(hr.Gs) == 10 and abs(rf.error(vals) - hr.f) / hr.f <= 1e-4
+    # MatchGeometryFactor on hand-made matches against the oracle, all four robust losses
+    mm = {"matched_locations_1d_0": ma["mloc"], "matched_locations_homo_0": ma["mhomo"], "matched_locations_1d_1": ma["mloc1"],
+          "matched_locations_homo_1": ma["mhomo1"]}
+    for lt in helpers.MG_LOSSES:
+        mf = factors.MatchGeometryFactor(sage_ctx, d0, d1, mm, ma["mg_weight"], ma["mg_loss"], robust_loss_type=lt, psd="none")
+        hm = mf.linearize(vals)
+        A, b, e = O.match_geometry_jac_error(a["R10"], a["t10"], a["R0"], a["t0"], a["R1"], a["t1"], a["bias0"], a["bias1"], a["jac0"],
+                                             a["jac1"], a["code0"], a["code1"], ma["mhomo"], ma["mhomo1"], ma["mloc"], ma["mloc1"],
+                                             a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"], lt)[:3]
+        G, g = hm.information()
+        assert helpers.rel_err(G, (A + A.T) / 2) <= 1e-4 and helpers.rel_err(g, b) <= 1e-4 and abs(hm.f - e) <= 1e-4 * abs(e)
+        e_only = O.match_geometry_error(a["R10"], a["t10"], a["bias0"], a["bias1"], a["jac0"], a["jac1"], a["code0"], a["code1"], ma["mhomo"],
+                                        ma["mhomo1"], ma["mloc"], ma["mloc1"], a["scale0"], a["scale1"], ma["mg_loss"], ma["mg_weight"], lt)
+        e_only = float(np.asarray(e_only).reshape(-1)[0])  # the error-only kernel of the reference is its own function (may differ from f)
+        assert len(hm.Gs) == 21 and mf.dim() == 30 and abs(mf.error(vals) - e_only) <= 1e-4 * abs(e_only)
+
+
+@pytest.mark.gpu
+def test_factors_from_descriptor_matches(sage_ctx):
+    """The constructors' matching step end to end: descriptors -> cycle matches (row f3) -> Reprojection / MatchGeometry
+    factors; with view-consistent synthetic descriptors the matches are true correspondences, so both factors must be small
+    at the ground-truth poses and grow when a pose is perturbed."""
+    from sage_slam_b200 import factors
+
+    kfs = sage.synthetic.make_scene(num_kf=2, W=64, H=48, L=3, F=16, C=8, seed=21, with_desc=True, pose_noise=0.0)
+    d0, d1 = sage.DeviceKeyframe(sage_ctx, kfs[0]), sage.DeviceKeyframe(sage_ctx, kfs[1])
+    m = factors.cycle_matches(sage_ctx, kfs[0], kfs[1], 128, 2.0)
+    assert m is not None and m["desc_inlier_ratio"] > 0.5
+    M = len(m["matched_locations_1d_0"])
+    assert m["matched_locations_homo_0"].shape == (M, 3) and m["matched_locations_2d_1"].shape == (M, 2)
+    vals = factors.Values()
+    for k in kfs:
+        vals[factors.pose_key(k.id)] = k.pose_wk_true
+        vals[factors.code_key(k.id)] = k.code.astype(np.float64)
+        vals[factors.scale_key(k.id)] = k.dpt_scale
+    rf = factors.ReprojectionFactor(sage_ctx, d0, d1, m["matched_locations_1d_0"], m["matched_locations_homo_0"], m["matched_locations_2d_1"],
+                                    0.1, 0.03 * 64 ** 2)
+    mf = factors.MatchGeometryFactor(sage_ctx, d0, d1, m, 0.1, 1.0)
+    e_r, e_m = rf.error(vals), mf.error(vals)
+    R, t = kfs[1].pose_wk_true
+    moved = factors.Values(vals)
+    moved[factors.pose_key(1)] = (R, (t + np.array([0.1, 0.0, 0.0], np.float32)).astype(np.float32))
+    assert rf.error(moved) > 1.2 * e_r and mf.error(moved) > 1.2 * e_m
 
 
 @pytest.mark.gpu
