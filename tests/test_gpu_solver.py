@@ -340,3 +340,49 @@ def test_full_and_sparse_covisibility_graphs_match_dense_oracle(sage_ctx, kind, 
     assert np.abs(d_gpu - d_same).max() <= 1e-9 * max(1.0, np.abs(d_same).max())
     rep = ba.lm(max_iters=4)
     assert rep["final_cost"] < rep["initial_cost"]
+
+
+@pytest.mark.gpu
+def test_global_graph_256_keyframes(sage_ctx):
+    """BASELINE configs[4] in shape (256 keyframes, sparse covisibility of average degree 8, all three factor kinds on every
+    ordered pair: 6144 factors, 3840 variables) at reduced image size: the batched path must assemble, solve (fused Schur on
+    the dense system) and converge; the step must satisfy the damped normal equations it was computed from."""
+    K = 256
+    kfs = sage.synthetic.make_scene(num_kf=K, step=0.005, rot_step_deg=0.2, **{**pc.PRM, "W": 48, "H": 32, "L": 2})
+    rng = np.random.default_rng(11)
+    und = {(i, i + 1) for i in range(K - 1)}
+    while len(und) < 4 * K:  # average degree 8
+        i = int(rng.integers(0, K))
+        j = int(np.clip(i + rng.integers(-12, 13), 0, K - 1))  # covisible keyframes are near in time, plus a few loop closures
+        if rng.random() < 0.05:
+            j = int(rng.integers(0, K))
+        if i != j:
+            und.add((min(i, j), max(i, j)))
+    pairs = [p for (i, j) in sorted(und) for p in ((i, j), (j, i))]
+    assert len(pairs) == 8 * K
+    dk = [sage.DeviceKeyframe(sage_ctx, k) for k in kfs]
+    ba = sage.LocalBA(sage_ctx, dk)
+    for i, j in pairs:
+        ba.add_photometric(i, j, helpers.PHOTO_WEIGHTS[:2])
+        ba.add_geometric(i, j, pc.geo_loss(kfs), 0.1)
+        loc, homo, uv = sage.synthetic.make_matches(kfs[i], kfs[j], M=32)
+        ba.add_reprojection(i, j, loc, homo, uv, 0.03 * 48 ** 2, 0.1)
+    for k in range(K):
+        ba.add_code_prior(k, pc.CODE_W)
+        ba.add_scale_prior(k, 1.0, pc.SCALE_W)
+    ba.fix(0, pose=True, scale=True)
+    ba.set_state([k.pose_wk for k in kfs], np.stack([k.code for k in kfs]), [k.dpt_scale for k in kfs], helpers.EPS)
+    assert ba.dim == K * (7 + pc.PRM["C"])
+    ba.linearize()
+    H, g, cost = ba.assemble(want_matrix=True)
+    damp = 1e-3
+    d = ba.solve(damp, want_delta=True)
+    fixed = list(range(6)) + [6 * K + pc.PRM["C"]]
+    Hd = H + damp * np.diag(np.diag(H))
+    free = np.setdiff1d(np.arange(len(g)), fixed)
+    r = Hd[np.ix_(free, free)] @ d[free] - g[free]
+    assert np.abs(r).max() <= 1e-8 * max(1.0, np.abs(g).max()) and np.all(d[fixed] == 0)
+    rep = ba.lm(max_iters=5)
+    assert rep["final_cost"] < 0.9 * rep["initial_cost"] and rep["accepted"] >= 1
+    for x in dk:
+        x.close()
