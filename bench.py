@@ -193,15 +193,9 @@ def run_ours(args):
         state = {"damp": 1e-4, "cost": None}
 
         def lm_iteration():
-            ba.linearize()  # includes the all-reduce of the packed factor buffer when world > 1
-            cost = ba.assemble()
-            ba.solve(state["damp"])
-            cand = ba.evaluate(candidate=True)
-            if cand < cost:
-                ba.accept()
-                state["damp"] = max(1e-6, state["damp"] / 10.0)
-            else:
-                state["damp"] = min(1e2, state["damp"] * 10.0)
+            # one LM iteration through the library's own driver: linearise (+ all-reduce of the packed factor buffer when
+            # world > 1) -> assemble -> solve -> evaluate the candidate -> accept / reject, one host synchronisation
+            cost, cand, _, state["damp"] = ba.lm_step(state["damp"], min_damp=1e-6, max_damp=1e2)
             state["cost"] = min(cand, cost)
             return cost, cand
 

@@ -390,6 +390,13 @@ typedef struct sage_ba_lm_report
   double initial_cost, final_cost, final_damp;
 } sage_ba_lm_report;
 
+/* One LM iteration exactly as BASELINE defines it (linearise every factor at the current estimate -> assemble -> Schur solve
+ * with *damp -> evaluate the candidate -> accept / reject), enqueued back to back with ONE host synchronisation that returns
+ * both costs.  *damp is updated by the tracker's rule (divide by damp_dec_factor on acceptance, multiply by damp_inc_factor
+ * otherwise, clamped; camera_tracker.cpp:1218-1245).  The reference's hand-written LM syncs >= 6 times per iteration. */
+int sage_ba_problem_lm_step(sage_ba_problem *p, double *damp, double min_damp, double max_damp, double damp_dec_factor,
+                            double damp_inc_factor, double *cost, double *candidate_cost, int *accepted);
+
 /* Full LM loop (linearize -> [allreduce] -> assemble -> solve -> evaluate -> [allreduce] ->
  * accept/reject), acceptance rule as the tracker's (camera_tracker.cpp:1218-1245). */
 int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_ba_lm_report *report);

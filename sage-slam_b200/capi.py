@@ -118,6 +118,7 @@ SIGNATURES = {
     "sage_ba_problem_profile": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_profile_read": (C.c_int, [vp, c_double_p, C.POINTER(C.c_long), C.c_int]),
     "sage_ba_problem_shard_counts": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "sage_ba_problem_lm_step": (C.c_int, [vp, c_double_p, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p, c_double_p, c_int_p]),
     "sage_ba_problem_lm": (C.c_int, [vp, C.POINTER(LMOptions), C.POINTER(LMReport)]),
 }
 

@@ -1307,6 +1307,44 @@ int sage_ba_problem_shard_counts(const sage_ba_problem *p, int *n_photo, int *n_
   return 0;
 }
 
+int sage_ba_problem_lm_step(sage_ba_problem *p, double *damp, double min_damp, double max_damp, double damp_dec_factor,
+                            double damp_inc_factor, double *cost, double *candidate_cost, int *accepted)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(damp, "null damping");
+  problem_build(p);
+  cudaStream_t s = ctx__->stream;
+  // everything of the iteration is enqueued before the host looks at anything: linearise, assemble, solve, evaluate the
+  // candidate; ONE synchronisation then delivers both costs (the damping of this step does not depend on them)
+  SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
+  if (p->allreduce && p->world > 1)
+    SAGE_CHECK(p->allreduce(p->fbuf.p, p->fbuf_count, p->allreduce_user) == 0, "all-reduce callback failed");
+  SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, nullptr) == 0, ctx__->err);
+  SAGE_CUDA(cudaMemcpyAsync(p->hcost.p, p->total_cost.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SAGE_CHECK(sage_ba_problem_solve(p, *damp, nullptr) == 0, ctx__->err);
+  SAGE_CHECK(sage_ba_problem_evaluate(p, 1) == 0, ctx__->err);
+  if (p->allreduce && p->world > 1)
+    SAGE_CHECK(p->allreduce(p->cbuf.p, p->metas.size() * 2, p->allreduce_user) == 0, "all-reduce callback failed");
+  double cand = 0.0;
+  SAGE_CHECK(sage_ba_problem_cost(p, 1, &cand) == 0, ctx__->err); // the synchronisation
+  const double cur = p->hcost.p[0];
+  const bool ok = p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0 && cand < cur;
+  if (ok)
+  {
+    SAGE_CHECK(sage_ba_problem_accept(p) == 0, ctx__->err);
+    *damp = std::min(std::max(min_damp, *damp / damp_dec_factor), max_damp);
+  }
+  else
+    *damp = std::min(std::max(min_damp, *damp * damp_inc_factor), max_damp);
+  if (cost)
+    *cost = cur;
+  if (candidate_cost)
+    *candidate_cost = cand;
+  if (accepted)
+    *accepted = ok ? 1 : 0;
+  SAGE_PCATCH
+}
+
 int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_ba_lm_report *rep)
 {
   SAGE_PTRY(p)

@@ -249,6 +249,16 @@ class LocalBA:
         self.ctx.check(self.ctx.lib.sage_ba_problem_lm(self.h, C.byref(opt), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in capi.LMReport._fields_}
 
+    def lm_step(self, damp, min_damp=1e-6, max_damp=1e2, damp_dec_factor=10.0, damp_inc_factor=10.0):
+        """One LM iteration (linearise, assemble, solve, evaluate the candidate, accept / reject) with a single host
+        synchronisation.  Returns (cost, candidate_cost, accepted, new_damp)."""
+        d, c0, c1, acc = C.c_double(damp), C.c_double(0), C.c_double(0), C.c_int(0)
+        if self.world > 1 and self._cb is None:
+            self.enable_allreduce()
+        self.ctx.check(self.ctx.lib.sage_ba_problem_lm_step(self.h, C.byref(d), min_damp, max_damp, damp_dec_factor, damp_inc_factor,
+                                                            C.byref(c0), C.byref(c1), C.byref(acc)))
+        return c0.value, c1.value, bool(acc.value), d.value
+
     def profile(self, enable=True):
         self.ctx.check(self.ctx.lib.sage_ba_problem_profile(self.h, int(enable)))
 

@@ -386,3 +386,30 @@ def test_global_graph_256_keyframes(sage_ctx):
     assert rep["final_cost"] < 0.9 * rep["initial_cost"] and rep["accepted"] >= 1
     for x in dk:
         x.close()
+
+
+@pytest.mark.gpu
+def test_lm_step_equals_the_explicit_sequence(sage_ctx):
+    """sage_ba_problem_lm_step (one synchronisation per iteration) against the same iteration spelled out call by call."""
+    kfs, pairs, _ = pc.build(4)
+    a, _ = make_ba(sage_ctx, kfs, pairs)
+    b, _ = make_ba(sage_ctx, kfs, pairs)
+    damp_a = damp_b = 1e-4
+    for _ in range(4):
+        a.linearize()
+        cost = a.assemble()
+        a.solve(damp_a)
+        cand = a.evaluate(candidate=True)
+        if cand < cost:
+            a.accept()
+            damp_a = max(1e-6, damp_a / 10.0)
+        else:
+            damp_a = min(1e2, damp_a * 10.0)
+        c0, c1, acc, damp_b = b.lm_step(damp_b)
+        assert c0 == cost and c1 == cand and acc == (cand < cost) and damp_b == damp_a
+    sa, sb = a.get_state(), b.get_state()
+    for (Ra, ta), (Rb, tb) in zip(sa[0], sb[0]):
+        np.testing.assert_array_equal(Ra, Rb)
+        np.testing.assert_array_equal(ta, tb)
+    np.testing.assert_array_equal(sa[1], sb[1])
+    np.testing.assert_array_equal(sa[2], sb[2])
