@@ -12,8 +12,11 @@ Two layers:
     (core/mapping/mapper.cpp:1385-1426, mapping_utils.h:236-252), valid locations
     (mapping_utils.h:254-287), SE(3) exp / retract (mapping_utils.h:316-346,
     gtsam/gtsam_traits.h:45-70), NearestPsd (mapping_utils.h:104-128), the tracker's LM
-    loop (core/system/camera_tracker.cpp:1156-1279) and a dense fp64 normal-equation
-    solve that stands in for the (unbuildable) GTSAM solve.
+    loop (core/system/camera_tracker.cpp:1156-1279), the descriptor cycle-matching of the
+    factor constructors (core/gtsam/reprojection_factor.cpp:57-92; pinned by the torch replay
+    of those lines in make_golden_desc.py, CPU and B200), UpdateDepth (mapping_utils.h:216-222)
+    and a dense fp64 normal-equation solve that stands in for the (unbuildable) GTSAM solve
+    (solver-level parity is therefore UNPINNED by the reference).
 """
 import ctypes
 import os
