@@ -1,5 +1,7 @@
 """CPU: host-side pieces of the path -- camera pyramid, Gaussian pyramid + gradients, retraction, NearestPsd,
 the tracker LM restatement, factor packing / dense assembly -- against independent restatements."""
+import os
+
 import numpy as np
 import torch
 
@@ -145,3 +147,23 @@ def test_factor_partition_and_nearest_psd_match_oracle():
     np.testing.assert_array_equal(g, b.astype(np.float64))
     hg = factors._partition(np.eye(14 + 2 * C), np.zeros(14 + 2 * C), list(range(6)), [6, 6, C, C, 1, 1], 0.0, "none")
     assert len(hg.Gs) == 21
+
+
+def test_bench_accounting_matches_the_survey():
+    """bench.py's roofline numerator is SURVEY.md section 8(d)'s per-pair figure: 68.2 / 40.3 / 23.9 MB at 320x256, F = C = 32,
+    L = 4, dense sampling; the clock sampler degrades to a well-formed record where neither NVML nor nvidia-smi has a GPU."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("sage_bench", os.path.join(helpers.ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    photo, photo_err, geo = bench.algorithmic_bytes(bench.WORKLOAD)
+    assert abs(photo / 1e6 - 68.2) < 0.1 and abs(photo_err / 1e6 - 40.3) < 0.1 and abs(geo / 1e6 - 23.9) < 0.1
+    wl = bench.WORKLOAD
+    assert (wl["num_kf"], wl["W"], wl["H"], wl["F"], wl["C"], wl["L"]) == (32, 320, 256, 32, 32, 4)  # BASELINE configs[3]
+    s = bench.ClockSampler(0)
+    s.start()
+    s.mark_begin()
+    s.mark_end()
+    c = s.stop()
+    assert set(c) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
