@@ -325,11 +325,22 @@ struct Syrk
 //   A (16x8, row): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B (8x8, col): b0 (t, g) b1 (t+4, g)
 //   C (16x8): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)       with g = lane >> 2, t = lane & 3
 // ------------------------------------------------------------------------------------------------
+// x = hi + lo with hi, lo representable in TF32 (sign, 8 exponent, 10 mantissa bits = the top 19 bits of an fp32 word).
+// Truncation split: hi = x with the low 13 mantissa bits cleared, so x - hi is exact in fp32 and holds the next 13 bits; lo is
+// that remainder truncated to TF32.  |x - hi - lo| <= 2^-20 |x|, the same order as the lo*lo term the 3xTF32 scheme drops.
+// Three instructions per value (LOP3, FADD, LOP3).  `cvt.rna.tf32.f32` (round to nearest, error 4x smaller) is emulated on
+// sm_100a by ~5 integer / predicate instructions per conversion: with it the conversions were 42 % of all instructions of
+// the geometric kernel (profiles/r1c_instruction_mix.txt: FSETP, IMAD, LOP3, SEL, IADD3).  -DSAGE_TF32_RNA restores it.
 __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 {
+#ifdef SAGE_TF32_RNA
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float rest = x - __uint_as_float(hi);
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+#else
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+#endif
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
