@@ -167,3 +167,29 @@ def test_bench_accounting_matches_the_survey():
     s.mark_end()
     c = s.stop()
     assert set(c) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+
+
+def test_truncation_tf32_split_error_bound():
+    """The kernels' 3xTF32 rank-k update splits x = hi + lo by truncation (sage_common.cuh split_tf32).  Restated in numpy:
+    hi + lo reproduces x to 2^-20, and hi*hi' + hi*lo' + lo*hi' (what the three MMAs add up) reproduces the fp32 product sum to
+    ~1e-6 relative -- two orders inside the 1e-4 parity gate."""
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(200000) * np.exp(rng.uniform(-8, 8, 200000))).astype(np.float32)
+    y = (rng.standard_normal(200000) * np.exp(rng.uniform(-8, 8, 200000))).astype(np.float32)
+
+    def split(v):
+        hi = (v.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = ((v - hi).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        return hi, lo
+
+    xh, xl = split(x)
+    yh, yl = split(y)
+    assert np.all(np.abs(x.astype(np.float64) - xh - xl.astype(np.float64)) <= 2.0 ** -20 * np.abs(x))
+    # TF32 operands have 10 mantissa bits: both parts must be exactly representable
+    for part in (xh, xl):
+        assert np.all((part.view(np.uint32) & np.uint32(0x1FFF)) == 0)
+    prod = xh.astype(np.float64) * yh + xh.astype(np.float64) * yl + xl.astype(np.float64) * yh
+    exact = x.astype(np.float64) * y
+    assert np.all(np.abs(prod - exact) <= 4e-6 * np.abs(exact))
+    # a Gram-matrix entry: positive terms, errors do not accumulate beyond the per-term bound
+    assert abs((xh.astype(np.float64) ** 2 + 2 * xh.astype(np.float64) * xl).sum() / (x.astype(np.float64) ** 2).sum() - 1.0) < 2e-6
