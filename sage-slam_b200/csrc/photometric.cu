@@ -246,6 +246,7 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
                  (selB[k] == 1 ? cam.fx[l] : selB[k] == 2 ? cam.fy[l] : 1.f);
 
       // -------------------------------------------------------------- lane == channel quad: gathers
+      float ev[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; // ERR: squared error of sample i of my group, my channel quad
 #pragma unroll kUnroll
       for (int i = 0; i < LPG; ++i)
       {
@@ -283,11 +284,14 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
           }
         }
         else
-        {
-          const float es = group_sum<LPG>(e);
-          if (gl == i)
-            eacc = fmaf(fs.w[l], es, eacc);
-        }
+          ev[i * VPL] = e; // value index i * VPL: after the reduce-scatter lane gl owns the total of sample gl, its own
+      }
+      if constexpr (!T::kJac)
+      {
+        // one reduce-scatter of the group's LPG per-sample sums (7 shuffles for 8 samples) instead of LPG group reductions
+        float r[VPL];
+        reduce_scatter8<LPG>(ev, gl, r);
+        eacc = fmaf(fs.w[l], r[0], eacc);
       }
     }
 
