@@ -21,6 +21,7 @@ from typing import List, Tuple
 import numpy as np
 
 from . import ops
+from .frames import std_shuffle
 
 F32 = np.float32
 
@@ -197,7 +198,7 @@ class ReprojectionFactor:
         return _partition(AtA, Atb, self.keys, [6, 6, self.kf.C, 1], e, self.psd)
 
 
-def cycle_matches(ctx, kf_rec, fr_rec, num_keypoints, cyc_consis_thresh, seed=None):
+def cycle_matches(ctx, kf_rec, fr_rec, num_keypoints, cyc_consis_thresh, seed=None, libstdcxx="13"):
     """The descriptor-matching part of the ReprojectionFactor / MatchGeometryFactor constructors
     (reprojection_factor.cpp:36-112): draw `num_keypoints` of kf's valid locations, cycle-match their descriptors against fr
     (ops.cycle_feature_matching = row f3 on the device), keep the cycle-consistent ones.
@@ -205,12 +206,12 @@ def cycle_matches(ctx, kf_rec, fr_rec, num_keypoints, cyc_consis_thresh, seed=No
     kf_rec / fr_rec are frames.Keyframe records with feat_desc.  Returns None without inliers, else a dict with the
     reference's member names: matched_locations_1d_0 [M] int32, matched_locations_homo_0 [M,3], matched_locations_1d_1 [M] int32,
     matched_locations_2d_1 [M,2], matched_locations_homo_1 [M,3], desc_inlier_ratio.
-    Not reproduced: libstdc++'s std::shuffle (a numpy MT19937 permutation seeded kf.id * fr.id like the reference is used)
-    and the TEASER++ filtering that follows (reprojection_factor.cpp:136-186, third-party)."""
+    The keypoint draw is std::shuffle(iota(n), std::mt19937(kf.id * fr.id)) like the reference (frames.std_shuffle; `libstdcxx`
+    selects the library generation, see there).  Not reproduced: the TEASER++ filtering that follows
+    (reprojection_factor.cpp:136-186, third-party)."""
     n = len(kf_rec.sampled_locations_1d)
     K = min(int(num_keypoints), n)
-    rs = np.random.RandomState(kf_rec.id * fr_rec.id if seed is None else seed)
-    idx = rs.permutation(n)[:K]
+    idx = std_shuffle(n, kf_rec.id * fr_rec.id if seed is None else seed, libstdcxx)[:K]
     kp = np.asarray(kf_rec.sampled_locations_1d)[idx]
     r = ops.cycle_feature_matching(ctx, kf_rec.feat_desc, fr_rec.feat_desc, kp, cyc_consis_thresh)
     sel = r["inlier_within_keypoint_indexes"]

@@ -130,3 +130,62 @@ class Keyframe:
             return self.dpt_map_stored
         H, W = self.video_mask.shape
         return (F32(self.dpt_scale) * (self.dpt_map_bias + self.dpt_jac_code @ self.code)).reshape(H, W).astype(F32)
+
+
+def std_shuffle(n, seed, libstdcxx="13"):
+    """std::shuffle(iota(n), std::mt19937(seed)) as libstdc++ implements it -- the keypoint / sample draw of the reference
+    (core/gtsam/reprojection_factor.cpp:43-50, core/system/camera_tracker.cpp:818-823, core/mapping/mapper.cpp:1222-1239).
+
+    libstdcxx="13": bits/stl_algo.h + uniform_int_distribution of GCC 11+ (Lemire's multiply-shift for a 32-bit engine);
+    verified against g++ 13.3 (tests/golden/std_shuffle_gcc13.txt, generated by tests/golden/make_std_shuffle.cpp).
+    libstdcxx="9": the same shuffle with GCC <= 10's scale-and-reject uniform_int_distribution (the reference's Docker image,
+    nvcr.io/nvidia/pytorch:21.04, ships GCC 9); restated from the sources, not verifiable in this image.
+    Returns the permuted indices (int64)."""
+    raw = np.random.RandomState(int(seed) & 0xFFFFFFFF)._bit_generator  # init_genrand(seed) == std::mt19937(seed)
+    pool = []
+
+    def g():
+        if not pool:
+            pool.extend(int(v) for v in raw.random_raw(4096)[::-1])
+        return pool.pop()
+
+    def uniform(hi):  # uniform integer in [0, hi], hi < 2^32
+        erange = hi + 1
+        if erange > 0xFFFFFFFF:
+            return g()
+        if libstdcxx == "13":
+            prod = g() * erange
+            low = prod & 0xFFFFFFFF
+            if low < erange:
+                thr = ((1 << 32) - erange) % erange
+                while low < thr:
+                    prod = g() * erange
+                    low = prod & 0xFFFFFFFF
+            return prod >> 32
+        scaling = 0xFFFFFFFF // erange
+        past = erange * scaling
+        while True:
+            r = g()
+            if r < past:
+                return r // scaling
+
+    idx = list(range(n))
+    if n < 2:
+        return np.array(idx, np.int64)
+    if 0xFFFFFFFF // n >= n:  # two swaps per engine call
+        i = 1
+        if n % 2 == 0:
+            j = uniform(1)
+            idx[i], idx[j] = idx[j], idx[i]
+            i += 1
+        while i < n:
+            b0, b1 = i + 1, i + 2
+            x = uniform(b0 * b1 - 1)
+            for j in (x // b1, x % b1):
+                idx[i], idx[j] = idx[j], idx[i]
+                i += 1
+    else:
+        for i in range(1, n):
+            j = uniform(i)
+            idx[i], idx[j] = idx[j], idx[i]
+    return np.array(idx, np.int64)

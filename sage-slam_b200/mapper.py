@@ -7,8 +7,8 @@ the same factor set per link, but the solve is the device-side batched LM of lib
 re-linearised every iteration; no incremental elimination), and the write-back runs UpdateDepth on the device.
 
 Not reproduced (out of scope): work-item bookkeeping/removal, marginalisation, loop-closure links,
-TEASER++ filtering of the descriptor matches (reprojection_factor.cpp:136-186) -- cycle-consistent matches are used as is --
-and libstdc++'s std::shuffle for the keypoint draw (a numpy MT19937 permutation with the reference's seed is used).
+and TEASER++ filtering of the descriptor matches (reprojection_factor.cpp:136-186) -- cycle-consistent matches are used as is.
+The keypoint draw is the reference's std::shuffle with std::mt19937(kf.id * fr.id) (frames.std_shuffle).
 """
 import ctypes as C
 from dataclasses import dataclass, field

@@ -193,3 +193,27 @@ def test_truncation_tf32_split_error_bound():
     assert np.all(np.abs(prod - exact) <= 4e-6 * np.abs(exact))
     # a Gram-matrix entry: positive terms, errors do not accumulate beyond the per-term bound
     assert abs((xh.astype(np.float64) ** 2 + 2 * xh.astype(np.float64) * xl).sum() / (x.astype(np.float64) ** 2).sum() - 1.0) < 2e-6
+
+
+def test_std_shuffle_reproduces_libstdcxx():
+    """frames.std_shuffle against std::shuffle + std::mt19937 of g++ 13 (tests/golden/std_shuffle_gcc13.txt, generated by
+    tests/golden/make_std_shuffle.cpp): both code paths (two swaps per engine call for n <= 65535, one otherwise)."""
+    from sage_slam_b200 import frames
+
+    n_cases = 0
+    for line in open(os.path.join(helpers.ROOT, "tests", "golden", "std_shuffle_gcc13.txt")):
+        if line.startswith("#"):
+            continue
+        left, h = line.split("|")
+        t = [int(v) for v in left.split()]
+        n, seed, first = t[0], t[1], t[2:]
+        idx = frames.std_shuffle(n, seed)
+        assert list(idx[:len(first)]) == first
+        hh = 1469598103934665603
+        for v in idx.tolist():
+            hh = ((hh ^ v) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert hh == int(h)
+        n_cases += 1
+    assert n_cases == 7
+    old = frames.std_shuffle(1000, 42, libstdcxx="9")  # GCC <= 10 variant: a permutation, different draw
+    assert sorted(old.tolist()) == list(range(1000)) and list(old[:8]) != list(frames.std_shuffle(1000, 42)[:8])
