@@ -208,6 +208,7 @@ extern "C" int sage_ba_cycle_match(sage_ba_context *ctx, int memory, const float
   SAGE_CHECK(feat_desc_0 && feat_desc_1 && keypoint_locations_1d && num_inliers, "null argument");
   SAGE_CHECK(memory == SAGE_BA_HOST || memory == SAGE_BA_DEVICE, "memory must be SAGE_BA_HOST or SAGE_BA_DEVICE");
   const int K = num_keypoints, CD = channels, HW = height * width;
+  SAGE_CHECK(CD == 8 || CD == 16 || CD == 32 || CD == 64, "descriptor channels must be 8, 16, 32 or 64");
   SAGE_CHECK(K > 0 && K <= (1 << 20), "num_keypoints out of range");
   SAGE_CHECK(height > 0 && width > 0 && (long)height * width < (1l << 24), "image size out of range");
   for (int k = 0; k < K; ++k)
@@ -240,12 +241,22 @@ extern "C" int sage_ba_cycle_match(sage_ba_context *ctx, int memory, const float
     hk[k] = (int)keypoint_locations_1d[k];
   SAGE_CUDA(cudaMemcpyAsync(kp, hk, sizeof(int) * K, cudaMemcpyHostToDevice, s));
 
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  struct Events // destroyed on every exit path
+  {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~Events()
+    {
+      if (a)
+        cudaEventDestroy(a);
+      if (b)
+        cudaEventDestroy(b);
+    }
+  } ev;
   if (kernel_ms)
   {
-    SAGE_CUDA(cudaEventCreate(&e0));
-    SAGE_CUDA(cudaEventCreate(&e1));
-    SAGE_CUDA(cudaEventRecord(e0, s));
+    SAGE_CUDA(cudaEventCreate(&ev.a));
+    SAGE_CUDA(cudaEventCreate(&ev.b));
+    SAGE_CUDA(cudaEventRecord(ev.a, s));
   }
   desc_gather_kernel<<<(K * CD + 255) / 256, 256, 0, s>>>(d0, kp, K, CD, HW, q0);
   launch_response_any(CD, d1, q0, K, HW, chunk, nchunks, pbest, pidx, s);
@@ -255,17 +266,13 @@ extern "C" int sage_ba_cycle_match(sage_ba_context *ctx, int memory, const float
   desc_cycle_select_kernel<<<1, 1024, 0, s>>>(kp, cyc, K, width, cyc_consis_thresh * cyc_consis_thresh, sel, cnt);
   ctx->launches += 6;
   if (kernel_ms)
-    SAGE_CUDA(cudaEventRecord(e1, s));
+    SAGE_CUDA(cudaEventRecord(ev.b, s));
   SAGE_CUDA(cudaGetLastError());
   // raw | cyc | sel | count are contiguous
   SAGE_CUDA(cudaMemcpyAsync(hk, raw, sizeof(int) * ((size_t)3 * K + 1), cudaMemcpyDeviceToHost, s));
   SAGE_CUDA(cudaStreamSynchronize(s));
   if (kernel_ms)
-  {
-    SAGE_CUDA(cudaEventElapsedTime(kernel_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  }
+    SAGE_CUDA(cudaEventElapsedTime(kernel_ms, ev.a, ev.b));
   const int M = hk[3 * K];
   if (raw_matched_locations_1d_1)
     memcpy(raw_matched_locations_1d_1, hk, sizeof(int) * K);
