@@ -108,8 +108,11 @@ def run_case(name, far, mod=None):
 def main():
     outdir = os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name in helpers.CASES:
-        for far in (False, True):
+    only = set(sys.argv[1:])
+    for name, far in helpers.GOLDEN_RUNS:
+        if only and name not in only:
+            continue
+        if True:
             out = run_case(name, far)
             fn = os.path.join(outdir, f"{name}{'_far' if far else ''}.npz")
             np.savez_compressed(fn, **{k: np.asarray(v) for k, v in out.items()})

@@ -117,6 +117,9 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
 #ifndef PH_UNROLL_ERR
 #define PH_UNROLL_ERR 8 // error-only kernels fetch 5 lines per sample-level instead of 13: twice the samples in flight (2.67 -> 2.50 ms)
 #endif
+#ifndef PH_ILV
+#define PH_ILV 1 // gather step i serves samples i*NG + q (x-adjacent samples in ONE instruction: their taps share 128-byte lines at levels >= 1)
+#endif
 #define PH_STR2(x) #x
 #define PH_STR(x) PH_STR2(x)
 
@@ -250,7 +253,9 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
 #pragma unroll kUnroll
       for (int i = 0; i < LPG; ++i)
       {
-        const int src = q * LPG + i;
+        // which sample the group serves in step i.  Interleaved (PH_ILV): the NG groups of the warp take NG raster-adjacent
+        // samples, so at pyramid level l >= 1 (2^l samples per cell and row) one LDG touches 1-3 distinct lines instead of NG.
+        const int src = PH_ILV ? i * NG + q : q * LPG + i;
         const TapSet s1 = shfl_tapset(t1, src);
         const float *pnw = fg1 + (s1.pk & ~3);
         const float *pne = pnw + ((s1.pk & 2) ? 3 * F : 0);
@@ -307,7 +312,14 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       Gxx = g0.x * m2; Gxy = g0.y * m2; Gyy = g0.z * m2; bx = g0.w * m2; by = g1.x * m2;
       esum = g1.y;
     }
-    err_acc += wm * esum; // feat_error = within_mask * diff^2 (:228)
+    if constexpr (!T::kJac && PH_ILV)
+    {
+      // the reduce-scatter left lane gl of group q with the total of the sample served in step gl: gl * NG + q
+      const float wme = __shfl_sync(0xffffffffu, wm, gl * NG + q);
+      err_acc += wme * esum;
+    }
+    else
+      err_acc += wm * esum; // feat_error = within_mask * diff^2 (:228)
     inl_acc += valid;
 
     if constexpr (T::kJac)

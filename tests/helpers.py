@@ -22,7 +22,14 @@ CASES = {
     "small_c8_f16": dict(W=64, H=48, L=3, F=16, C=8, num_samples=None, mask="full", seed=11),
     "native_c16_f16": dict(W=80, H=64, L=4, F=16, C=16, num_samples=3072, mask="ellipse", seed=12),
     "small_c32_f32": dict(W=64, H=48, L=4, F=32, C=32, num_samples=None, mask="full", seed=13),
+    # BASELINE.json sizes: configs[0] (128x96, F16, C8, L=4, dense) and the bench shape of configs[1..4] (320x256, F=C=32, L=4,
+    # dense N=81920), the latter also under the endoscope (ellipse) mask
+    "cfg0_c8_f16": dict(W=128, H=96, L=4, F=16, C=8, num_samples=None, mask="full", seed=14),
+    "bench_c32_f32": dict(W=320, H=256, L=4, F=32, C=32, num_samples=None, mask="full", seed=15),
+    "bench_ell_c32_f32": dict(W=320, H=256, L=4, F=32, C=32, num_samples=None, mask="ellipse", seed=16),
 }
+# (case, far) combinations with a golden fixture; far = KF1 moved away so that nothing overlaps
+GOLDEN_RUNS = [(n, far) for n in CASES for far in (False, True) if not (far and n in ("cfg0_c8_f16", "bench_ell_c32_f32"))]
 PHOTO_WEIGHTS = [10.0, 9.0, 8.0, 7.0]
 EPS = 1e-4
 
@@ -124,3 +131,49 @@ MG_LOSSES = ("fair", "L2", "huber", "unbiased")
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def system_blocks(key, D, C):
+    """Variable blocks of a factor's normal equations, in the reference's column order (name, start, stop)."""
+    if key in ("photo", "rep"):  # [pose0 6 | pose1 6 | code0 C | scale0]   photometric_factor_kernels.cpp:241-364
+        b = [("pose0", 0, 6), ("pose1", 6, 12), ("code0", 12, 12 + C), ("scale0", 12 + C, 13 + C)]
+    elif key == "geo" or key.startswith("mmg_"):  # [pose0 | pose1 | code0 | code1 | scale0 | scale1]   geometric_factor_kernels.cpp:671-696
+        b = [("pose0", 0, 6), ("pose1", 6, 12), ("code0", 12, 12 + C), ("code1", 12 + C, 12 + 2 * C), ("scale0", 12 + 2 * C, 13 + 2 * C),
+             ("scale1", 13 + 2 * C, 14 + 2 * C)]
+    elif key == "lmg":  # loop closure: [pose0 | pose1 | scale0 | scale1]
+        b = [("pose0", 0, 6), ("pose1", 6, 12), ("scale0", 12, 13), ("scale1", 13, 14)]
+    else:  # tracker forms: [pose 6 (| scale)]
+        b = [("pose", 0, 6)] + ([("scale", 6, 7)] if D == 7 else [])
+    assert b[-1][2] == D, (key, D, C)
+    return b
+
+
+def block_errors(key, A, b, A_ref, b_ref, C):
+    """Per-block error of a factor's (AtA, Atb) against a reference, in the Jacobi-scaled system: every variable is scaled to
+    unit diagonal (A~ = S A S, b~ = S b, S = diag(A_ref)^-1/2), so that pose-pose entries (~ f^2/z^2) cannot hide errors in the
+    code / scale blocks -- |A~_ij| <= 1 for every entry of a Gram matrix, and an entry's rounding error scales with the norms
+    of its two columns.  Returns {(rowblock, colblock): max |dA~|} and {block: max |db~| / max |b~_ref|}."""
+    A, A_ref = np.asarray(A, np.float64), np.asarray(A_ref, np.float64)
+    b, b_ref = np.asarray(b, np.float64).reshape(-1), np.asarray(b_ref, np.float64).reshape(-1)
+    D = A_ref.shape[0]
+    d = np.diag(A_ref).copy()
+    live = d > 0
+    s = np.where(live, 1.0 / np.sqrt(np.where(live, d, 1.0)), 1.0)
+    dA = np.abs(A - A_ref) * s[:, None] * s[None, :]
+    bs = np.abs(b_ref * s).max()
+    db = np.abs(b - b_ref) * s / max(bs, 1e-30)
+    blocks = system_blocks(key, D, C)
+    ea = {(r[0], c[0]): float(dA[r[1]:r[2], c[1]:c[2]].max()) for r in blocks for c in blocks}
+    eb = {r[0]: float(db[r[1]:r[2]].max()) for r in blocks}
+    return ea, eb
+
+
+def assert_blocks_close(key, A, b, A_ref, b_ref, C, tol, label):
+    if not np.any(np.asarray(A_ref)):  # zero-overlap fallback: all-zero system
+        assert not np.any(np.asarray(A)) and not np.any(np.asarray(b)), f"{label}: {key} must be an all-zero system"
+        return 0.0
+    ea, eb = block_errors(key, A, b, A_ref, b_ref, C)
+    worst = max(list(ea.values()) + list(eb.values()))
+    bad = {k: v for k, v in list(ea.items()) + list(eb.items()) if v > tol}
+    assert not bad, f"{label}: {key} blocks over {tol:g} in the Jacobi-scaled system: {bad}"
+    return worst

@@ -16,13 +16,15 @@ TOL = 1e-4
 KEYS = ["photo", "geo", "rep", "trk", "trks", "trkrep", "mg", "mgs", "lmg"] + [f"mmg_{lt}" for lt in helpers.MG_LOSSES]
 
 
-def _compare(mine, ref, label):
+def _compare(mine, ref, label, C):
     for k in KEYS:
         for part in ("AtA", "Atb", "err"):
             key = f"{k}_{part}"
             if key in ref:
                 e = helpers.rel_err(np.asarray(mine[key]).reshape(-1), np.asarray(ref[key]).reshape(-1))
                 assert e <= TOL, f"{label}: {key} rel err {e:.3e}"
+        if f"{k}_AtA" in ref:  # block by block in the Jacobi-scaled system (a global max-norm hides the code / scale blocks)
+            helpers.assert_blocks_close(k, mine[f"{k}_AtA"], mine[f"{k}_Atb"], ref[f"{k}_AtA"], ref[f"{k}_Atb"], C, TOL, label)
         key = f"{k}_err_only"
         if key in ref:
             e = helpers.rel_err(mine[key], ref[key])
@@ -30,13 +32,12 @@ def _compare(mine, ref, label):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(helpers.CASES))
-@pytest.mark.parametrize("far", [False, True])
+@pytest.mark.parametrize("name,far", helpers.GOLDEN_RUNS)
 def test_kernels_match_oracle(sage_ctx, name, far):
     kfs = helpers.build_case(name, far=far)
     mine = sage_run.run_sage(sage_ctx, kfs)
     orc = oracle_run.run_oracle(kfs, np.float32)
-    _compare(mine, orc, f"{name} far={far} vs oracle")
+    _compare(mine, orc, f"{name} far={far} vs oracle", helpers.CASES[name]["C"])
     for k in ("photo", "geo", "rep"):
         assert mine[f"{k}_inl"] == orc[f"{k}_inl"]
     np.testing.assert_array_equal(mine["cam_pyramid"], orc["cam_pyramid"])
@@ -48,8 +49,7 @@ def test_kernels_match_oracle(sage_ctx, name, far):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(helpers.CASES))
-@pytest.mark.parametrize("far", [False, True])
+@pytest.mark.parametrize("name,far", helpers.GOLDEN_RUNS)
 def test_kernels_match_reference_golden(sage_ctx, name, far):
     fn = os.path.join(GOLDEN, f"{name}{'_far' if far else ''}.npz")
     assert os.path.exists(fn), "golden fixture missing: run oracle/make_golden.py on a GPU box"
@@ -58,11 +58,11 @@ def test_kernels_match_reference_golden(sage_ctx, name, far):
         assert f"{k}_AtA" in ref and f"{k}_err" in ref, f"golden fixture lacks {k}: regenerate with oracle/make_golden.py"
     kfs = helpers.build_case(name, far=far)
     mine = sage_run.run_sage(sage_ctx, kfs)
-    _compare(mine, ref, f"{name} far={far} vs reference kernels")
+    _compare(mine, ref, f"{name} far={far} vs reference kernels", helpers.CASES[name]["C"])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(helpers.CASES))
+@pytest.mark.parametrize("name", ["small_c8_f16", "native_c16_f16", "small_c32_f32", "bench_c32_f32"])
 def test_presample_matches_grid_sample(sage_ctx, name):
     """sage_ba_tracker_presample == the tracker's F::grid_sample pre-sampling (camera_tracker.cpp:1104-1123)."""
     kfs = helpers.build_case(name)

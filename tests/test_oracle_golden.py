@@ -9,7 +9,7 @@ import helpers
 import oracle_run
 
 GOLDEN = os.path.join(helpers.ROOT, "tests", "golden")
-CASES = [(n, far) for n in helpers.CASES for far in (False, True)]
+CASES = helpers.GOLDEN_RUNS
 
 
 @pytest.mark.parametrize("name,far", CASES)
@@ -28,6 +28,9 @@ def test_oracle_reproduces_reference_kernels(name, far):
             continue
         e = helpers.rel_err(np.asarray(orc[k]).reshape(-1), np.asarray(v).reshape(-1))
         assert e <= 2e-5, f"{name} far={far}: {k} rel err {e:.3e}"
+        if k.endswith("_AtA"):  # and block by block, every variable scaled to unit diagonal
+            helpers.assert_blocks_close(k[:-4], orc[k], orc[k[:-4] + "_Atb"], v, ref[k[:-4] + "_Atb"], helpers.CASES[name]["C"], 1e-4,
+                                        f"{name} far={far} oracle vs reference kernels")
 
 
 def test_f32_and_f64_oracles_agree():
