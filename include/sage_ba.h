@@ -59,6 +59,8 @@ const char *sage_ba_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches counter) */
 long sage_ba_launch_count(const sage_ba_context *ctx);
 int sage_ba_synchronize(sage_ba_context *ctx);
+/* the cudaStream_t every call on this context is enqueued on (the caller's, or the private one created by sage_ba_create) */
+void *sage_ba_stream(const sage_ba_context *ctx);
 
 /* ------------------------------------------------------------------------------------------
  * Keyframe: the immutable per-frame tensors of df::Frame<float> (core/mapping/frame.h:16-125),
@@ -292,6 +294,12 @@ int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe *frame0, co
                         const float *match_homo_0, const float *match_dpts_1, const float *match_homo_1, int num_matches,
                         sage_ba_tracker_report *report);
 
+/* Host helpers of the tracker loops, exposed for callers that keep their own LM loop (and pinned against the reference's Eigen
+ * code, tests/golden/host_pins.npz): x = (AtA + damp diag(AtA)).colPivHouseholderQr().solve(Atb), n = 6 | 7, float
+ * (core/system/camera_tracker.cpp:1182-1183); se3_exp<float> (core/mapping/mapping_utils.h:316-346), R [9] row-major, t [3]. */
+int sage_ba_tracker_solve(const float *AtA, const float *Atb, int n, float damp, float *x);
+int sage_ba_se3_exp(const float *omega, const float *v, float *R, float *t);
+
 /* ------------------------------------------------------------------------------------------
  * Batched local bundle adjustment (new; the reference delegates this to GTSAM ISAM2,
  * core/mapping/mapper.cpp:544).  A problem owns K keyframes' states (pose_wk, code, scale) on
@@ -312,13 +320,29 @@ int sage_ba_problem_add_code_prior(sage_ba_problem *p, int kf, const float *init
 int sage_ba_problem_add_scale_prior(sage_ba_problem *p, int kf, float init_scale, float weight);
 /* hold a keyframe's pose (and optionally scale) fixed: the gauge anchor (mapper.cpp:190-192) */
 int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale);
-/* linear solver: 0 auto = Schur complement onto the pose block fused into one Cholesky factorisation (the code+scale block is
- * ordered first, so cuSOLVER potrf eliminates it, forms S in the trailing 6K x 6K block and factors it; 3 launches);
- * 1 the same elimination as explicit steps (potrf H_cc, trsm, syrk, potrf S; ~40 launches, kept as a cross-check);
- * 2 block-banded Cholesky over keyframes (chain-shaped covisibility only; one launch, slower on a B200 at K = 32 -- opt-in). */
+/* linear solver (stands where ISAM2's multifrontal Cholesky stands, core/mapping/mapper.cpp:544):
+ * 0 (default) hand-written block-sparse Cholesky over keyframes: eliminating a keyframe's [pose | code | scale] block column is
+ *   the Schur complement of that keyframe onto the keyframes it shares factors with; one CTA per block column, columns run as
+ *   soon as the columns they depend on are done (nested-dissection order over the keyframe index line); fp64; 2 launches;
+ * 1 cross-check: the dense system with the code+scale block ordered first and ONE cuSOLVER potrf (the Schur complement onto the
+ *   6K x 6K pose block forms in the trailing sub-matrix) -- O(dim^2) memory, library kernels;
+ * 2 as 0 with the natural (temporal) elimination order. */
 int sage_ba_problem_set_solver(sage_ba_problem *p, int solver);
-/* restrict this process to the factors with index % world == rank (multi-GPU sharding) */
+/* Multi-GPU sharding, one process per GPU: the ordered pair (kf0 -> kf1) belongs to the rank that owns kf0, and keyframes are
+ * owned in contiguous ranges, sage_ba_shard_owner(K, world, kf) = kf * world / K.  Call before adding factors.  Every rank adds
+ * EVERY factor (the list defines the normal equations); a rank needs the device data only of the keyframes its own factors
+ * touch (host of an owned pair: depth + samples + features; target: features + mask (+ depth for geometric factors)) and may
+ * pass NULL for the others in sage_ba_problem_create. */
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);
+int sage_ba_shard_owner(int num_keyframes, int world, int kf);
+/* sage_ba_problem_lm_step re-uses the linearisation after a rejected step (the state did not move); always != 0 forces the full
+ * iteration every time (what BASELINE's "LM iteration" metric counts). */
+int sage_ba_problem_set_relinearize_always(sage_ba_problem *p, int always);
+/* CTAs per factor are normally sized so that a launch ends on a full wave of THIS rank's factors (fastest; a factor's outputs
+ * then agree across GPU counts to fp32 round-off).  on != 0 makes the decomposition depend on the problem only: with the
+ * fixed-order assembly and the flag-ordered solver the whole LM trajectory is then bit-identical for every number of GPUs, at
+ * ~5-10 % of the factor kernels' speed.  Call before the first linearisation. */
+int sage_ba_problem_set_deterministic(sage_ba_problem *p, int on);
 
 int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses /* [K,12] R row-major then t */,
                               const float *codes /* [K,C] */, const float *scales /* [K] */, float eps);
@@ -331,9 +355,15 @@ int sage_ba_problem_update_map(sage_ba_problem *p, float *poses, float *codes, f
 int sage_ba_problem_dim(const sage_ba_problem *p);         /* K * (7 + C)                       */
 int sage_ba_problem_num_factors(const sage_ba_problem *p); /* all kinds, priors included        */
 long sage_ba_problem_num_residuals(const sage_ba_problem *p); /* scalar residual rows per linearisation */
-/* packed per-factor output buffer (DEVICE, fp32): every factor's [AtA | Atb | error | inliers];
- * this is the buffer a multi-GPU host all-reduces (sum) once per LM iteration. */
+/* packed per-factor output buffer (DEVICE, fp32): every factor's [AtA | Atb | error | inliers], laid out as `world` equal
+ * segments, segment r holding the factors rank r owns in order of addition (world = 1: simply the order of addition).  This is
+ * the buffer the ranks exchange once per LM iteration (in-place all-gather of the segments). */
 int sage_ba_problem_factor_buffer(sage_ba_problem *p, float **device_ptr, size_t *count);
+/* per factor (order of addition): offset in the factor buffer, offset in the cost buffer, owner rank; any may be NULL */
+int sage_ba_problem_factor_offsets(sage_ba_problem *p, int *offsets, int *cost_offsets, int *owners);
+/* symbolic factorisation of solver 0 / 2: blocks of the factor (diagonal + sub-diagonal incl. fill), fill blocks, and the
+ * longest dependency chain of block columns (the critical path of the elimination) */
+int sage_ba_problem_solver_info(sage_ba_problem *p, int *num_blocks, int *fill_blocks, int *depth);
 /* packed per-factor [error | inliers] buffer of the last cost evaluation (DEVICE, fp32) */
 int sage_ba_problem_cost_buffer(sage_ba_problem *p, float **device_ptr, size_t *count);
 
@@ -366,13 +396,27 @@ enum
   SAGE_BA_PROF_DEPTH_PREP = 6,
   SAGE_BA_PROF_ASSEMBLE = 7,
   SAGE_BA_PROF_SOLVE = 8,
-  SAGE_BA_PROF_KINDS = 9
+  SAGE_BA_PROF_COMM = 9,
+  SAGE_BA_PROF_KINDS = 10
 };
 int sage_ba_problem_profile(sage_ba_problem *p, int enable);
 int sage_ba_problem_profile_read(sage_ba_problem *p, double *ms /* [KINDS] */, long *counts /* [KINDS] */, int reset);
 /* factors of each kind this process's shard owns (valid after the first linearize / buffer query) */
 int sage_ba_problem_shard_counts(const sage_ba_problem *p, int *n_photo, int *n_geo, int *n_reproj);
 
+/* Collectives.  Preferred: a NCCL communicator owned by the library -- the exchange is then issued from C++ on the context's
+ * stream inside linearize/evaluate's callers (sage_ba_problem_lm_step / _lm / _exchange), one ncclAllGather of the owned segment
+ * per linearisation and one (a few hundred bytes) per trial step.  libnccl is bound at run time (the copy already loaded in the
+ * process is used when there is one).  Rank 0 draws an id, the host program distributes the 128 bytes by any means. */
+typedef struct sage_ba_comm sage_ba_comm;
+int sage_ba_nccl_unique_id(char id[128]);
+int sage_ba_comm_create(sage_ba_context *ctx, const char id[128], int rank, int world, sage_ba_comm **comm);
+int sage_ba_comm_wrap(void *nccl_comm /* ncclComm_t of the caller */, int rank, int world, sage_ba_comm **comm);
+void sage_ba_comm_destroy(sage_ba_comm *comm);
+int sage_ba_problem_set_comm(sage_ba_problem *p, sage_ba_comm *comm);
+/* make the factor buffer (which = 0) or the cost buffer (which = 1) complete on every rank (no-op for world = 1) */
+int sage_ba_problem_exchange(sage_ba_problem *p, int which);
+/* Alternative for hosts without NCCL: a callback that sum-all-reduces a device buffer (other ranks' segments are zero). */
 typedef int (*sage_ba_allreduce_fn)(void *device_buffer, size_t count, void *user); /* fp32 sum, on ctx stream */
 int sage_ba_problem_set_allreduce(sage_ba_problem *p, sage_ba_allreduce_fn fn, void *user);
 

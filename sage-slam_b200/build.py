@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsage_ba.so")
-SOURCES = ["photometric.cu", "geometric.cu", "reprojection.cu", "match_geometry.cu", "descriptor.cu", "prep.cu", "api.cu", "problem.cu", "tracker.cu", "banded.cu"]
+SOURCES = ["photometric.cu", "geometric.cu", "reprojection.cu", "match_geometry.cu", "descriptor.cu", "prep.cu", "api.cu", "problem.cu", "tracker.cu", "blocksolve.cu", "comm.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fvisibility=default"]
 
@@ -50,7 +50,7 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, objdir=None):
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(run, jobs))
     if jobs or not os.path.exists(lib):
-        run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcublas", "-lcusolver", "-lcudart"])
+        run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcublas", "-lcusolver", "-lcudart", "-ldl"])
     return lib
 
 

@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SAGE_BA_LIB", os.path.join(HERE, "lib", "libsage_ba.so"))
 MAX_LEVELS = 8
-PROF_KINDS = ["photo_jac", "geo_jac", "reproj_jac", "photo_err", "geo_err", "reproj_err", "depth_prep", "assemble", "solve"]
+PROF_KINDS = ["photo_jac", "geo_jac", "reproj_jac", "photo_err", "geo_err", "reproj_err", "depth_prep", "assemble", "solve", "comm"]
 HOST, DEVICE = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
@@ -64,6 +64,7 @@ SIGNATURES = {
     "sage_ba_version": (C.c_char_p, []),
     "sage_ba_launch_count": (C.c_long, [vp]),
     "sage_ba_synchronize": (C.c_int, [vp]),
+    "sage_ba_stream": (vp, [vp]),
     "sage_ba_keyframe_create": (C.c_int, [vp, C.POINTER(KeyframeDesc), C.POINTER(vp)]),
     "sage_ba_keyframe_destroy": (None, [vp, vp]),
     "sage_ba_keyframe_set_bias": (C.c_int, [vp, vp, vp, C.c_int]),
@@ -90,6 +91,8 @@ SIGNATURES = {
                                       C.POINTER(TrackerReport)]),
     "sage_ba_track_new_frame": (C.c_int, [vp, vp, vp, vp, F, C.POINTER(TrackerConfig), vp, vp, vp, vp, vp, C.c_int,
                                           C.POINTER(TrackerReport)]),
+    "sage_ba_tracker_solve": (C.c_int, [vp, vp, C.c_int, F, vp]),
+    "sage_ba_se3_exp": (C.c_int, [vp, vp, vp, vp]),
     "sage_ba_problem_create": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "sage_ba_problem_destroy": (None, [vp]),
     "sage_ba_problem_add_photometric": (C.c_int, [vp, C.c_int, C.c_int, vp]),
@@ -100,6 +103,17 @@ SIGNATURES = {
     "sage_ba_problem_fix": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
     "sage_ba_problem_set_solver": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
+    "sage_ba_shard_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "sage_ba_problem_set_relinearize_always": (C.c_int, [vp, C.c_int]),
+    "sage_ba_problem_set_deterministic": (C.c_int, [vp, C.c_int]),
+    "sage_ba_problem_factor_offsets": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "sage_ba_problem_solver_info": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "sage_ba_nccl_unique_id": (C.c_int, [vp]),
+    "sage_ba_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "sage_ba_comm_wrap": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    "sage_ba_comm_destroy": (None, [vp]),
+    "sage_ba_problem_set_comm": (C.c_int, [vp, vp]),
+    "sage_ba_problem_exchange": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_set_state": (C.c_int, [vp, vp, vp, vp, F]),
     "sage_ba_problem_get_state": (C.c_int, [vp, vp, vp, vp]),
     "sage_ba_problem_update_map": (C.c_int, [vp, vp, vp, vp, vp, C.c_int]),

@@ -4,6 +4,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <algorithm>
+#include <mutex>
+
 #include "sage_internal.h"
 
 using namespace sage;
@@ -105,6 +108,64 @@ static void check_pair(const sage_ba_keyframe *a, const sage_ba_keyframe *b)
   SAGE_CHECK(a->H == b->H && a->W == b->W && a->L == b->L && a->F == b->F && a->C == b->C, "keyframes have different shapes");
 }
 
+// Tile-major sample order for the staged photometric kernels: samples sorted by (32 x 4 pixel tile, row in tile, column), so
+// that the 4 consecutive batches of 32 samples a CTA works on cover one tile whose projection into the other frame is a small
+// window.  Any sample set works (sub-sampled, masked); sparse ones just produce larger windows.  The order only changes the
+// order of summation inside the kernels.  Thread-safe for concurrent problems sharing a keyframe.
+void ensure_sorted_samples(sage_ba_context *ctx, sage_ba_keyframe *kf)
+{
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (kf->sfeat_s || kf->N <= 0)
+    return;
+  SAGE_CHECK(kf->loc1d && kf->homo && kf->fg, "keyframe lacks sample / feature data");
+  cudaStream_t s = ctx->stream;
+  const int N = kf->N, W = kf->W;
+  std::vector<int> loc(N), perm(N);
+  SAGE_CUDA(cudaMemcpyAsync(loc.data(), kf->loc1d, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  const int ntx = (W + 31) / 32;
+  std::vector<uint64_t> key(N);
+  for (int n = 0; n < N; ++n)
+  {
+    const int y = loc[n] / W, x = loc[n] - y * W;
+    const uint64_t tile = (uint64_t)(y >> 2) * ntx + (x >> 5);
+    key[n] = (((tile << 7) | (uint64_t)((y & 3) << 5) | (uint64_t)(x & 31)) << 32) | (uint32_t)n; // ties keep the caller's order
+  }
+  std::sort(key.begin(), key.end());
+  for (int n = 0; n < N; ++n)
+    perm[n] = (int)(key[n] & 0xffffffffu);
+  int *dperm = nullptr;
+  SAGE_CUDA(cudaMalloc(&dperm, sizeof(int) * N));
+  int *loc_s = nullptr;
+  float4 *homo_s = nullptr;
+  float *sfeat_s = nullptr;
+  try
+  {
+    SAGE_CUDA(cudaMemcpyAsync(dperm, perm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, s));
+    SAGE_CUDA(cudaMalloc(&loc_s, sizeof(int) * N));
+    SAGE_CUDA(cudaMalloc(&homo_s, sizeof(float4) * N));
+    SAGE_CUDA(cudaMalloc(&sfeat_s, sizeof(float) * (size_t)kf->L * N * kf->F));
+    launch_permute_samples(dperm, kf->loc1d, kf->homo, loc_s, homo_s, N, s);
+    launch_presample(kf->fg, nullptr, nullptr, loc_s, homo_s, nullptr, 1.f, kf->pyr, kf->F, kf->C, N, nullptr, nullptr, sfeat_s, s);
+    ctx->launches += 2;
+    SAGE_CUDA(cudaGetLastError());
+    SAGE_CUDA(cudaStreamSynchronize(s));
+  }
+  catch (...)
+  {
+    cudaFree(dperm);
+    cudaFree(loc_s);
+    cudaFree(homo_s);
+    cudaFree(sfeat_s);
+    throw;
+  }
+  cudaFree(dperm);
+  kf->loc1d_s = loc_s;
+  kf->homo_s = homo_s;
+  kf->sfeat_s = sfeat_s; // published last: the early-out above tests it
+}
+
 } // namespace sage
 
 extern "C" {
@@ -170,6 +231,7 @@ void sage_ba_destroy(sage_ba_context *ctx)
 
 const char *sage_ba_last_error(const sage_ba_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 long sage_ba_launch_count(const sage_ba_context *ctx) { return ctx ? ctx->launches : 0; }
+void *sage_ba_stream(const sage_ba_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int sage_ba_synchronize(sage_ba_context *ctx)
 {
@@ -326,6 +388,9 @@ void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf)
   cudaFree(kf->sfeat);
   cudaFree(kf->dgm);
   cudaFree(kf->dscr);
+  cudaFree(kf->loc1d_s);
+  cudaFree(kf->homo_s);
+  cudaFree(kf->sfeat_s);
   delete kf;
 }
 

@@ -1,0 +1,832 @@
+// blocksolve.cu -- the linear algebra of one LM iteration, hand-written and aware of the block sparsity of the problem.
+//
+// Stands where GTSAM's multifrontal Cholesky stands in the reference (core/mapping/mapper.cpp:544, isam_graph_->update):
+// the normal equations of a keyframe graph are block-sparse with one (7 + C) x (7 + C) block per keyframe ([pose 6 | code C |
+// scale]) on the diagonal and one per pair of keyframes that share a factor.  Eliminating keyframe k's block column IS the
+// Schur complement of k's variables onto the keyframes it is linked to; doing it for every keyframe in an elimination order is
+// a block Cholesky factorisation.  Three pieces:
+//
+//  * assemble_blocks_kernel: one CTA per non-zero block gathers the contributions of the factors touching that pair of
+//    keyframes from the packed per-factor buffer, in the order the factors were added (fixed order, no atomics: the result is
+//    bit-identical from run to run and for every GPU count) and adds the priors (core/gtsam/code_factor.cpp:42-104,
+//    scale_factor.cpp:115-130).  Memory is O(K + links) blocks instead of the dense (K (7+C))^2 matrix.
+//  * symbolic analysis (host, once per problem): elimination order = nested dissection over the keyframe index line
+//    (temporal links make the graph banded: separators are b consecutive keyframes), fill blocks, and for every block
+//    column the list of earlier columns it depends on.
+//  * bs_factor_kernel: left-looking block Cholesky, ONE CTA PER BLOCK COLUMN, all columns in flight at once.  A column waits
+//    (acquire on a per-column flag) only for the columns it really depends on, so independent subtrees of the elimination
+//    tree run concurrently on different SMs and a dependent column overlaps its updates from older columns with the
+//    factorisation of the newest one.  Inside a CTA: updates are 4x4 register-tiled fp64 block GEMMs on operands staged
+//    k-major in shared memory, the diagonal block is factored by one warp holding rows in registers, the panel is solved one
+//    row per thread.  The forward substitution rides along (the gradient is one more panel row); bs_backward_kernel walks the
+//    tree in the opposite direction.  fp64 throughout: the damped system reaches condition numbers ~1e9.
+#include <algorithm>
+#include <cstring>
+#include <set>
+
+#include "blocksolve.h"
+
+namespace sage
+{
+
+template <int C>
+struct BsCfg
+{
+  static constexpr int S = 7 + C;
+  static constexpr int SP = (S + 7) / 8 * 8; // 40 / 24 / 16
+  static constexpr int SPP = SP + 1;         // row stride of the panel blocks (odd: conflict-free column access)
+  static constexpr int NT = 256;
+  static constexpr int MAXS = C == 32 ? 8 : 16; // panel blocks resident in shared memory at a time
+  static constexpr int TQ = SP / 4;
+  static constexpr int TILES = TQ * TQ;
+  static constexpr int NR = (SP + 31) / 32; // rows per lane in the warp-level factorisation
+  static constexpr size_t factor_smem() { return sizeof(double) * ((size_t)MAXS * SP * SPP + 4 * SP * SP + 4 * SP); }
+  static constexpr size_t backward_smem() { return sizeof(double) * ((size_t)SP * SPP + SP * SP + 2 * SP); }
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// column of factor `m` that holds variable `var` ([pose 6 | code C | scale]) of keyframe `unit`, or -1
+__device__ __forceinline__ int factor_col(const FactorMeta &m, int unit, int var, int C)
+{
+  const bool is_i = unit == m.i;
+  if (!is_i && unit != m.j)
+    return -1;
+  if (var < 6)
+    return is_i ? var : 6 + var;
+  const int c = var - 6;
+  if (c < C)
+    return is_i ? 12 + c : (m.kind == 1 ? 12 + C + c : -1);
+  return is_i ? (m.kind == 1 ? 12 + 2 * C : 12 + C) : (m.kind == 1 ? 13 + 2 * C : -1);
+}
+
+__device__ __host__ __forceinline__ int global_var(int unit, int var, int K, int C)
+{
+  return var < 6 ? 6 * unit + var : 6 * K + unit * (C + 1) + (var - 6);
+}
+
+// ------------------------------------------------------------------------------------------------ assembly
+__global__ void __launch_bounds__(256)
+assemble_blocks_kernel(const float *__restrict__ fbuf, const FactorMeta *__restrict__ metas, const AsmBlock *__restrict__ blocks,
+                       const int *__restrict__ asm_factors, const PriorSpec *__restrict__ priors, const int *__restrict__ asm_priors,
+                       const float *__restrict__ codes, const float *__restrict__ scales, double *__restrict__ Hblk, double *__restrict__ g,
+                       int C, int SP)
+{
+  const AsmBlock b = blocks[blockIdx.x];
+  const int S = 7 + C;
+  const bool diag = b.runit == b.cunit;
+  for (int e = threadIdx.x; e < SP * SP; e += blockDim.x)
+  {
+    const int u = e / SP, v = e - u * SP;
+    double sum = 0.0;
+    if (u < S && v < S)
+    {
+      for (int q = b.fbeg; q < b.fend; ++q)
+      {
+        const FactorMeta m = metas[asm_factors[q]];
+        const int lu = factor_col(m, b.runit, u, C), lv = factor_col(m, b.cunit, v, C);
+        if (lu >= 0 && lv >= 0)
+          sum += (double)fbuf[m.off + lu * m.D + lv];
+      }
+      if (diag && u == v && u >= 6)
+        for (int q = b.pbeg; q < b.pend; ++q)
+        {
+          const PriorSpec &pr = priors[asm_priors[q]];
+          if (pr.kind == 0 && u < 6 + C)
+            sum += (double)pr.weight; // CodeFactor: AtA = w I
+          else if (pr.kind == 1 && u == 6 + C)
+          {
+            const double s = (double)scales[pr.kf];
+            sum += (double)pr.weight / (s * s); // ScaleFactor: AtA = w / s^2
+          }
+        }
+    }
+    Hblk[(size_t)b.blk * SP * SP + e] = sum;
+  }
+  if (diag)
+    for (int u = threadIdx.x; u < SP; u += blockDim.x)
+    {
+      double sum = 0.0;
+      if (u < S)
+      {
+        for (int q = b.fbeg; q < b.fend; ++q)
+        {
+          const FactorMeta m = metas[asm_factors[q]];
+          const int lu = factor_col(m, b.runit, u, C);
+          if (lu >= 0)
+            sum += (double)fbuf[m.off + m.D * m.D + lu];
+        }
+        if (u >= 6)
+          for (int q = b.pbeg; q < b.pend; ++q)
+          {
+            const PriorSpec &pr = priors[asm_priors[q]];
+            if (pr.kind == 0 && u < 6 + C)
+              sum += (double)pr.weight * ((double)pr.init_code[u - 6] - (double)codes[pr.kf * C + (u - 6)]);
+            else if (pr.kind == 1 && u == 6 + C)
+            {
+              const double s = (double)scales[pr.kf];
+              sum += (double)pr.weight / s * (log((double)pr.init_scale) - log(s));
+            }
+          }
+      }
+      g[(size_t)b.runit * SP + u] = sum;
+    }
+}
+
+__global__ void expand_dense_kernel(const AsmBlock *__restrict__ blocks, const double *__restrict__ Hblk, const double *__restrict__ gb,
+                                    double *__restrict__ H, double *__restrict__ g, int n, int K, int C, int SP)
+{
+  const AsmBlock b = blocks[blockIdx.x];
+  const int S = 7 + C;
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x)
+  {
+    const int u = e / S, v = e - u * S;
+    const double val = Hblk[(size_t)b.blk * SP * SP + u * SP + v];
+    const int gu = global_var(b.runit, u, K, C), gv = global_var(b.cunit, v, K, C);
+    H[(size_t)gu * n + gv] = val;
+    if (b.runit != b.cunit)
+      H[(size_t)gv * n + gu] = val;
+  }
+  if (b.runit == b.cunit)
+    for (int u = threadIdx.x; u < S; u += blockDim.x)
+      g[global_var(b.runit, u, K, C)] = gb[(size_t)b.runit * SP + u];
+}
+
+// ------------------------------------------------------------------------------------------------ factorisation
+// Compile-time recursion over the pivot column: every register-array index is a constant (a doubly nested `#pragma unroll` of
+// 40 x 40 iterations is beyond what nvcc unrolls, and a dynamically indexed array would live in local memory).
+template <int SP, int c>
+struct TrsmStep
+{
+  __device__ __forceinline__ static void run(double (&a)[SP], const double *invd, const double *Lt)
+  {
+    const double xv = a[c] * invd[c];
+    a[c] = xv;
+#pragma unroll
+    for (int qq = c + 1; qq < SP; ++qq)
+      a[qq] = fma(-xv, Lt[c * SP + qq], a[qq]);
+    TrsmStep<SP, c + 1>::run(a, invd, Lt);
+  }
+};
+template <int SP>
+struct TrsmStep<SP, SP>
+{
+  __device__ __forceinline__ static void run(double (&)[SP], const double *, const double *) {}
+};
+
+// One step of the warp-level Cholesky: lane r < RW keeps row r in registers (columns < RW); rows RW .. SP-1 (C = 32: 8 rows)
+// stay in the panel (shared memory, row stride SPP) and their trailing update is spread over all 32 lanes -- lane l updates
+// columns l and l + 32 of every such row -- so that no lane walks a row serially.
+template <int SP, int SPP, int RW, int c>
+struct PotrfStep
+{
+  __device__ __forceinline__ static void run(double (&a)[RW], double *P, double *colb, double *invd, int lane, bool &bad)
+  {
+    constexpr int XR = SP - RW;
+    double piv;
+    if constexpr (c < RW)
+      piv = __shfl_sync(0xffffffffu, a[c], c);
+    else
+      piv = P[c * SPP + c];
+    if (!(piv > 0.0))
+    {
+      bad = true;
+      piv = 1.0;
+    }
+    const double inv = rsqrt(piv), dg = piv * inv;
+    if constexpr (c < RW)
+    {
+      if (lane < RW)
+      {
+        const double v = lane == c ? dg : (lane > c ? a[c] * inv : 0.0);
+        a[c] = v;
+        colb[lane] = v;
+      }
+    }
+    if (XR > 0 && lane < XR)
+    {
+      const int r = RW + lane;
+      const double v = r == c ? dg : (r > c ? P[r * SPP + c] * inv : 0.0);
+      P[r * SPP + c] = v;
+      colb[r] = v;
+    }
+    if (lane == 0)
+      invd[c] = inv;
+    __syncwarp();
+    if constexpr (c < RW)
+    {
+#pragma unroll
+      for (int qq = c + 1; qq < RW; ++qq)
+        if (lane >= qq)
+          a[qq] = fma(-a[c], colb[qq], a[qq]);
+    }
+    if constexpr (XR > 0)
+    {
+#pragma unroll
+      for (int h = 0; h < (SP + 31) / 32; ++h)
+      {
+        const int qq = lane + 32 * h;
+        if (qq > c && qq < SP)
+        {
+          const double cq = colb[qq];
+#pragma unroll
+          for (int r = (c + 1 > RW ? c + 1 : RW); r < SP; ++r)
+            if (r >= qq)
+              P[r * SPP + qq] = fma(-colb[r], cq, P[r * SPP + qq]);
+        }
+      }
+    }
+    __syncwarp();
+    PotrfStep<SP, SPP, RW, c + 1>::run(a, P, colb, invd, lane, bad);
+  }
+};
+template <int SP, int SPP, int RW>
+struct PotrfStep<SP, SPP, RW, SP>
+{
+  __device__ __forceinline__ static void run(double (&)[RW], double *, double *, double *, int, bool &) {}
+};
+
+// Global storage of a factor block is TRANSPOSED (k-major): Lt[k * SP + r] = L[r][k], so that consumers stage it with a
+// straight copy and read 4 consecutive rows of one column with two LDS.128.
+template <int C>
+__global__ void __launch_bounds__(BsCfg<C>::NT, 1)
+bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *__restrict__ g, double *__restrict__ Lblk,
+                 double *__restrict__ ybuf, double *__restrict__ dinv, const double damp, int *__restrict__ sync)
+{
+  using T = BsCfg<C>;
+  constexpr int SP = T::SP, SPP = T::SPP, NT = T::NT, MAXS = T::MAXS, TQ = T::TQ, NR = T::NR;
+  extern __shared__ double sm[];
+  double *P = sm;                          // [MAXS][SP][SPP] panel blocks, row-major
+  double *Bt = P + (size_t)MAXS * SP * SPP; // [SP][SP] k-major L(p, j)
+  double *At = Bt + SP * SP;               // [2][SP][SP] k-major L(i, j)
+  double *Lt = At + 2 * SP * SP;           // [SP][SP] k-major L(p, p)
+  double *gv = Lt + SP * SP;               // [SP] gradient / forward-substituted y_p
+  double *yj = gv + SP;                    // [SP]
+  double *invd = yj + SP;                  // [SP] 1 / L(p,p)[c][c]
+  double *colb = invd + SP;                // [SP] column broadcast of the warp-level factorisation
+  __shared__ int s_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // columns are handed out in the order the CTAs actually start: a CTA only ever waits for columns that are already running
+  if (tid == 0)
+    s_p = atomicAdd(&sync[0], 1);
+  __syncthreads();
+  const int p = s_p;
+  int *flags = sync + 2;
+  const int unit = d.unit_of_pos[p];
+  const int cbeg = d.col_ptr[p], nslots = d.col_ptr[p + 1] - cbeg + 1;
+  const size_t BS = (size_t)SP * SP;
+
+  for (int s0 = 0; s0 < nslots; s0 += MAXS)
+  {
+    const int s1 = min(nslots, s0 + MAXS);
+    const bool first = s0 == 0;
+    // ---- load this chunk of the column from H with the damping / gauge rules of the LM step applied
+    for (int idx = tid; idx < (s1 - s0) * (int)BS; idx += NT)
+    {
+      const int sl = idx / (int)BS, e = idx - sl * (int)BS, u = e / SP, v = e - u * SP, slot = s0 + sl;
+      const int blk = slot == 0 ? p : d.col_blk[cbeg + slot - 1];
+      const int runit = slot == 0 ? unit : d.unit_of_pos[d.col_rowpos[cbeg + slot - 1]];
+      double val = Hblk[(size_t)blk * BS + e];
+      const bool fu = d.fixed[runit * SP + u], fv = d.fixed[unit * SP + v];
+      if (slot == 0)
+      {
+        if (fu || fv)
+          val = u == v ? 1.0 : 0.0; // fixed variable: identity row / column
+        else if (u == v)
+        {
+          val = val + damp * val;
+          if (!(val > 0.0))
+            val = 1.0; // variable untouched by any factor: keep the system positive definite
+        }
+      }
+      else if (fu || fv)
+        val = 0.0;
+      P[(size_t)sl * SP * SPP + u * SPP + v] = val;
+    }
+    if (first && tid < SP)
+      gv[tid] = d.fixed[unit * SP + tid] ? 0.0 : g[(size_t)unit * SP + tid];
+    __syncthreads();
+
+    // ---- left-looking updates from every earlier column j with L(p, j) != 0
+    for (int dep = d.dep_ptr[p]; dep < d.dep_ptr[p + 1]; ++dep)
+    {
+      const int j = d.dep_col[dep];
+      if (first)
+      {
+        if (tid == 0)
+          while (ld_acquire(&flags[j]) == 0)
+            __nanosleep(40);
+        __syncthreads();
+      }
+      const double *Bsrc = Lblk + (size_t)d.dep_blk[dep] * BS;
+      for (int e = tid; e < (int)BS; e += NT)
+        Bt[e] = __ldcg(Bsrc + e);
+      if (first && tid < SP)
+        yj[tid] = __ldcg(ybuf + (size_t)j * SP + tid);
+      __syncthreads();
+      if (first && tid < SP)
+      {
+        double a = 0.0;
+        for (int k = 0; k < SP; ++k)
+          a = fma(Bt[k * SP + tid], yj[k], a);
+        gv[tid] -= a; // g_p -= L(p, j) y_j
+      }
+      const int pe = d.dep_pair_ptr[dep + 1];
+      int q = d.dep_pair_ptr[dep];
+      while (q < pe)
+      {
+        int sel[2], nsel = 0;
+        while (q < pe && nsel < 2)
+        {
+          const int dst = d.pair_dst[q];
+          if (dst >= s0 && dst < s1)
+            sel[nsel++] = q;
+          ++q;
+        }
+        if (nsel == 0)
+          break;
+        for (int h = 0; h < nsel; ++h)
+        {
+          const double *Asrc = Lblk + (size_t)d.pair_src[sel[h]] * BS;
+          for (int e = tid; e < (int)BS; e += NT)
+            At[h * BS + e] = __ldcg(Asrc + e);
+        }
+        __syncthreads();
+        {
+          const int half = tid >> 7, t = tid & 127;
+          if (half < nsel && t < T::TILES)
+          {
+            const int tr = t / TQ, tc = t - tr * TQ;
+            const double *A = At + half * BS + tr * 4, *B = Bt + tc * 4;
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                acc[i][jj] = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < SP; ++k)
+            {
+              const double2 a01 = *reinterpret_cast<const double2 *>(A + k * SP), a23 = *reinterpret_cast<const double2 *>(A + k * SP + 2);
+              const double2 b01 = *reinterpret_cast<const double2 *>(B + k * SP), b23 = *reinterpret_cast<const double2 *>(B + k * SP + 2);
+              const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  acc[i][jj] = fma(a[i], b[jj], acc[i][jj]);
+            }
+            double *Cd = P + (size_t)(d.pair_dst[sel[half]] - s0) * SP * SPP + (tr * 4) * SPP + tc * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                Cd[i * SPP + jj] -= acc[i][jj]; // A(i, p) -= L(i, j) L(p, j)^T
+          }
+        }
+        __syncthreads();
+      }
+      __syncthreads(); // Bt / yj are overwritten by the next dependency
+    }
+
+    // ---- factor the diagonal block: one warp, rows in registers, one column broadcast through shared memory per step
+    if (first)
+    {
+      if (warp == 0)
+      {
+        constexpr int RW = SP < 32 ? SP : 32, XR = SP - RW;
+        double a[RW];
+        const double *xrow = P + (RW + (lane < XR ? lane : 0)) * SPP;
+#pragma unroll
+        for (int c = 0; c < RW; ++c)
+          a[c] = lane < RW ? P[lane * SPP + c] : 0.0;
+        bool bad = false;
+        PotrfStep<SP, SPP, RW, 0>::run(a, P, colb, invd, lane, bad);
+        __syncwarp();
+        if (bad && lane == 0)
+          atomicMax(&sync[1], p + 1);
+        if (lane < RW)
+        {
+#pragma unroll
+          for (int k = 0; k < RW; ++k)
+            Lt[k * SP + lane] = k <= lane ? a[k] : 0.0;
+          for (int k = RW; k < SP; ++k)
+            Lt[k * SP + lane] = 0.0;
+        }
+        if (XR > 0 && lane < XR)
+          for (int k = 0; k < SP; ++k)
+            Lt[k * SP + RW + lane] = k <= RW + lane ? xrow[k] : 0.0;
+      }
+      __syncthreads();
+    }
+
+    // ---- panel: X L(p,p)^T = A, one row per thread; the gradient is one more row (y_p = L(p,p)^-1 g_p)
+    {
+      const int sb = first ? 1 : s0;
+      const int nrows = (s1 - sb) * SP + (first ? 1 : 0);
+      for (int row = tid; row < nrows; row += NT)
+      {
+        const bool isg = first && row == nrows - 1;
+        double *src = isg ? gv : P + (size_t)(sb - s0 + row / SP) * SP * SPP + (row % SP) * SPP;
+        double a[SP];
+#pragma unroll
+        for (int c = 0; c < SP; ++c)
+          a[c] = src[c];
+        TrsmStep<SP, 0>::run(a, invd, Lt);
+#pragma unroll
+        for (int c = 0; c < SP; ++c)
+          src[c] = a[c];
+      }
+    }
+    __syncthreads();
+
+    // ---- publish the chunk (k-major)
+    for (int idx = tid; idx < (s1 - s0) * (int)BS; idx += NT)
+    {
+      const int sl = idx / (int)BS, e = idx - sl * (int)BS, k = e / SP, r = e - k * SP, slot = s0 + sl;
+      const int blk = slot == 0 ? p : d.col_blk[cbeg + slot - 1];
+      Lblk[(size_t)blk * BS + e] = slot == 0 ? Lt[e] : P[(size_t)sl * SP * SPP + r * SPP + k];
+    }
+    if (first && tid < SP)
+    {
+      ybuf[(size_t)p * SP + tid] = gv[tid];
+      dinv[(size_t)p * SP + tid] = invd[tid];
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0)
+    st_release(&flags[p], 1);
+}
+
+// x_p = L(p,p)^-T (y_p - sum_{i in struct(p)} L(i,p)^T x_i), columns in reverse order, same flag protocol
+template <int C>
+__global__ void __launch_bounds__(BsCfg<C>::NT, 1)
+bs_backward_kernel(const BsDev d, const double *__restrict__ Lblk, const double *__restrict__ ybuf, const double *__restrict__ dinv,
+                   double *__restrict__ xbuf, double *__restrict__ delta, int Ccode, int *__restrict__ sync)
+{
+  using T = BsCfg<C>;
+  constexpr int S = T::S, SP = T::SP, SPP = T::SPP, NT = T::NT, NR = T::NR;
+  extern __shared__ double sm[];
+  double *Lrow = sm;           // [SP][SPP] L(p,p) row-major
+  double *Bt = Lrow + SP * SPP; // [SP][SP] k-major L(i, p)
+  double *acc = Bt + SP * SP;   // [SP]
+  double *xr = acc + SP;        // [SP]
+  __shared__ int s_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = d.K;
+  int *ticket = sync + 2 + K, *flags = sync + 3 + K;
+  if (tid == 0)
+    s_p = K - 1 - atomicAdd(ticket, 1);
+  __syncthreads();
+  const int p = s_p;
+  const int unit = d.unit_of_pos[p];
+  const int cbeg = d.col_ptr[p], nr = d.col_ptr[p + 1] - cbeg;
+  const size_t BS = (size_t)SP * SP;
+  for (int e = tid; e < (int)BS; e += NT)
+  {
+    const int k = e / SP, r = e - k * SP;
+    Lrow[r * SPP + k] = __ldcg(Lblk + (size_t)p * BS + e);
+  }
+  if (tid < SP)
+    acc[tid] = __ldcg(ybuf + (size_t)p * SP + tid);
+  __syncthreads();
+  for (int s = 0; s < nr; ++s)
+  {
+    const int rp = d.col_rowpos[cbeg + s];
+    if (tid == 0)
+      while (ld_acquire(&flags[rp]) == 0)
+        __nanosleep(40);
+    __syncthreads();
+    const double *src = Lblk + (size_t)d.col_blk[cbeg + s] * BS;
+    for (int e = tid; e < (int)BS; e += NT)
+      Bt[e] = __ldcg(src + e);
+    if (tid < SP)
+      xr[tid] = __ldcg(xbuf + (size_t)rp * SP + tid);
+    __syncthreads();
+    if (tid < SP)
+    {
+      double a = 0.0;
+      for (int r = 0; r < SP; ++r)
+        a = fma(Bt[tid * SP + r], xr[r], a); // (L(i,p)^T x_i)[k] = sum_r L[r][k] x[r]
+      acc[tid] -= a;
+    }
+    __syncthreads();
+  }
+  if (warp == 0)
+  {
+    double a[NR];
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+      a[rr] = lane + 32 * rr < SP ? acc[lane + 32 * rr] : 0.0;
+#pragma unroll
+    for (int c = SP - 1; c >= 0; --c)
+    {
+      const double xc = __shfl_sync(0xffffffffu, a[c >> 5], c & 31) * __ldcg(dinv + (size_t)p * SP + c);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr)
+      {
+        const int qq = lane + 32 * rr;
+        if (qq == c)
+          a[rr] = xc;
+        else if (qq < c)
+          a[rr] = fma(-Lrow[c * SPP + qq], xc, a[rr]);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+    {
+      const int r = lane + 32 * rr;
+      if (r < SP)
+      {
+        xbuf[(size_t)p * SP + r] = a[rr];
+        if (r < S)
+          delta[global_var(unit, r, K, Ccode)] = a[rr];
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0)
+    st_release(&flags[p], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+BsDev BlockSystem::dev() const
+{
+  BsDev d;
+  d.K = K;
+  d.unit_of_pos = unit_of_pos.p;
+  d.col_ptr = col_ptr.p;
+  d.col_rowpos = col_rowpos.p;
+  d.col_blk = col_blk.p;
+  d.dep_ptr = dep_ptr.p;
+  d.dep_col = dep_col.p;
+  d.dep_blk = dep_blk.p;
+  d.dep_pair_ptr = dep_pair_ptr.p;
+  d.pair_src = pair_src.p;
+  d.pair_dst = pair_dst.p;
+  d.fixed = fixed.p;
+  return d;
+}
+
+static void nested_dissection(int lo, int hi, int b, std::vector<int> &out)
+{
+  const int n = hi - lo;
+  if (n <= std::max(3 * b, 8))
+  {
+    for (int u = lo; u < hi; ++u)
+      out.push_back(u);
+    return;
+  }
+  const int s0 = lo + n / 2 - b / 2, s1 = s0 + b;
+  nested_dissection(lo, s0, b, out);
+  nested_dissection(s1, hi, b, out);
+  for (int u = s0; u < s1; ++u)
+    out.push_back(u);
+}
+
+template <typename V>
+static void upload(DevBuf<typename V::value_type> &dst, const V &src, cudaStream_t s)
+{
+  using E = typename V::value_type;
+  dst.ensure(std::max<size_t>(src.size(), 1));
+  if (!src.empty())
+    SAGE_CUDA(cudaMemcpyAsync((void *)dst.p, (const void *)src.data(), src.size() * sizeof(E), cudaMemcpyHostToDevice, s));
+}
+
+void BlockSystem::build(int K_, int C_, const std::vector<FactorMeta> &metas, const std::vector<PriorSpec> &priors,
+                        const std::vector<unsigned char> &fixed_vars, int order_mode_, cudaStream_t s)
+{
+  K = K_;
+  C = C_;
+  S = 7 + C;
+  SP = (S + 7) / 8 * 8;
+  order_mode = order_mode_;
+  // ---- keyframe graph
+  std::set<std::pair<int, int>> links;
+  std::vector<int> span;
+  for (const FactorMeta &m : metas)
+  {
+    const int a = std::min(m.i, m.j), b = std::max(m.i, m.j);
+    if (links.insert({a, b}).second)
+      span.push_back(b - a);
+  }
+  // ---- elimination order
+  order.clear();
+  if (order_mode == 1 || span.empty())
+    for (int u = 0; u < K; ++u)
+      order.push_back(u);
+  else
+  {
+    std::sort(span.begin(), span.end());
+    const int b = std::max(1, span[std::min(span.size() - 1, (size_t)(0.9 * span.size()))]); // band of the temporal links
+    nested_dissection(0, K, b, order);
+  }
+  pos.assign(K, 0);
+  for (int q = 0; q < K; ++q)
+    pos[order[q]] = q;
+  // ---- symbolic factorisation in position space
+  std::vector<std::set<int>> cs(K);
+  std::set<std::pair<int, int>> orig; // (row pos, col pos) of assembled sub-diagonal blocks
+  for (const auto &l : links)
+  {
+    const int a = pos[l.first], b = pos[l.second];
+    cs[std::min(a, b)].insert(std::max(a, b));
+    orig.insert({std::max(a, b), std::min(a, b)});
+  }
+  for (int q = 0; q < K; ++q)
+    if (!cs[q].empty())
+    {
+      auto it = cs[q].begin();
+      const int parent = *it;
+      for (++it; it != cs[q].end(); ++it)
+        cs[parent].insert(*it);
+    }
+  std::vector<int> h_col_ptr(K + 1, 0), h_rowpos, h_blk;
+  for (int q = 0; q < K; ++q)
+  {
+    for (int r : cs[q])
+    {
+      h_rowpos.push_back(r);
+      h_blk.push_back(K + (int)h_blk.size());
+    }
+    h_col_ptr[q + 1] = (int)h_rowpos.size();
+  }
+  nblocks = K + (int)h_rowpos.size();
+  fill_blocks = (long)h_rowpos.size() - (long)orig.size();
+  auto block_id = [&](int r, int c) -> int {
+    if (r == c)
+      return c;
+    for (int e = h_col_ptr[c]; e < h_col_ptr[c + 1]; ++e)
+      if (h_rowpos[e] == r)
+        return h_blk[e];
+    return -1;
+  };
+  auto slot_of = [&](int r, int c) -> int {
+    if (r == c)
+      return 0;
+    for (int e = h_col_ptr[c]; e < h_col_ptr[c + 1]; ++e)
+      if (h_rowpos[e] == r)
+        return e - h_col_ptr[c] + 1;
+    return -1;
+  };
+  // ---- dependency lists (left-looking): column p needs every earlier column j with p in struct(j)
+  std::vector<std::vector<int>> rowlist(K);
+  for (int j = 0; j < K; ++j)
+    for (int r : cs[j])
+      rowlist[r].push_back(j);
+  std::vector<int> h_dep_ptr(K + 1, 0), h_dep_col, h_dep_blk, h_dep_pair_ptr(1, 0), h_pair_src, h_pair_dst, chain(K, 1);
+  depth = K ? 1 : 0;
+  for (int q = 0; q < K; ++q)
+  {
+    for (int j : rowlist[q])
+    {
+      h_dep_col.push_back(j);
+      h_dep_blk.push_back(block_id(q, j));
+      for (int i : cs[j])
+        if (i >= q)
+        {
+          const int sl = slot_of(i, q);
+          SAGE_CHECK(sl >= 0, "symbolic factorisation: missing fill block");
+          h_pair_src.push_back(block_id(i, j));
+          h_pair_dst.push_back(sl);
+        }
+      h_dep_pair_ptr.push_back((int)h_pair_src.size());
+      chain[q] = std::max(chain[q], chain[j] + 1);
+    }
+    h_dep_ptr[q + 1] = (int)h_dep_col.size();
+    depth = std::max(depth, chain[q]);
+  }
+  // ---- assembly lists: diagonal blocks and one block per linked pair, contributors in the order the factors were added
+  asm_blocks_h.clear();
+  std::vector<int> h_asm_factors, h_asm_priors;
+  for (int u = 0; u < K; ++u)
+  {
+    AsmBlock b;
+    b.blk = pos[u];
+    b.runit = b.cunit = u;
+    b.fbeg = (int)h_asm_factors.size();
+    for (size_t f = 0; f < metas.size(); ++f)
+      if (metas[f].i == u || metas[f].j == u)
+        h_asm_factors.push_back((int)f);
+    b.fend = (int)h_asm_factors.size();
+    b.pbeg = (int)h_asm_priors.size();
+    for (size_t q = 0; q < priors.size(); ++q)
+      if (priors[q].kf == u)
+        h_asm_priors.push_back((int)q);
+    b.pend = (int)h_asm_priors.size();
+    asm_blocks_h.push_back(b);
+  }
+  for (const auto &l : links)
+  {
+    const int a = l.first, c = l.second;
+    const bool a_row = pos[a] > pos[c];
+    AsmBlock b;
+    b.runit = a_row ? a : c;
+    b.cunit = a_row ? c : a;
+    b.blk = block_id(pos[b.runit], pos[b.cunit]);
+    SAGE_CHECK(b.blk >= 0, "symbolic factorisation: missing link block");
+    b.fbeg = (int)h_asm_factors.size();
+    for (size_t f = 0; f < metas.size(); ++f)
+      if ((metas[f].i == a && metas[f].j == c) || (metas[f].i == c && metas[f].j == a))
+        h_asm_factors.push_back((int)f);
+    b.fend = (int)h_asm_factors.size();
+    b.pbeg = b.pend = 0;
+    asm_blocks_h.push_back(b);
+  }
+  norig = (int)asm_blocks_h.size();
+  // ---- fixed variables per keyframe, padding marked fixed
+  std::vector<unsigned char> h_fixed((size_t)K * SP, 1);
+  for (int u = 0; u < K; ++u)
+    for (int v = 0; v < S; ++v)
+    {
+      const int gi = global_var(u, v, K, C);
+      h_fixed[(size_t)u * SP + v] = gi < (int)fixed_vars.size() ? fixed_vars[gi] : 0;
+    }
+  upload(unit_of_pos, order, s);
+  upload(col_ptr, h_col_ptr, s);
+  upload(col_rowpos, h_rowpos, s);
+  upload(col_blk, h_blk, s);
+  upload(dep_ptr, h_dep_ptr, s);
+  upload(dep_col, h_dep_col, s);
+  upload(dep_blk, h_dep_blk, s);
+  upload(dep_pair_ptr, h_dep_pair_ptr, s);
+  upload(pair_src, h_pair_src, s);
+  upload(pair_dst, h_pair_dst, s);
+  upload(asm_factors, h_asm_factors, s);
+  upload(asm_priors, h_asm_priors, s);
+  upload(asm_blocks, asm_blocks_h, s);
+  upload(fixed, h_fixed, s);
+  const size_t BS = (size_t)SP * SP;
+  Hblk.ensure((size_t)nblocks * BS);
+  Lblk.ensure((size_t)nblocks * BS);
+  g.ensure((size_t)K * SP);
+  y.ensure((size_t)K * SP);
+  x.ensure((size_t)K * SP);
+  dinv.ensure((size_t)K * SP);
+  sync.ensure(4 + 2 * (size_t)K);
+  SAGE_CUDA(cudaMemsetAsync(Hblk.p, 0, sizeof(double) * nblocks * BS, s)); // fill blocks stay zero
+  SAGE_CUDA(cudaStreamSynchronize(s)); // the host vectors above go out of scope
+}
+
+void BlockSystem::assemble(const float *fbuf, const FactorMeta *metas_d, const PriorSpec *priors_d, const float *codes, const float *scales,
+                           cudaStream_t s, long *launches)
+{
+  if (norig <= 0)
+    return;
+  assemble_blocks_kernel<<<norig, 256, 0, s>>>(fbuf, metas_d, asm_blocks.p, asm_factors.p, priors_d, asm_priors.p, codes, scales, Hblk.p,
+                                               g.p, C, SP);
+  if (launches)
+    *launches += 1;
+}
+
+template <int C>
+static void solve_t(BlockSystem &b, double damp, double *delta_d, cudaStream_t s)
+{
+  using T = BsCfg<C>;
+  static bool once = false;
+  if (!once)
+  {
+    cudaFuncSetAttribute(bs_factor_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::factor_smem());
+    cudaFuncSetAttribute(bs_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::backward_smem());
+    once = true;
+  }
+  bs_factor_kernel<C><<<b.K, T::NT, T::factor_smem(), s>>>(b.dev(), b.Hblk.p, b.g.p, b.Lblk.p, b.y.p, b.dinv.p, damp, b.sync.p);
+  bs_backward_kernel<C><<<b.K, T::NT, T::backward_smem(), s>>>(b.dev(), b.Lblk.p, b.y.p, b.dinv.p, b.x.p, delta_d, C, b.sync.p);
+}
+
+void BlockSystem::solve(double damp, double *delta_d, int *info_d, cudaStream_t s, long *launches)
+{
+  SAGE_CUDA(cudaMemsetAsync(sync.p, 0, sizeof(int) * (4 + 2 * (size_t)K), s));
+  switch (C)
+  {
+  case 32: solve_t<32>(*this, damp, delta_d, s); break;
+  case 16: solve_t<16>(*this, damp, delta_d, s); break;
+  case 8: solve_t<8>(*this, damp, delta_d, s); break;
+  default: SAGE_CHECK(false, "unsupported code_size");
+  }
+  if (info_d)
+    SAGE_CUDA(cudaMemcpyAsync(info_d, sync.p + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (launches)
+    *launches += 2;
+}
+
+void BlockSystem::expand_dense(double *H, double *gd, int n, cudaStream_t s, long *launches)
+{
+  SAGE_CUDA(cudaMemsetAsync(H, 0, sizeof(double) * (size_t)n * n, s));
+  SAGE_CUDA(cudaMemsetAsync(gd, 0, sizeof(double) * n, s));
+  if (norig > 0)
+    expand_dense_kernel<<<norig, 256, 0, s>>>(asm_blocks.p, Hblk.p, g.p, H, gd, n, K, C, SP);
+  if (launches)
+    *launches += 1;
+}
+
+} // namespace sage

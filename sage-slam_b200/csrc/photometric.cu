@@ -123,8 +123,93 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
 #define PH_STR2(x) #x
 #define PH_STR(x) PH_STR2(x)
 
-template <int F, int C, int MODE>
-__global__ void __launch_bounds__(PH_CTA, (MODE == PH_MAP_JAC || MODE == PH_TRK_JAC) ? PH_MINB : PH_MINB_ERR)
+// ------------------------------------------------------------------------------------------------
+// Staged variant (STG): the taps of pyramid levels >= 1 come from shared memory.
+// A CTA's PH_WARPS warps work on one TILE of PH_WARPS consecutive batches at a time; with the tile-major sample order the
+// library builds for problem keyframes (api.cu: sort_samples) that is a 32 x PH_WARPS block of pixels, whose projection into
+// frame 1 at level l covers about (32/2^l + 2) x (PH_WARPS/2^l + 2) pixels.  Each warp reduces the bounding box of its taps
+// per level (REDUX), one block barrier publishes the boxes, and warp 0 copies the window rows of fg1 -- contiguous runs of
+// [3][F] floats in the channel-last layout -- into shared memory with cp.async.bulk (TMA engine, SASS UBLKCP), completion
+// counted on an mbarrier (expect_tx).  The copy flies while every warp gathers level 0 straight from global memory (no reuse
+// there beyond what L1 gives); the levels above, where 4 / 16 / 64 samples share a cell, then read their 12 lines per
+// sample-level from the window at shared-memory latency instead of L2 latency, with no register held per line in flight.
+// Taps outside the window (clipped box: strong rotation, depth discontinuity) keep their global address: generic loads
+// serve both, there is no second code path.
+// ------------------------------------------------------------------------------------------------
+#ifndef PH_WIN_KB_JAC
+#define PH_WIN_KB_JAC (PH_HALF ? 48 : 64) // window bytes per CTA: 3 CTAs/SM with the half-size row staging, 2 with the full one
+#endif
+#ifndef PH_WIN_KB_ERR
+#define PH_WIN_KB_ERR 52 // error-only kernels have no row staging: 4 CTAs/SM
+#endif
+#ifndef PH_MINB_STG
+#define PH_MINB_STG (PH_HALF ? 3 : 2)
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!ok)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct WinBox
+{
+  int x0, y0, w, h, base; // window origin / size in pixels of the level, first float of the window in the staging area
+};
+
+// window of level l from the PH_WARPS per-warp boxes (xmin, ymin, xmax, ymax), clipped to what is left of the budget
+__device__ __forceinline__ WinBox make_window(const int (*box)[4], int nwarps, int used_px, int budget_px, int stride)
+{
+  int xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1;
+  for (int w = 0; w < nwarps; ++w)
+  {
+    xmin = min(xmin, box[w][0]);
+    ymin = min(ymin, box[w][1]);
+    xmax = max(xmax, box[w][2]);
+    ymax = max(ymax, box[w][3]);
+  }
+  WinBox b;
+  b.x0 = xmin;
+  b.y0 = ymin;
+  b.w = xmax >= xmin ? xmax - xmin + 1 : 0;
+  b.h = ymax >= ymin ? ymax - ymin + 1 : 0;
+  const int avail = budget_px - used_px;
+  if (b.w > avail)
+    b.w = avail;
+  if (b.w > 0 && b.w * b.h > avail)
+    b.h = avail / b.w;
+  if (b.h > 32)
+    b.h = 32; // one lane of warp 0 issues one row
+  if (b.w <= 0 || b.h <= 0)
+    b.w = b.h = 0;
+  b.base = used_px * stride;
+  return b;
+}
+
+template <int F, int C, int MODE, bool STG>
+__global__ void __launch_bounds__(PH_CTA, STG ? ((MODE == PH_MAP_JAC || MODE == PH_TRK_JAC) ? PH_MINB_STG : PH_MINB_ERR)
+                                              : ((MODE == PH_MAP_JAC || MODE == PH_TRK_JAC) ? PH_MINB : PH_MINB_ERR))
 photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ CamPyr cam, float *__restrict__ partH,
              float *__restrict__ partE)
 {
@@ -138,6 +223,20 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   __shared__ __align__(16) float XP[PH_WARPS][32 * 9 + 3];
   __shared__ PhotoFactor fs;
   __shared__ float red[32];
+  // staged variant: window (dynamic shared memory), its mbarrier and the per-warp tap boxes of levels 1..L-1
+  extern __shared__ __align__(128) float win[];
+  __shared__ __align__(8) uint64_t win_bar;
+  __shared__ int wbox[STG ? SAGE_MAX_LEVELS : 1][PH_WARPS][4];
+  constexpr int WIN_PX = STG ? ((T::kJac ? PH_WIN_KB_JAC : PH_WIN_KB_ERR) * 1024) / (3 * F * 4) : 0;
+  uint32_t win_phase = 0;
+  if constexpr (STG)
+  {
+    if (threadIdx.x == 0)
+    {
+      mbar_init(&win_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
 
   {
     const int *src = reinterpret_cast<const int *>(factors + blockIdx.y);
@@ -169,8 +268,11 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   }
 
   const int nbatch = (N + 31) / 32;
-  for (int batch = blockIdx.x * PH_WARPS + warp; batch < nbatch; batch += gridDim.x * PH_WARPS)
+  // STG: every warp of the CTA runs the same number of rounds (block barrier inside); a warp past the end works on masked lanes
+  const int nround = STG ? (nbatch + PH_WARPS - 1) / PH_WARPS : nbatch;
+  for (int it = STG ? blockIdx.x : blockIdx.x * PH_WARPS + warp; it < nround; it += STG ? gridDim.x : gridDim.x * PH_WARPS)
   {
+    const int batch = STG ? it * PH_WARPS + warp : it;
     // ------------------------------------------------------------------ lane == sample: geometry
     const int n = batch * 32 + lane;
     const bool live = n < N;
@@ -234,11 +336,85 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
       __syncwarp();
     }
 
+    if constexpr (STG)
+    {
+      // bounding box of this warp's clamped taps at every level >= 1 (valid samples only)
+      for (int l = 1; l < L; ++l)
+      {
+        const int W = cam.w[l], H = cam.h[l];
+        const float pxl = (ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, pyl = (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f;
+        const int x0 = (int)floorf(pxl), y0 = (int)floorf(pyl);
+        const int x1 = x0 < 0x7fffffff ? x0 + 1 : x0, y1 = y0 < 0x7fffffff ? y0 + 1 : y0;
+        const int xa = min(max(x0, 0), W - 1), xb = min(max(x1, 0), W - 1), ya = min(max(y0, 0), H - 1), yb = min(max(y1, 0), H - 1);
+        const bool in = valid != 0.f;
+        const int bx0 = __reduce_min_sync(0xffffffffu, in ? xa : 0x7fffffff), by0 = __reduce_min_sync(0xffffffffu, in ? ya : 0x7fffffff);
+        const int bx1 = __reduce_max_sync(0xffffffffu, in ? xb : -1), by1 = __reduce_max_sync(0xffffffffu, in ? yb : -1);
+        if (lane == 0)
+        {
+          wbox[l][warp][0] = bx0;
+          wbox[l][warp][1] = by0;
+          wbox[l][warp][2] = bx1;
+          wbox[l][warp][3] = by1;
+        }
+      }
+      __syncthreads(); // boxes visible; every warp is done reading the previous tile's window
+      if (warp == 0)
+      {
+        int used = 0;
+        uint32_t bytes = 0;
+        for (int l = 1; l < L; ++l)
+        {
+          const WinBox b = make_window(wbox[l], PH_WARPS, used, WIN_PX, 3 * F);
+          used += b.w * b.h;
+          bytes += (uint32_t)(b.w * b.h) * (3 * F * 4);
+        }
+        if (lane == 0)
+        {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic reads of the old window before the async writes
+          mbar_expect_tx(&win_bar, bytes);
+        }
+        __syncwarp();
+        used = 0;
+        for (int l = 1; l < L; ++l)
+        {
+          const WinBox b = make_window(wbox[l], PH_WARPS, used, WIN_PX, 3 * F);
+          used += b.w * b.h;
+          if (lane < b.h)
+            bulk_g2s(win + b.base + (size_t)lane * b.w * (3 * F),
+                     fs.fg1 + ((size_t)cam.off[l] + (size_t)(b.y0 + lane) * cam.w[l] + b.x0) * (3 * F), (uint32_t)b.w * (3 * F * 4), &win_bar);
+        }
+      }
+    }
+    int win_used = 0;
+
     for (int l = 0; l < L; ++l)
     {
       const int W = cam.w[l], H = cam.h[l];
       // pixel at level l = (pixel_0 + 0.5) * f_l / f_0 - 0.5   (:142-144)
-      const TapSet t1 = make_tapset((ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H, 3 * F);
+      TapSet t1 = make_tapset((ux + 0.5f) * cam.fx[l] / cam.ofx - 0.5f, (uy + 0.5f) * cam.fy[l] / cam.ofy - 0.5f, W, H, 3 * F);
+      int win_rowo = 0;
+      const float *wbase = nullptr;
+      if constexpr (STG)
+      {
+        if (l >= 1)
+        {
+          if (l == 1)
+          {
+            mbar_wait(&win_bar, win_phase);
+            win_phase ^= 1u;
+          }
+          const WinBox b = make_window(wbox[l], PH_WARPS, win_used, WIN_PX, 3 * F);
+          win_used += b.w * b.h;
+          win_rowo = b.w * (3 * F);
+          wbase = win + b.base + gl * 4;
+          // re-express the tap set relative to the window when all four (clamped) taps lie inside it: bit 2 of pk marks it
+          const int pix = t1.pk / (3 * F); // clamped nw pixel (the flags live below 3F)
+          const int ya = pix / W, xa = pix - ya * W;
+          const int xb = xa + ((t1.pk & 2) ? 1 : 0), yb = ya + ((t1.pk & 1) ? 1 : 0);
+          if (xa >= b.x0 && xb < b.x0 + b.w && ya >= b.y0 && yb < b.y0 + b.h)
+            t1.pk = (((ya - b.y0) * b.w + (xa - b.x0)) * (3 * F)) | 4 | (t1.pk & 3);
+        }
+      }
       const float *fg1 = fs.fg1 + (size_t)cam.off[l] * (3 * F) + gl * 4;
       const float *sf0 = fs.sfeat0 + (size_t)l * N * F + gl * 4; // KF0 features pre-sampled at its own sample points
       const int rowo = W * (3 * F);
@@ -257,19 +433,20 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
         // samples, so at pyramid level l >= 1 (2^l samples per cell and row) one LDG touches 1-3 distinct lines instead of NG.
         const int src = PH_ILV ? i * NG + q : q * LPG + i;
         const TapSet s1 = shfl_tapset(t1, src);
-        const float *pnw = fg1 + (s1.pk & ~3);
+        const bool inw = STG && (s1.pk & 4);
+        const float *pnw = (inw ? wbase : fg1) + (s1.pk & ~7);
         const float *pne = pnw + ((s1.pk & 2) ? 3 * F : 0);
-        const float *psw = pnw + ((s1.pk & 1) ? rowo : 0);
+        const float *psw = pnw + ((s1.pk & 1) ? (inw ? win_rowo : rowo) : 0);
         const float *pse = psw + ((s1.pk & 2) ? 3 * F : 0);
-        const float4 f1 = gather4(pnw, pse, psw, pne, s1.w);
+        const float4 f1 = gather4<STG>(pnw, pse, psw, pne, s1.w);
         const int ns = min(batch * 32 + src, N - 1);
         const float4 f0 = ldg4(sf0 + (size_t)ns * F);
         const float dfx = f0.x - f1.x, dfy = f0.y - f1.y, dfz = f0.z - f1.z, dfw = f0.w - f1.w;
         const float e = dfx * dfx + dfy * dfy + dfz * dfz + dfw * dfw;
         if constexpr (T::kJac)
         {
-          const float4 gx = gather4(pnw + F, pse + F, psw + F, pne + F, s1.w);
-          const float4 gy = gather4(pnw + 2 * F, pse + 2 * F, psw + 2 * F, pne + 2 * F, s1.w);
+          const float4 gx = gather4<STG>(pnw + F, pse + F, psw + F, pne + F, s1.w);
+          const float4 gy = gather4<STG>(pnw + 2 * F, pse + 2 * F, psw + 2 * F, pne + 2 * F, s1.w);
           float v[8];
           v[0] = gx.x * gx.x + gx.y * gx.y + gx.z * gx.z + gx.w * gx.w;
           v[1] = gx.x * gy.x + gx.y * gy.y + gx.z * gy.z + gx.w * gy.w;
@@ -527,24 +704,50 @@ __global__ void photo_finalize_kernel(const PhotoFactor *__restrict__ factors, i
 }
 
 template <int F, int C, int MODE>
+constexpr size_t photo_window_bytes()
+{
+  return (size_t)((MODE == PH_MAP_JAC || MODE == PH_TRK_JAC) ? PH_WIN_KB_JAC : PH_WIN_KB_ERR) * 1024;
+}
+
+template <int F, int C, int MODE, bool STG>
 static void launch_photo_t(const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH, float *partE,
                            float *out, int out_stride, int D, cudaStream_t stream)
 {
   dim3 grid(slices, nfactors);
-  photo_kernel<F, C, MODE><<<grid, PH_CTA, 0, stream>>>(factors, cam, partH, partE);
+  const size_t dyn = STG ? photo_window_bytes<F, C, MODE>() : 0;
+  if constexpr (STG)
+  {
+    static bool once = false; // per instantiation; the attribute is per device function, setting it twice is harmless
+    if (!once)
+    {
+      cudaFuncSetAttribute(photo_kernel<F, C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      once = true;
+    }
+  }
+  photo_kernel<F, C, MODE, STG><<<grid, PH_CTA, dyn, stream>>>(factors, cam, partH, partE);
   photo_finalize_kernel<C, MODE><<<nfactors, 256, 0, stream>>>(factors, cam.L, slices, partH, partE, out, out_stride, D);
 }
 
 template <int F, int C>
-static void launch_photo_fc(int mode, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
+static void launch_photo_fc(int mode, bool staged, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
                             float *partE, float *out, int out_stride, int D, cudaStream_t stream)
 {
   switch (mode)
   {
-  case PH_MAP_JAC: launch_photo_t<F, C, PH_MAP_JAC>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
-  case PH_MAP_ERR: launch_photo_t<F, C, PH_MAP_ERR>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
-  case PH_TRK_JAC: launch_photo_t<F, C, PH_TRK_JAC>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
-  default: launch_photo_t<F, C, PH_TRK_ERR>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
+  case PH_MAP_JAC:
+    if (staged)
+      launch_photo_t<F, C, PH_MAP_JAC, true>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);
+    else
+      launch_photo_t<F, C, PH_MAP_JAC, false>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);
+    break;
+  case PH_MAP_ERR:
+    if (staged)
+      launch_photo_t<F, C, PH_MAP_ERR, true>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);
+    else
+      launch_photo_t<F, C, PH_MAP_ERR, false>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);
+    break;
+  case PH_TRK_JAC: launch_photo_t<F, C, PH_TRK_JAC, false>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
+  default: launch_photo_t<F, C, PH_TRK_ERR, false>(factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream); break;
   }
 }
 
@@ -552,16 +755,27 @@ int photo_row_width(int mode, int C) { return (mode == PH_MAP_JAC || mode == PH_
 int photo_samples_per_cta() { return PH_WARPS * 32; }
 
 // resident CTAs per SM of the kernel the given configuration launches (occupancy API); 0 for an unsupported (F, C)
-int photo_ctas_per_sm(int mode, int F, int C)
+int photo_ctas_per_sm(int mode, int F, int C, bool staged)
 {
   int n = 0;
-#define SAGE_OCC(FF, CC)                                                                                               \
-  if (F == FF && C == CC)                                                                                              \
-  {                                                                                                                    \
-    if (mode == PH_MAP_JAC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_MAP_JAC>, PH_CTA, 0); \
-    else if (mode == PH_MAP_ERR) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_MAP_ERR>, PH_CTA, 0); \
-    else if (mode == PH_TRK_JAC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_TRK_JAC>, PH_CTA, 0); \
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, PH_TRK_ERR>, PH_CTA, 0);               \
+#define SAGE_OCC1(FF, CC, MM)                                                                                                   \
+  {                                                                                                                             \
+    if (staged && (MM == PH_MAP_JAC || MM == PH_MAP_ERR))                                                                       \
+    {                                                                                                                           \
+      cudaFuncSetAttribute(photo_kernel<FF, CC, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
+                           (int)photo_window_bytes<FF, CC, MM>());                                                              \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, true>, PH_CTA, photo_window_bytes<FF, CC, MM>()); \
+    }                                                                                                                           \
+    else                                                                                                                        \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, false>, PH_CTA, 0);                            \
+  }
+#define SAGE_OCC(FF, CC)                                     \
+  if (F == FF && C == CC)                                    \
+  {                                                          \
+    if (mode == PH_MAP_JAC) SAGE_OCC1(FF, CC, PH_MAP_JAC)    \
+    else if (mode == PH_MAP_ERR) SAGE_OCC1(FF, CC, PH_MAP_ERR) \
+    else if (mode == PH_TRK_JAC) SAGE_OCC1(FF, CC, PH_TRK_JAC) \
+    else SAGE_OCC1(FF, CC, PH_TRK_ERR)                       \
   }
   SAGE_OCC(32, 32)
   SAGE_OCC(16, 16)
@@ -569,20 +783,22 @@ int photo_ctas_per_sm(int mode, int F, int C)
   SAGE_OCC(32, 16)
   SAGE_OCC(16, 32)
 #undef SAGE_OCC
+#undef SAGE_OCC1
   return n;
 }
 
-// returns 0 on success, -1 for an unsupported (F, C)
+// returns 0 on success, -1 for an unsupported (F, C).  staged: the samples of kf0 are in tile-major order (problem keyframes);
+// only the mapping forms have a staged instantiation.
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
-                 float *partE, float *out, int out_stride, int D, cudaStream_t stream)
+                 float *partE, float *out, int out_stride, int D, cudaStream_t stream, bool staged)
 {
   if (nfactors <= 0)
     return 0;
-#define SAGE_CASE(FF, CC)                                                                                       \
-  if (F == FF && C == CC)                                                                                       \
-  {                                                                                                             \
-    launch_photo_fc<FF, CC>(mode, factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);   \
-    return 0;                                                                                                   \
+#define SAGE_CASE(FF, CC)                                                                                               \
+  if (F == FF && C == CC)                                                                                               \
+  {                                                                                                                     \
+    launch_photo_fc<FF, CC>(mode, staged, factors, nfactors, cam, slices, partH, partE, out, out_stride, D, stream);   \
+    return 0;                                                                                                           \
   }
   SAGE_CASE(32, 32)
   SAGE_CASE(16, 16)

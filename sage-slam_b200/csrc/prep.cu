@@ -104,6 +104,24 @@ void launch_pack_homo(const float *homo3, float4 *homo4, int N, cudaStream_t str
     pack_homo_kernel<<<(N + 255) / 256, 256, 0, stream>>>(homo3, homo4, N);
 }
 
+// sorted[i] = src[perm[i]] for the sample arrays (tile-major order of the staged photometric kernels)
+__global__ void permute_samples_kernel(const int *__restrict__ perm, const int *__restrict__ loc, const float4 *__restrict__ homo,
+                                       int *__restrict__ loc_s, float4 *__restrict__ homo_s, int N)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N)
+  {
+    const int j = perm[i];
+    loc_s[i] = loc[j];
+    homo_s[i] = homo[j];
+  }
+}
+void launch_permute_samples(const int *perm, const int *loc, const float4 *homo, int *loc_s, float4 *homo_s, int N, cudaStream_t stream)
+{
+  if (N > 0)
+    permute_samples_kernel<<<(N + 255) / 256, 256, 0, stream>>>(perm, loc, homo, loc_s, homo_s, N);
+}
+
 // D[p] = bias[p] + basis[p,:] . code      (UpdateDepth without the scale, mapping_utils.h:216-222)
 __global__ void depth_unscaled_kernel(const float *__restrict__ bias, const float *__restrict__ basis, const float *__restrict__ code,
                                       float *__restrict__ D, int HW, int C)

@@ -1,6 +1,6 @@
-// problem.cu -- batched local bundle adjustment: device-resident state, one launch per factor kind,
-// dense fp64 normal equations, Schur complement of the code+scale block onto the pose block with
-// cuSOLVER, and the host LM loop.  New design: the reference hands this to GTSAM ISAM2
+// problem.cu -- batched local bundle adjustment: device-resident state, one launch per factor kind, block-sparse fp64
+// normal equations assembled in a fixed order, elimination by the hand-written block Cholesky of blocksolve.cu (per-keyframe
+// Schur complements), keyframe-owner sharding with the collective issued from C++ (NCCL), and the host LM loop.  New design: the reference hands this to GTSAM ISAM2
 // (core/mapping/mapper.cpp:544); the per-factor arithmetic is the reference's (a1, a4, a5 of SURVEY.md
 // section 8), the priors are CodeFactor / ScaleFactor (core/gtsam/code_factor.cpp:42-104,
 // scale_factor.cpp:115-130) and the retraction is the left-multiplicative one of
@@ -11,30 +11,14 @@
 
 #include <cstdlib>
 
+#include "blocksolve.h"
+#include "comm.h"
 #include "sage_internal.h"
 
 using namespace sage;
 
 namespace sage
 {
-
-struct FactorMeta
-{
-  int kind; // 0 photometric, 1 geometric, 2 reprojection
-  int i, j;
-  int D;
-  int off;      // offset of [AtA | Atb | error | inliers] in the factor buffer
-  int cost_off; // offset of [error | inliers] in the cost buffer
-};
-
-struct PriorSpec
-{
-  int kind; // 0 code, 1 scale
-  int kf;
-  float weight;
-  float init_scale;
-  float init_code[SAGE_MAX_CODE];
-};
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -131,12 +115,13 @@ struct KfMaps
   const float *bias, *basis, *mask;
   float4 *dgm;
   float *dscr;
+  int k; // keyframe index (row of the state arrays)
 };
 
 __global__ void depth_unscaled_batched_kernel(const KfMaps *maps, const float *codes, int HW, int C)
 {
   __shared__ float sc[SAGE_MAX_CODE];
-  const int k = blockIdx.y;
+  const int k = maps[blockIdx.y].k;
   if (threadIdx.x < C)
     sc[threadIdx.x] = codes[k * C + threadIdx.x];
   __syncthreads();
@@ -159,7 +144,7 @@ __global__ void depth_unscaled_batched_kernel(const KfMaps *maps, const float *c
 __global__ void update_depth_batched_kernel(const KfMaps *maps, const float *codes, const float *scales, int HW, int C, float *out)
 {
   __shared__ float sc[SAGE_MAX_CODE];
-  const int k = blockIdx.y;
+  const int k = maps[blockIdx.y].k;
   if (threadIdx.x < C)
     sc[threadIdx.x] = codes[k * C + threadIdx.x];
   __syncthreads();
@@ -191,43 +176,6 @@ __global__ void depth_pack_batched_kernel(const KfMaps *maps, int H, int W)
   const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
   const float *D = m.dscr;
   m.dgm[p] = make_float4(D[p], 0.5f * (D[y * W + xp] - D[y * W + xm]), 0.5f * (D[yp * W + x] - D[ym * W + x]), m.mask[p]);
-}
-
-__device__ __forceinline__ int var_index(const FactorMeta &m, int c, int K, int C)
-{
-  const int cb_i = 6 * K + m.i * (C + 1), cb_j = 6 * K + m.j * (C + 1);
-  if (c < 6)
-    return 6 * m.i + c;
-  if (c < 12)
-    return 6 * m.j + (c - 6);
-  if (m.kind == 1)
-  {
-    if (c < 12 + C)
-      return cb_i + (c - 12);
-    if (c < 12 + 2 * C)
-      return cb_j + (c - 12 - C);
-    return c == 12 + 2 * C ? cb_i + C : cb_j + C;
-  }
-  if (c < 12 + C)
-    return cb_i + (c - 12);
-  return cb_i + C;
-}
-
-// H (fp64, dense n x n) += every factor's AtA scattered to the global variable order; g += Atb
-__global__ void assemble_kernel(const float *__restrict__ fbuf, const FactorMeta *__restrict__ metas, double *__restrict__ H,
-                                double *__restrict__ g, int n, int K, int C)
-{
-  const FactorMeta m = metas[blockIdx.x];
-  const float *A = fbuf + m.off;
-  const int D = m.D;
-  for (int e = threadIdx.x; e < D * D; e += blockDim.x)
-  {
-    const float v = A[e];
-    if (v != 0.f)
-      atomicAdd(&H[(size_t)var_index(m, e / D, K, C) * n + var_index(m, e % D, K, C)], (double)v);
-  }
-  for (int r = threadIdx.x; r < D; r += blockDim.x)
-    atomicAdd(&g[var_index(m, r, K, C)], (double)A[D * D + r]);
 }
 
 // priors: CodeFactor (AtA = w I, Atb = w (init - code), err = w mean((init-code)^2)) and ScaleFactor
@@ -296,28 +244,8 @@ __global__ void total_cost_kernel(const float *buf, const int *pos, int nf, cons
     *total = red[0] + *prior;
 }
 
-// Hd = H with damped diagonal; fixed variables become identity rows/cols with zero gradient
-__global__ void damp_kernel(const double *H, const double *g, const unsigned char *fixed, double *Hd, double *gd, int n, double damp)
-{
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (size_t)n * n)
-    return;
-  const int r = (int)(e / n), c = (int)(e % n);
-  double v = H[e];
-  if (fixed[r] || fixed[c])
-    v = (r == c) ? 1.0 : 0.0;
-  else if (r == c)
-  {
-    v = v + damp * v;
-    if (!(v > 0.0))
-      v = 1.0; // variable untouched by any factor: keep the system positive definite
-  }
-  Hd[e] = v;
-  if (c == 0)
-    gd[r] = fixed[r] ? 0.0 : g[r];
-}
-
-// Same as damp_kernel, but writes the system with the code+scale block FIRST and the pose block LAST (variable v moves to
+// Dense cross-check solver: Hd = H with damped diagonal (fixed variables become identity rows / columns with zero gradient),
+// written with the code+scale block FIRST and the pose block LAST (variable v moves to
 // v + nc for poses, v - np for the rest), so that one Cholesky factorisation of the whole matrix eliminates the code block,
 // forms the Schur complement onto the pose block in its trailing sub-matrix and factors it (block Cholesky == Schur).
 __global__ void damp_perm_kernel(const double *H, const double *g, const unsigned char *fixed, double *Hd, double *gd, int n, int np,
@@ -412,16 +340,18 @@ __global__ void retract_kernel(const float *poses, const float *codes, const flo
 
 } // namespace sage
 
+
 struct sage_ba_problem
 {
   sage_ba_context *ctx = nullptr;
   int K = 0, F = 0, C = 0, L = 0, H = 0, W = 0, N = 0;
-  std::vector<sage_ba_keyframe *> kfs;
+  std::vector<sage_ba_keyframe *> kfs; // entries of keyframes this rank never touches may be null
+  sage_ba_keyframe *kf_any = nullptr;  // any non-null keyframe (shapes, cameras)
   float eps = 1e-4f;
   int rank = 0, world = 1;
   bool built = false;
 
-  // factor specs in order of addition (global index = position in `metas`)
+  // factor specs in order of addition (global index = position in `metas`); typed lists hold only this rank's factors
   std::vector<FactorMeta> metas;
   std::vector<PhotoFactor> photo_h;
   std::vector<GeoFactor> geo_h;
@@ -430,7 +360,7 @@ struct sage_ba_problem
   std::vector<PriorSpec> priors;
   std::vector<unsigned char> fixed_h;
   std::vector<void *> owned; // device allocations owned by the problem (match arrays)
-  size_t fbuf_count = 0;
+  size_t fbuf_count = 0, fseg = 0, cseg = 0; // packed buffers: `world` segments of fseg / cseg floats, one per owner
   long residuals = 0;
 
   // device
@@ -442,23 +372,28 @@ struct sage_ba_problem
   DevBuf<FactorMeta> metas_d;
   DevBuf<PriorSpec> priors_d;
   DevBuf<int> errpos_d, costpos_d;
-  DevBuf<KfMaps> maps_d;
+  DevBuf<KfMaps> maps_d, maps_all_d;
+  int n_maps = 0; // keyframes whose depth map this rank rebuilds per state (targets of its geometric factors)
   DevBuf<float> state[2][3]; // [which][poses, codes, scales]
   DevBuf<float> fbuf, cbuf, partH, partE, depth_out;
-  DevBuf<double> Hm, gv, Hd, gd, delta, prior_cost, total_cost, work;
+  DevBuf<double> Hm, gv, Hd, gd, delta, prior_cost, total_cost, work; // Hm .. gd / work: dense cross-check path only
   DevBuf<int> info;
   DevBuf<unsigned char> fixed_d;
   PinBuf<double> hcost;
   PinBuf<int> hinfo;
   int potrf_lwork = 0;
-  int bandwidth = 0;       // max |i - j| over the factors' keyframe pairs
-  int solver = 0;          // 0: auto, 1: dense Schur + cuSOLVER, 2: block-banded Cholesky
-  bool use_banded = false; // decided at build time
-  DevBuf<double> band;
+  int solver = 0;      // 0: block Cholesky, nested-dissection order; 1: dense fused-Schur potrf (cuSOLVER, cross-check); 2: block Cholesky, natural order
+  bool staged = false; // opt-in (SAGE_BA_STAGED=1): photometric kernels read levels >= 1 from TMA-staged windows; measured slower, see profiles/README.md
+  bool dense_valid = false;
+  bool lin_valid = false;         // fbuf / H hold the linearisation at state[0]
+  bool relinearize_always = false; // lm_step: linearise even when the state did not change since the last linearisation
+  bool deterministic = false;      // CTA decomposition independent of the rank count (bit-identical results for any world size)
+  BlockSystem bs;
   int slices_photo = 32, slices_geo = 32, slices_photo_err = 32, slices_geo_err = 32; // CTAs per factor (linearise / error-only)
 
   sage_ba_allreduce_fn allreduce = nullptr;
   void *allreduce_user = nullptr;
+  sage_ba_comm *comm = nullptr;
 
   // optional CUDA-event profiling of the launches (bench.py's roofline leg)
   bool profiling = false;
@@ -473,6 +408,7 @@ struct sage_ba_problem
   long prof_n[SAGE_BA_PROF_KINDS] = {0};
 
   int dim() const { return K * (7 + C); }
+  int owner_of(int kf) const { return sage_ba_shard_owner(K, world, kf); }
 };
 
 namespace sage
@@ -502,11 +438,13 @@ struct ProfScope
     cudaEventRecord(a, p->ctx->stream);
     p->spans.push_back({kind, a, b});
   }
-  ~ProfScope()
+  void end()
   {
     if (b)
       cudaEventRecord(b, p->ctx->stream);
+    b = nullptr;
   }
+  ~ProfScope() { end(); }
 };
 
 static void problem_build(sage_ba_problem *p)
@@ -516,41 +454,53 @@ static void problem_build(sage_ba_problem *p)
   sage_ba_context *ctx = p->ctx;
   cudaStream_t s = ctx->stream;
   const int K = p->K, C = p->C;
-  // shard: factor with global index f belongs to rank f % world
-  std::vector<PhotoFactor> ph;
-  std::vector<GeoFactor> ge;
-  std::vector<ReprojFactor> re;
+  // ---- packed output buffers: one segment per owner rank (all-gather friendly), factors in order of addition inside it
+  {
+    std::vector<size_t> used(p->world, 0), cnt(p->world, 0);
+    for (FactorMeta &m : p->metas)
+    {
+      m.off = (int)used[m.owner];
+      m.cost_off = (int)(2 * cnt[m.owner]);
+      used[m.owner] += (size_t)m.D * m.D + m.D + 2;
+      cnt[m.owner] += 1;
+    }
+    size_t fmax = 4, cmax = 4;
+    for (int r = 0; r < p->world; ++r)
+    {
+      fmax = std::max(fmax, used[r]);
+      cmax = std::max(cmax, 2 * cnt[r]);
+    }
+    p->fseg = (fmax + 31) / 32 * 32;
+    p->cseg = (cmax + 31) / 32 * 32;
+    for (FactorMeta &m : p->metas)
+    {
+      m.off += (int)(m.owner * p->fseg);
+      m.cost_off += (int)(m.owner * p->cseg);
+    }
+    p->fbuf_count = p->fseg * p->world;
+  }
   std::vector<int2> pij, gij, rij, poff, goff, roff;
   for (size_t q = 0; q < p->photo_h.size(); ++q)
   {
     const FactorMeta &m = p->metas[p->photo_g[q]];
-    if (p->photo_g[q] % p->world != p->rank)
-      continue;
-    ph.push_back(p->photo_h[q]);
     pij.push_back(make_int2(m.i, m.j));
     poff.push_back(make_int2(m.off, m.cost_off));
   }
   for (size_t q = 0; q < p->geo_h.size(); ++q)
   {
     const FactorMeta &m = p->metas[p->geo_g[q]];
-    if (p->geo_g[q] % p->world != p->rank)
-      continue;
-    ge.push_back(p->geo_h[q]);
     gij.push_back(make_int2(m.i, m.j));
     goff.push_back(make_int2(m.off, m.cost_off));
   }
   for (size_t q = 0; q < p->reproj_h.size(); ++q)
   {
     const FactorMeta &m = p->metas[p->reproj_g[q]];
-    if (p->reproj_g[q] % p->world != p->rank)
-      continue;
-    re.push_back(p->reproj_h[q]);
     rij.push_back(make_int2(m.i, m.j));
     roff.push_back(make_int2(m.off, m.cost_off));
   }
-  p->n_photo = (int)ph.size();
-  p->n_geo = (int)ge.size();
-  p->n_reproj = (int)re.size();
+  p->n_photo = (int)p->photo_h.size();
+  p->n_geo = (int)p->geo_h.size();
+  p->n_reproj = (int)p->reproj_h.size();
   auto up = [&](auto &dev, const auto &host) {
     using T = typename std::remove_reference<decltype(host[0])>::type;
     if (host.empty())
@@ -558,9 +508,9 @@ static void problem_build(sage_ba_problem *p)
     auto *d = dev.ensure(host.size());
     SAGE_CUDA(cudaMemcpyAsync((void *)d, (const void *)host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   };
-  up(p->photo_d, ph);
-  up(p->geo_d, ge);
-  up(p->reproj_d, re);
+  up(p->photo_d, p->photo_h);
+  up(p->geo_d, p->geo_h);
+  up(p->reproj_d, p->reproj_h);
   up(p->photo_ij, pij);
   up(p->geo_ij, gij);
   up(p->reproj_ij, rij);
@@ -577,35 +527,48 @@ static void problem_build(sage_ba_problem *p)
   }
   up(p->errpos_d, errpos);
   up(p->costpos_d, costpos);
-  std::vector<KfMaps> maps;
-  for (sage_ba_keyframe *kf : p->kfs)
-    maps.push_back(KfMaps{kf->bias, kf->basis, kf->mask, kf->dgm, kf->dscr});
+  // depth maps are rebuilt per state only for the targets of this rank's geometric factors
+  std::vector<KfMaps> maps, maps_all;
+  {
+    std::vector<char> need(K, 0);
+    for (size_t q = 0; q < p->geo_h.size(); ++q)
+      need[p->metas[p->geo_g[q]].j] = 1;
+    for (int k = 0; k < K; ++k)
+    {
+      sage_ba_keyframe *kf = p->kfs[k];
+      if (kf && kf->bias)
+        maps_all.push_back(KfMaps{kf->bias, kf->basis, kf->mask, kf->dgm, kf->dscr, k});
+      if (need[k])
+        maps.push_back(KfMaps{kf->bias, kf->basis, kf->mask, kf->dgm, kf->dscr, k});
+    }
+  }
+  p->n_maps = (int)maps.size();
   up(p->maps_d, maps);
+  up(p->maps_all_d, maps_all);
   if (p->fixed_h.empty())
     p->fixed_h.assign(p->dim(), 0);
   up(p->fixed_d, p->fixed_h);
+  p->bs.build(K, C, p->metas, p->priors, p->fixed_h, p->solver == 2 ? 1 : (getenv("SAGE_BA_NATURAL_ORDER") ? 1 : 0), s);
 
-  p->bandwidth = 0;
-  for (const FactorMeta &m : p->metas)
-    p->bandwidth = std::max(p->bandwidth, std::abs(m.i - m.j));
-  // block-banded Cholesky pays off for chain-shaped graphs; dense Schur + cuSOLVER is the general path
-  const bool banded_ok = p->bandwidth <= 7 && banded_smem_bytes(C, p->bandwidth) <= 200 * 1024 &&
-                         (size_t)K * (p->bandwidth + 1) * (p->bandwidth + 1) <= 4096;
-  // measured on B200 (32 KF, b = 3): single-CTA banded 3.8 ms vs dense Schur + cuSOLVER 1.4 ms -> auto stays dense
-  p->use_banded = p->solver == 2 ? banded_ok : false;
-  SAGE_CHECK(p->solver != 2 || banded_ok, "banded solver requested but the covisibility graph is not narrow-banded");
-  if (p->use_banded)
-    p->band.ensure(banded_workspace_doubles(K, C, p->bandwidth));
-  const int n = p->dim();
   p->fbuf.ensure(std::max<size_t>(p->fbuf_count, 4));
-  p->cbuf.ensure(std::max<size_t>(p->metas.size() * 2, 4));
+  p->cbuf.ensure(std::max<size_t>(p->cseg * p->world, 4));
   SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf.cap * sizeof(float), s));
   SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->cbuf.cap * sizeof(float), s));
-  // slices = CTAs per factor.  The factor kernels run a handful of waves, so the count is chosen to END on a full wave:
-  // slices = floor(waves * resident_CTAs / factors) for the largest wave count that still leaves every CTA a few thousand
-  // samples (per-CTA cost: factor load, partial store, one more partial for the finalize kernel).  Measured on B200,
-  // 32 KF / 180 pairs: photometric linearisation 7.41 ms at 14 slices (5.7 waves) vs 7.19 ms at 12 (4.9 waves); error pass
-  // 2.51 -> 2.24 ms at 16; geometric 3.00 -> 2.60 ms at 46 (7.0 waves instead of 0.9).
+  // slices = CTAs per factor.  Two policies:
+  //  * default: end the launch on a full wave -- slices = floor(waves * resident CTAs / owned factors) for the largest wave count
+  //    that still leaves every CTA a couple of thousand samples.  The factor kernels run only a handful of waves and a CTA costs
+  //    ~20 us beyond its samples (its four warps drift apart, the slot idles until the last one is done), so coarse slices that
+  //    fill whole waves are worth 10 % (32 KF / 180 pairs, B200: lineariser 6.97 ms at 12 slices, 7.7 ms at 40, 8.0 ms at 80).
+  //    The count then depends on how many factors the rank owns, i.e. on the number of GPUs: a factor's partial sums are added
+  //    in a different order, its outputs agree across GPU counts to fp32 round-off (1e-7), not bit for bit.
+  //  * deterministic (sage_ba_problem_set_deterministic, SAGE_BA_DETERMINISTIC=1): the count depends on the problem only (samples
+  //    per keyframe).  With the fixed-order assembly and the flag-ordered solver the whole LM trajectory is then BIT-identical
+  //    for every number of GPUs (tests/test_gpu_multirank.py), at the price above.
+  auto per_cta = [&](const char *env, int dflt) {
+    const char *e = getenv(env);
+    const int spc = e ? std::max(32, atoi(e)) : dflt;
+    return std::max(1, (p->N + spc - 1) / spc);
+  };
   auto pick = [&](int nfac, int ctas_per_sm, int max_waves, int min_samples_per_cta) {
     if (nfac <= 0)
       return 1;
@@ -619,47 +582,57 @@ static void problem_build(sage_ba_problem *p)
     }
     return std::max(1, std::min(cap, slots / nfac));
   };
-  p->slices_photo = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_JAC, p->F, C), 5, 2048);
-  p->slices_photo_err = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_ERR, p->F, C), 5, 2048);
-  p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C), 7, 1024);
-  p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C), 8, 512);
-  // tuning aid: override the heuristics above
-  if (const char *e = getenv("SAGE_BA_SLICES_PHOTO"))
-    p->slices_photo = std::max(1, atoi(e));
-  if (const char *e = getenv("SAGE_BA_SLICES_GEO"))
-    p->slices_geo = std::max(1, atoi(e));
-  if (const char *e = getenv("SAGE_BA_SLICES_PHOTO_ERR"))
-    p->slices_photo_err = std::max(1, atoi(e));
-  if (const char *e = getenv("SAGE_BA_SLICES_GEO_ERR"))
-    p->slices_geo_err = std::max(1, atoi(e));
+  if (p->deterministic)
+  {
+    p->slices_photo = per_cta("SAGE_BA_SPC_PHOTO", 2048);
+    p->slices_photo_err = per_cta("SAGE_BA_SPC_PHOTO_ERR", 2048);
+    p->slices_geo = per_cta("SAGE_BA_SPC_GEO", 2048);
+    p->slices_geo_err = per_cta("SAGE_BA_SPC_GEO_ERR", 1024);
+  }
+  else
+  {
+    p->slices_photo = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), 5, 2048);
+    p->slices_photo_err = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_ERR, p->F, C, p->staged), 5, 2048);
+    p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C), 7, 1024);
+    p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C), 8, 512);
+    if (const char *e = getenv("SAGE_BA_SLICES_PHOTO"))
+      p->slices_photo = std::max(1, atoi(e));
+    if (const char *e = getenv("SAGE_BA_SLICES_GEO"))
+      p->slices_geo = std::max(1, atoi(e));
+    if (const char *e = getenv("SAGE_BA_SLICES_PHOTO_ERR"))
+      p->slices_photo_err = std::max(1, atoi(e));
+    if (const char *e = getenv("SAGE_BA_SLICES_GEO_ERR"))
+      p->slices_geo_err = std::max(1, atoi(e));
+  }
   const int WPp = 8 + C, WPg = 16 + 2 * C;
   const size_t nh = std::max((size_t)p->n_photo * p->slices_photo * WPp * WPp, (size_t)p->n_geo * p->slices_geo * WPg * WPg);
   p->partH.ensure(std::max<size_t>(nh, 4));
   p->partE.ensure(std::max<size_t>(2 * std::max((size_t)p->n_photo * std::max(p->slices_photo, p->slices_photo_err),
                                                  (size_t)p->n_geo * std::max(p->slices_geo, p->slices_geo_err)), 4));
-  p->Hm.ensure((size_t)n * n);
-  p->Hd.ensure((size_t)n * n);
-  p->gv.ensure(n);
-  p->gd.ensure(n);
+  const int n = p->dim();
   p->delta.ensure(n);
+  SAGE_CUDA(cudaMemsetAsync(p->delta.p, 0, sizeof(double) * n, s));
   p->prior_cost.ensure(2);
   p->total_cost.ensure(2);
   p->info.ensure(4);
   p->hcost.ensure(4);
   p->hinfo.ensure(4);
-  int lw1 = 0, lw2 = 0;
-  const int np = 6 * K, nc = n - np;
-  SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, nc, p->Hd.p, n, &lw1) == CUSOLVER_STATUS_SUCCESS,
-             "potrf_bufferSize failed");
-  SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, np, p->Hd.p, n, &lw2) == CUSOLVER_STATUS_SUCCESS,
-             "potrf_bufferSize failed");
-  int lw3 = 0;
-  SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, n, p->Hd.p, n, &lw3) == CUSOLVER_STATUS_SUCCESS,
-             "potrf_bufferSize failed");
-  p->potrf_lwork = std::max(std::max(lw1, lw2), lw3);
-  p->work.ensure(std::max(p->potrf_lwork, 4));
   SAGE_CUDA(cudaStreamSynchronize(s));
   p->built = true;
+}
+
+// dense copies of H / g (tests, the cuSOLVER cross-check solver); allocated on first use
+static void ensure_dense(sage_ba_problem *p)
+{
+  sage_ba_context *ctx = p->ctx;
+  const int n = p->dim();
+  p->Hm.ensure((size_t)n * n);
+  p->gv.ensure(n);
+  if (!p->dense_valid)
+  {
+    p->bs.expand_dense(p->Hm.p, p->gv.p, n, ctx->stream, &ctx->launches);
+    p->dense_valid = true;
+  }
 }
 
 static void refresh_factors(sage_ba_problem *p, int which, bool jac)
@@ -678,7 +651,7 @@ static void refresh_factors(sage_ba_problem *p, int which, bool jac)
     setup_geo_kernel<<<(p->n_geo + 127) / 128, 128, 0, s>>>(p->geo_d.p, p->geo_ij.p, p->geo_off.p, p->n_geo, poses, codes, scales, p->C,
                                                             p->eps, jac);
     const int HW = p->H * p->W;
-    dim3 grid((HW + 255) / 256, p->K);
+    dim3 grid((HW + 255) / 256, p->n_maps);
     ProfScope ps(p, SAGE_BA_PROF_DEPTH_PREP);
     depth_unscaled_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, codes, HW, p->C);
     depth_pack_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, p->H, p->W);
@@ -696,12 +669,12 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
 {
   sage_ba_context *ctx = p->ctx;
   cudaStream_t s = ctx->stream;
-  const sage_ba_keyframe *k0 = p->kfs[0];
+  const sage_ba_keyframe *k0 = p->kf_any;
   if (p->n_photo)
   {
     ProfScope ps(p, jac ? SAGE_BA_PROF_PHOTO_JAC : SAGE_BA_PROF_PHOTO_ERR);
     SAGE_CHECK(launch_photo(jac ? PH_MAP_JAC : PH_MAP_ERR, p->F, p->C, p->photo_d.p, p->n_photo, k0->pyr, jac ? p->slices_photo : p->slices_photo_err, p->partH.p,
-                            p->partE.p, out, 1, 13 + p->C, s) == 0,
+                            p->partE.p, out, 1, 13 + p->C, s, p->staged) == 0,
                "unsupported (feat_channels, code_size)");
     ctx->launches += 2;
   }
@@ -721,6 +694,21 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
     ctx->launches += 1;
   }
   SAGE_CUDA(cudaGetLastError());
+}
+
+// make a packed buffer (one segment per owner) complete on every rank
+static void exchange(sage_ba_problem *p, float *buf, size_t seg)
+{
+  if (p->world <= 1)
+    return;
+  ProfScope ps(p, SAGE_BA_PROF_COMM);
+  if (p->comm)
+  {
+    const std::string e = nccl_allgather_inplace(p->comm->nccl, buf, seg, p->rank, p->ctx->stream);
+    SAGE_CHECK(e.empty(), e);
+  }
+  else if (p->allreduce)
+    SAGE_CHECK(p->allreduce(buf, seg * p->world, p->allreduce_user) == 0, "all-reduce callback failed");
 }
 
 } // namespace sage
@@ -749,6 +737,14 @@ static void run_factors(sage_ba_problem *p, bool jac, float *out)
 
 extern "C" {
 
+int sage_ba_shard_owner(int num_keyframes, int world, int kf)
+{
+  if (world <= 1 || num_keyframes <= 0)
+    return 0;
+  const long r = (long)kf * world / num_keyframes;
+  return (int)std::min<long>(std::max<long>(r, 0), world - 1);
+}
+
 int sage_ba_problem_create(sage_ba_context *ctx, int num_keyframes, sage_ba_keyframe *const *kfs, sage_ba_problem **out)
 {
   if (!ctx || !out)
@@ -762,20 +758,28 @@ int sage_ba_problem_create(sage_ba_context *ctx, int num_keyframes, sage_ba_keyf
     p->K = num_keyframes;
     for (int k = 0; k < num_keyframes; ++k)
     {
-      SAGE_CHECK(kfs[k] && kfs[k]->bias && kfs[k]->loc1d && kfs[k]->fg && kfs[k]->mask && kfs[k]->sfeat,
-                 "keyframes of a problem need feature maps, mask, depth and sample data");
-      if (k)
-        SAGE_CHECK(kfs[k]->H == kfs[0]->H && kfs[k]->W == kfs[0]->W && kfs[k]->F == kfs[0]->F && kfs[k]->C == kfs[0]->C &&
-                       kfs[k]->L == kfs[0]->L,
+      // a null entry is a keyframe this process never touches (another rank owns every factor it takes part in)
+      if (kfs[k])
+      {
+        if (!p->kf_any)
+          p->kf_any = kfs[k];
+        SAGE_CHECK(kfs[k]->H == p->kf_any->H && kfs[k]->W == p->kf_any->W && kfs[k]->F == p->kf_any->F && kfs[k]->C == p->kf_any->C &&
+                       kfs[k]->L == p->kf_any->L,
                    "keyframes have different shapes");
+      }
       p->kfs.push_back(kfs[k]);
     }
-    p->F = kfs[0]->F;
-    p->C = kfs[0]->C;
-    p->L = kfs[0]->L;
-    p->H = kfs[0]->H;
-    p->W = kfs[0]->W;
-    p->N = kfs[0]->N;
+    SAGE_CHECK(p->kf_any, "need at least one keyframe");
+    if (const char *e = getenv("SAGE_BA_STAGED"))
+      p->staged = atoi(e) != 0;
+    if (const char *e = getenv("SAGE_BA_DETERMINISTIC"))
+      p->deterministic = atoi(e) != 0;
+    p->F = p->kf_any->F;
+    p->C = p->kf_any->C;
+    p->L = p->kf_any->L;
+    p->H = p->kf_any->H;
+    p->W = p->kf_any->W;
+    p->N = p->kf_any->N;
     SAGE_CUDA(cudaSetDevice(ctx->device));
     for (int w = 0; w < 2; ++w)
     {
@@ -801,6 +805,13 @@ void sage_ba_problem_destroy(sage_ba_problem *p)
   cudaStreamSynchronize(p->ctx->stream);
   for (void *q : p->owned)
     cudaFree(q);
+  for (auto &sp : p->spans)
+  {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  for (cudaEvent_t e : p->event_pool)
+    cudaEventDestroy(e);
   delete p;
 }
 
@@ -811,11 +822,21 @@ static int add_meta(sage_ba_problem *p, int kind, int i, int j, int D)
   m.i = i;
   m.j = j;
   m.D = D;
-  m.off = (int)p->fbuf_count;
-  m.cost_off = (int)p->metas.size() * 2;
-  p->fbuf_count += (size_t)D * D + D + 2;
+  m.off = 0; // offsets are assigned when the problem is built (they depend on the sharding)
+  m.cost_off = 0;
+  m.owner = p->owner_of(i);
   p->metas.push_back(m);
   return (int)p->metas.size() - 1;
+}
+
+static const sage_ba_keyframe *need_kf(sage_ba_problem *p, int k, bool depth, bool feats, bool samples)
+{
+  const sage_ba_keyframe *kf = p->kfs[k];
+  SAGE_CHECK(kf, "a keyframe this rank's factors touch was passed as null");
+  SAGE_CHECK(!depth || (kf->bias && kf->basis), "keyframe lacks depth data");
+  SAGE_CHECK(!feats || (kf->fg && kf->mask), "keyframe lacks feature maps / mask");
+  SAGE_CHECK(!samples || (kf->loc1d && kf->homo && kf->N == p->N), "keyframe lacks sample data (or sample counts differ)");
+  return kf;
 }
 
 int sage_ba_problem_add_photometric(sage_ba_problem *p, int i, int j, const float *weights)
@@ -823,22 +844,37 @@ int sage_ba_problem_add_photometric(sage_ba_problem *p, int i, int j, const floa
   SAGE_PTRY(p)
   SAGE_CHECK(!p->built, "problem already built");
   SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
-  const sage_ba_keyframe *a = p->kfs[i], *b = p->kfs[j];
-  PhotoFactor f;
-  memset(&f, 0, sizeof(f));
-  f.fg0 = a->fg;
-  f.sfeat0 = a->sfeat;
-  f.fg1 = b->fg;
-  f.mask1 = b->mask;
-  f.bias0 = a->bias;
-  f.basis0 = a->basis;
-  f.loc1d = a->loc1d;
-  f.homo = a->homo;
-  f.N = a->N;
-  memcpy(f.w, weights, sizeof(float) * p->L);
-  p->photo_h.push_back(f);
-  p->photo_g.push_back(add_meta(p, 0, i, j, 13 + p->C));
-  p->residuals += (long)p->L * a->N * p->F;
+  const int gi = add_meta(p, 0, i, j, 13 + p->C);
+  p->residuals += (long)p->L * p->N * p->F;
+  if (p->metas[gi].owner == p->rank)
+  {
+    const sage_ba_keyframe *a = need_kf(p, i, true, true, true), *b = need_kf(p, j, false, true, false);
+    SAGE_CHECK(a->sfeat, "keyframe lacks pre-sampled features");
+    PhotoFactor f;
+    memset(&f, 0, sizeof(f));
+    f.fg0 = a->fg;
+    f.fg1 = b->fg;
+    f.mask1 = b->mask;
+    f.bias0 = a->bias;
+    f.basis0 = a->basis;
+    if (p->staged)
+    {
+      ensure_sorted_samples(ctx__, p->kfs[i]);
+      f.sfeat0 = a->sfeat_s;
+      f.loc1d = a->loc1d_s;
+      f.homo = a->homo_s;
+    }
+    else
+    {
+      f.sfeat0 = a->sfeat;
+      f.loc1d = a->loc1d;
+      f.homo = a->homo;
+    }
+    f.N = a->N;
+    memcpy(f.w, weights, sizeof(float) * p->L);
+    p->photo_h.push_back(f);
+    p->photo_g.push_back(gi);
+  }
   SAGE_PCATCH
 }
 
@@ -847,21 +883,26 @@ int sage_ba_problem_add_geometric(sage_ba_problem *p, int i, int j, float loss_p
   SAGE_PTRY(p)
   SAGE_CHECK(!p->built, "problem already built");
   SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
-  const sage_ba_keyframe *a = p->kfs[i], *b = p->kfs[j];
-  GeoFactor f;
-  memset(&f, 0, sizeof(f));
-  f.bias0 = a->bias;
-  f.basis0 = a->basis;
-  f.loc1d = a->loc1d;
-  f.homo = a->homo;
-  f.dgm1 = b->dgm;
-  f.basis1 = b->basis;
-  f.N = a->N;
-  f.loss_param = loss_param;
-  f.weight = weight;
-  p->geo_h.push_back(f);
-  p->geo_g.push_back(add_meta(p, 1, i, j, 14 + 2 * p->C));
-  p->residuals += a->N;
+  const int gi = add_meta(p, 1, i, j, 14 + 2 * p->C);
+  p->residuals += p->N;
+  if (p->metas[gi].owner == p->rank)
+  {
+    const sage_ba_keyframe *a = need_kf(p, i, true, false, true), *b = need_kf(p, j, true, false, false);
+    SAGE_CHECK(b->mask && b->dgm, "keyframe lacks mask / depth-map buffers");
+    GeoFactor f;
+    memset(&f, 0, sizeof(f));
+    f.bias0 = a->bias;
+    f.basis0 = a->basis;
+    f.loc1d = a->loc1d;
+    f.homo = a->homo;
+    f.dgm1 = b->dgm;
+    f.basis1 = b->basis;
+    f.N = a->N;
+    f.loss_param = loss_param;
+    f.weight = weight;
+    p->geo_h.push_back(f);
+    p->geo_g.push_back(gi);
+  }
   SAGE_PCATCH
 }
 
@@ -872,32 +913,39 @@ int sage_ba_problem_add_reprojection(sage_ba_problem *p, int i, int j, const int
   SAGE_CHECK(!p->built, "problem already built");
   SAGE_CHECK(i >= 0 && j >= 0 && i < p->K && j < p->K && i != j, "bad keyframe index");
   SAGE_CHECK(M > 0 && M <= 4096, "num_matches out of range");
-  const sage_ba_keyframe *a = p->kfs[i];
-  float *dm = nullptr;
-  SAGE_CUDA(cudaMalloc(&dm, sizeof(float) * 6 * M));
-  p->owned.push_back(dm);
-  std::vector<float> hm((size_t)6 * M);
-  memcpy(hm.data(), homo, sizeof(float) * 3 * M);
-  memcpy(hm.data() + 3 * M, match2d, sizeof(float) * 2 * M);
-  memcpy(hm.data() + 5 * M, loc1d, sizeof(int32_t) * M);
-  SAGE_CUDA(cudaMemcpy(dm, hm.data(), sizeof(float) * 6 * M, cudaMemcpyHostToDevice));
-  ReprojFactor f;
-  memset(&f, 0, sizeof(f));
-  f.bias0 = a->bias;
-  f.basis0 = a->basis;
-  f.homo = dm;
-  f.match2d = dm + 3 * M;
-  f.loc1d = reinterpret_cast<const int *>(dm + 5 * M);
-  f.M = M;
-  f.loss_param = loss_param;
-  f.weight = weight;
-  f.fx = a->cams[0].fx;
-  f.fy = a->cams[0].fy;
-  f.cx = a->cams[0].u0;
-  f.cy = a->cams[0].v0;
-  p->reproj_h.push_back(f);
-  p->reproj_g.push_back(add_meta(p, 2, i, j, 13 + p->C));
+  SAGE_CHECK(loc1d && homo && match2d, "null match arrays");
+  for (int m = 0; m < M; ++m)
+    SAGE_CHECK(loc1d[m] >= 0 && loc1d[m] < p->H * p->W, "matched location outside the image");
+  const int gi = add_meta(p, 2, i, j, 13 + p->C);
   p->residuals += 2L * M;
+  if (p->metas[gi].owner == p->rank)
+  {
+    const sage_ba_keyframe *a = need_kf(p, i, true, false, false);
+    float *dm = nullptr;
+    SAGE_CUDA(cudaMalloc(&dm, sizeof(float) * 6 * M));
+    p->owned.push_back(dm);
+    std::vector<float> hm((size_t)6 * M);
+    memcpy(hm.data(), homo, sizeof(float) * 3 * M);
+    memcpy(hm.data() + 3 * M, match2d, sizeof(float) * 2 * M);
+    memcpy(hm.data() + 5 * M, loc1d, sizeof(int32_t) * M);
+    SAGE_CUDA(cudaMemcpy(dm, hm.data(), sizeof(float) * 6 * M, cudaMemcpyHostToDevice));
+    ReprojFactor f;
+    memset(&f, 0, sizeof(f));
+    f.bias0 = a->bias;
+    f.basis0 = a->basis;
+    f.homo = dm;
+    f.match2d = dm + 3 * M;
+    f.loc1d = reinterpret_cast<const int *>(dm + 5 * M);
+    f.M = M;
+    f.loss_param = loss_param;
+    f.weight = weight;
+    f.fx = a->cams[0].fx;
+    f.fy = a->cams[0].fy;
+    f.cx = a->cams[0].u0;
+    f.cy = a->cams[0].v0;
+    p->reproj_h.push_back(f);
+    p->reproj_g.push_back(gi);
+  }
   SAGE_PCATCH
 }
 
@@ -951,7 +999,7 @@ int sage_ba_problem_set_solver(sage_ba_problem *p, int solver)
 {
   SAGE_PTRY(p)
   SAGE_CHECK(!p->built, "problem already built");
-  SAGE_CHECK(solver >= 0 && solver <= 2, "solver must be 0 (auto), 1 (dense Schur) or 2 (block-banded)");
+  SAGE_CHECK(solver >= 0 && solver <= 2, "solver must be 0 (block Cholesky), 1 (dense cuSOLVER cross-check) or 2 (block Cholesky, natural order)");
   p->solver = solver;
   SAGE_PCATCH
 }
@@ -959,11 +1007,27 @@ int sage_ba_problem_set_solver(sage_ba_problem *p, int solver)
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world)
 {
   SAGE_PTRY(p)
-  SAGE_CHECK(!p->built, "problem already built");
+  SAGE_CHECK(!p->built && p->metas.empty(), "set the shard before adding factors");
   SAGE_CHECK(world >= 1 && rank >= 0 && rank < world, "bad shard");
   p->rank = rank;
   p->world = world;
   SAGE_PCATCH
+}
+
+int sage_ba_problem_set_deterministic(sage_ba_problem *p, int on)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!p->built, "problem already built");
+  p->deterministic = on != 0;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_set_relinearize_always(sage_ba_problem *p, int always)
+{
+  if (!p)
+    return 1;
+  p->relinearize_always = always != 0;
+  return 0;
 }
 
 int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses, const float *codes, const float *scales, float eps)
@@ -971,6 +1035,7 @@ int sage_ba_problem_set_state(sage_ba_problem *p, const float *poses, const floa
   SAGE_PTRY(p)
   cudaStream_t s = ctx__->stream;
   p->eps = eps;
+  p->lin_valid = false;
   SAGE_CUDA(cudaMemcpyAsync(p->state[0][0].p, poses, sizeof(float) * p->K * 12, cudaMemcpyHostToDevice, s));
   SAGE_CUDA(cudaMemcpyAsync(p->state[0][1].p, codes, sizeof(float) * p->K * p->C, cudaMemcpyHostToDevice, s));
   SAGE_CUDA(cudaMemcpyAsync(p->state[0][2].p, scales, sizeof(float) * p->K, cudaMemcpyHostToDevice, s));
@@ -1004,9 +1069,14 @@ int sage_ba_problem_update_map(sage_ba_problem *p, float *poses, float *codes, f
     SAGE_CUDA(cudaMemcpyAsync(scales, p->state[0][2].p, sizeof(float) * p->K, cudaMemcpyDeviceToHost, s));
   if (dpt_maps)
   {
+    // every keyframe resident on this rank with depth data (all of them unless the caller sharded the uploads)
+    int nk = 0;
+    for (int k = 0; k < p->K; ++k)
+      nk += (p->kfs[k] && p->kfs[k]->bias) ? 1 : 0;
+    SAGE_CHECK(nk == p->K, "update_map needs every keyframe's depth data on this rank");
     float *dst = memory == SAGE_BA_DEVICE ? dpt_maps : p->depth_out.ensure((size_t)p->K * HW);
     dim3 grid((unsigned)((HW + 255) / 256), p->K);
-    update_depth_batched_kernel<<<grid, 256, 0, s>>>(p->maps_d.p, p->state[0][1].p, p->state[0][2].p, (int)HW, p->C, dst);
+    update_depth_batched_kernel<<<grid, 256, 0, s>>>(p->maps_all_d.p, p->state[0][1].p, p->state[0][2].p, (int)HW, p->C, dst);
     ctx__->launches++;
     SAGE_CUDA(cudaGetLastError());
     if (memory == SAGE_BA_HOST)
@@ -1038,7 +1108,36 @@ int sage_ba_problem_cost_buffer(sage_ba_problem *p, float **ptr, size_t *count)
   if (ptr)
     *ptr = p->cbuf.p;
   if (count)
-    *count = p->metas.size() * 2;
+    *count = p->cseg * p->world;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_factor_offsets(sage_ba_problem *p, int *offsets, int *cost_offsets, int *owners)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  for (size_t f = 0; f < p->metas.size(); ++f)
+  {
+    if (offsets)
+      offsets[f] = p->metas[f].off;
+    if (cost_offsets)
+      cost_offsets[f] = p->metas[f].cost_off;
+    if (owners)
+      owners[f] = p->metas[f].owner;
+  }
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_solver_info(sage_ba_problem *p, int *num_blocks, int *fill_blocks, int *depth)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  if (num_blocks)
+    *num_blocks = p->bs.nblocks;
+  if (fill_blocks)
+    *fill_blocks = (int)p->bs.fill_blocks;
+  if (depth)
+    *depth = p->bs.depth;
   SAGE_PCATCH
 }
 
@@ -1051,15 +1150,82 @@ int sage_ba_problem_set_allreduce(sage_ba_problem *p, sage_ba_allreduce_fn fn, v
   return 0;
 }
 
+int sage_ba_nccl_unique_id(char id[128])
+{
+  const std::string e = nccl_unique_id(id);
+  if (!e.empty())
+    fprintf(stderr, "sage_ba: %s\n", e.c_str());
+  return e.empty() ? 0 : 1;
+}
+
+int sage_ba_comm_create(sage_ba_context *ctx, const char id[128], int rank, int world, sage_ba_comm **out)
+{
+  SAGE_TRY(ctx)
+  SAGE_CHECK(ctx && out && id && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+  SAGE_CUDA(cudaSetDevice(ctx->device));
+  void *c = nullptr;
+  const std::string e = nccl_comm_create(id, rank, world, &c);
+  SAGE_CHECK(e.empty(), e);
+  sage_ba_comm *cm = new sage_ba_comm();
+  cm->nccl = c;
+  cm->rank = rank;
+  cm->world = world;
+  cm->owned = true;
+  *out = cm;
+  SAGE_CATCH
+}
+
+int sage_ba_comm_wrap(void *nccl_comm, int rank, int world, sage_ba_comm **out)
+{
+  if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world)
+    return 1;
+  sage_ba_comm *cm = new sage_ba_comm();
+  cm->nccl = nccl_comm;
+  cm->rank = rank;
+  cm->world = world;
+  cm->owned = false;
+  *out = cm;
+  return 0;
+}
+
+void sage_ba_comm_destroy(sage_ba_comm *c)
+{
+  if (!c)
+    return;
+  if (c->owned)
+    nccl_comm_destroy(c->nccl);
+  delete c;
+}
+
+int sage_ba_problem_set_comm(sage_ba_problem *p, sage_ba_comm *comm)
+{
+  SAGE_PTRY(p)
+  SAGE_CHECK(!comm || (comm->rank == p->rank && comm->world == p->world), "communicator rank / size differ from the problem's shard");
+  p->comm = comm;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_exchange(sage_ba_problem *p, int which)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  if (which == 0)
+    exchange(p, p->fbuf.p, p->fseg);
+  else
+    exchange(p, p->cbuf.p, p->cseg);
+  SAGE_PCATCH
+}
+
 int sage_ba_problem_linearize(sage_ba_problem *p)
 {
   SAGE_PTRY(p)
   problem_build(p);
   cudaStream_t s = ctx__->stream;
-  if (p->world > 1)
-    SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf_count * sizeof(float), s));
+  if (p->world > 1 && !p->comm)
+    SAGE_CUDA(cudaMemsetAsync(p->fbuf.p, 0, p->fbuf_count * sizeof(float), s)); // sum all-reduce: other ranks' slots must be zero
   refresh_factors(p, 0, true);
   run_factors(p, true, p->fbuf.p);
+  p->lin_valid = false;
   SAGE_PCATCH
 }
 
@@ -1070,26 +1236,20 @@ int sage_ba_problem_assemble(sage_ba_problem *p, double *H, double *g, double *c
   cudaStream_t s = ctx__->stream;
   const int n = p->dim();
   ProfScope ps(p, SAGE_BA_PROF_ASSEMBLE);
-  SAGE_CUDA(cudaMemsetAsync(p->Hm.p, 0, sizeof(double) * n * n, s));
-  SAGE_CUDA(cudaMemsetAsync(p->gv.p, 0, sizeof(double) * n, s));
-  if (!p->metas.empty())
-  {
-    assemble_kernel<<<(unsigned)p->metas.size(), 256, 0, s>>>(p->fbuf.p, p->metas_d.p, p->Hm.p, p->gv.p, n, p->K, p->C);
-    ctx__->launches++;
-  }
-  priors_kernel<<<1, 256, 0, s>>>(p->priors_d.p, (int)p->priors.size(), p->state[0][1].p, p->state[0][2].p, p->Hm.p, p->gv.p,
-                                  p->prior_cost.p, n, p->K, p->C, 1);
+  p->bs.assemble(p->fbuf.p, p->metas_d.p, p->priors_d.p, p->state[0][1].p, p->state[0][2].p, s, &ctx__->launches);
+  p->dense_valid = false;
+  priors_kernel<<<1, 256, 0, s>>>(p->priors_d.p, (int)p->priors.size(), p->state[0][1].p, p->state[0][2].p, nullptr, nullptr,
+                                  p->prior_cost.p, n, p->K, p->C, 0);
   total_cost_kernel<<<1, 256, 0, s>>>(p->fbuf.p, p->errpos_d.p, (int)p->metas.size(), p->prior_cost.p, p->total_cost.p);
   ctx__->launches += 2;
   SAGE_CUDA(cudaGetLastError());
-  if (ps.b)
-  {
-    cudaEventRecord(ps.b, s);
-    ps.b = nullptr;
-  }
+  ps.end();
+  p->lin_valid = true;
   if (H || g || cost)
   {
     SAGE_CUDA(cudaMemcpyAsync(p->hcost.p, p->total_cost.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (H || g)
+      ensure_dense(p);
     if (H)
       SAGE_CUDA(cudaMemcpyAsync(H, p->Hm.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, s));
     if (g)
@@ -1106,103 +1266,43 @@ int sage_ba_problem_solve(sage_ba_problem *p, double damp, double *delta)
   SAGE_PTRY(p)
   problem_build(p);
   cudaStream_t s = ctx__->stream;
-  const int n = p->dim(), np = 6 * p->K, nc = n - np;
+  const int n = p->dim(), np = 6 * p->K;
   ProfScope ps(p, SAGE_BA_PROF_SOLVE);
-  double *Hd = p->Hd.p, *gd = p->gd.p, *dl = p->delta.p;
-  if (!p->use_banded && p->solver != 1)
+  double *dl = p->delta.p;
+  SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
+  if (p->solver != 1)
   {
-    // default: Schur complement fused into ONE factorisation (code+scale block ordered first): potrf eliminates H_cc,
-    // leaves S = H_pp - H_pc H_cc^-1 H_cp in the trailing 6K x 6K block and factors it; potrs does the two substitutions.
-    // 32 KF on B200: 0.8 ms instead of 1.36 ms for the explicit potrf / trsm / syrk / potrf sequence below (40 launches).
-    damp_perm_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, Hd, gd, n, np, damp);
-    SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
-    SAGE_CHECK(cusolverDnDpotrf(ctx__->cusolver, CUBLAS_FILL_MODE_LOWER, n, Hd, n, p->work.p, p->potrf_lwork, p->info.p) ==
+    // default: block-sparse Cholesky over keyframes (blocksolve.cu) -- per-keyframe Schur complements, one CTA per block column
+    p->bs.solve(damp, dl, p->info.p, s, &ctx__->launches);
+  }
+  else
+  {
+    // cross-check: the same system densely, Schur complement of the code+scale block fused into ONE cuSOLVER factorisation
+    // (that block is ordered first: potrf eliminates it, leaves S = H_pp - H_pc H_cc^-1 H_cp in the trailing 6K x 6K block and
+    // factors it; potrs does both substitutions)
+    ensure_dense(p);
+    p->Hd.ensure((size_t)n * n);
+    p->gd.ensure(n);
+    if (!p->potrf_lwork)
+    {
+      SAGE_CHECK(cusolverDnDpotrf_bufferSize(ctx__->cusolver, CUBLAS_FILL_MODE_LOWER, n, p->Hd.p, n, &p->potrf_lwork) == CUSOLVER_STATUS_SUCCESS,
+                 "potrf_bufferSize failed");
+      p->work.ensure(std::max(p->potrf_lwork, 4));
+    }
+    damp_perm_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, p->Hd.p, p->gd.p, n, np, damp);
+    SAGE_CHECK(cusolverDnDpotrf(ctx__->cusolver, CUBLAS_FILL_MODE_LOWER, n, p->Hd.p, n, p->work.p, p->potrf_lwork, p->info.p) ==
                    CUSOLVER_STATUS_SUCCESS,
                "potrf(H) failed to launch");
-    SAGE_CHECK(cusolverDnDpotrs(ctx__->cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, Hd, n, gd, n, p->info.p + 1) == CUSOLVER_STATUS_SUCCESS,
+    SAGE_CHECK(cusolverDnDpotrs(ctx__->cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, p->Hd.p, n, p->gd.p, n, p->info.p + 1) == CUSOLVER_STATUS_SUCCESS,
                "potrs failed");
-    unpermute_kernel<<<(n + 255) / 256, 256, 0, s>>>(gd, dl, n, np);
-    retract_kernel<<<(p->K + 63) / 64, 64, 0, s>>>(p->state[0][0].p, p->state[0][1].p, p->state[0][2].p, dl, p->state[1][0].p,
-                                                   p->state[1][1].p, p->state[1][2].p, p->K, p->C);
-    ctx__->launches += 3;
-    SAGE_CUDA(cudaGetLastError());
-    if (ps.b)
-    {
-      cudaEventRecord(ps.b, s);
-      ps.b = nullptr;
-    }
-    if (delta)
-    {
-      SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
-      SAGE_CUDA(cudaMemcpyAsync(p->hinfo.p, p->info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
-      SAGE_CUDA(cudaStreamSynchronize(s));
-      SAGE_CHECK(p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0, "normal equations are not positive definite");
-    }
-    return 0;
-  }
-  damp_kernel<<<(unsigned)(((size_t)n * n + 255) / 256), 256, 0, s>>>(p->Hm.p, p->gv.p, p->fixed_d.p, p->Hd.p, p->gd.p, n, damp);
-  ctx__->launches++;
-  if (p->use_banded)
-  {
-    SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
-    SAGE_CHECK(launch_banded_solve(Hd, gd, p->band.p, dl, p->info.p, n, p->K, p->C, p->bandwidth, s) == 0, "banded solver launch failed");
-    retract_kernel<<<(p->K + 63) / 64, 64, 0, s>>>(p->state[0][0].p, p->state[0][1].p, p->state[0][2].p, dl, p->state[1][0].p,
-                                                   p->state[1][1].p, p->state[1][2].p, p->K, p->C);
+    unpermute_kernel<<<(n + 255) / 256, 256, 0, s>>>(p->gd.p, dl, n, np);
     ctx__->launches += 2;
-    SAGE_CUDA(cudaGetLastError());
-    if (ps.b)
-    {
-      cudaEventRecord(ps.b, s);
-      ps.b = nullptr;
-    }
-    if (delta)
-    {
-      SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
-      SAGE_CUDA(cudaMemcpyAsync(p->hinfo.p, p->info.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
-      SAGE_CUDA(cudaStreamSynchronize(s));
-      SAGE_CHECK(p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0, "normal equations are not positive definite");
-    }
-    return 0;
   }
-  // H is symmetric, so the row-major buffer is also a valid column-major matrix (lda = n).
-  double *A = Hd;                        // pose block            [np x np]
-  double *Bt = Hd + np;                  // rows np.., cols 0..np  [nc x np]  (= H_cp)
-  double *Cc = Hd + (size_t)np * n + np; // code+scale block       [nc x nc]
-  const double one = 1.0, mone = -1.0;
-  cublasHandle_t cb = ctx__->cublas;
-  cusolverDnHandle_t cs = ctx__->cusolver;
-  SAGE_CUDA(cudaMemsetAsync(p->info.p, 0, sizeof(int) * 4, s));
-  // 1. H_cc = L L^T
-  SAGE_CHECK(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, nc, Cc, n, p->work.p, p->potrf_lwork, p->info.p) == CUSOLVER_STATUS_SUCCESS,
-             "potrf(H_cc) failed to launch");
-  // 2. W = L^-1 H_cp  (in place)
-  SAGE_CHECK(cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nc, np, &one, Cc, n, Bt, n) ==
-                 CUBLAS_STATUS_SUCCESS,
-             "trsm failed");
-  // 3. S = H_pp - W^T W
-  SAGE_CHECK(cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, np, nc, &mone, Bt, n, &one, A, n) == CUBLAS_STATUS_SUCCESS, "syrk failed");
-  // 4. y = L^-1 g_c ; rhs_p = g_p - W^T y
-  SAGE_CUDA(cudaMemcpyAsync(dl, gd, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-  SAGE_CHECK(cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, nc, Cc, n, dl + np, 1) == CUBLAS_STATUS_SUCCESS,
-             "trsv failed");
-  SAGE_CHECK(cublasDgemv(cb, CUBLAS_OP_T, nc, np, &mone, Bt, n, dl + np, 1, &one, dl, 1) == CUBLAS_STATUS_SUCCESS, "gemv failed");
-  // 5. S dp = rhs_p
-  SAGE_CHECK(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, np, A, n, p->work.p, p->potrf_lwork, p->info.p + 1) == CUSOLVER_STATUS_SUCCESS,
-             "potrf(S) failed to launch");
-  SAGE_CHECK(cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_LOWER, np, 1, A, n, dl, n, p->info.p + 2) == CUSOLVER_STATUS_SUCCESS, "potrs failed");
-  // 6. dc = L^-T (y - W dp)
-  SAGE_CHECK(cublasDgemv(cb, CUBLAS_OP_N, nc, np, &mone, Bt, n, dl, 1, &one, dl + np, 1) == CUBLAS_STATUS_SUCCESS, "gemv failed");
-  SAGE_CHECK(cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, nc, Cc, n, dl + np, 1) == CUBLAS_STATUS_SUCCESS,
-             "trsv failed");
   retract_kernel<<<(p->K + 63) / 64, 64, 0, s>>>(p->state[0][0].p, p->state[0][1].p, p->state[0][2].p, dl, p->state[1][0].p,
                                                  p->state[1][1].p, p->state[1][2].p, p->K, p->C);
-  ctx__->launches++;
+  ctx__->launches += 1;
   SAGE_CUDA(cudaGetLastError());
-  if (ps.b)
-  {
-    cudaEventRecord(ps.b, s);
-    ps.b = nullptr;
-  }
+  ps.end();
   if (delta)
   {
     SAGE_CUDA(cudaMemcpyAsync(delta, dl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -1218,8 +1318,8 @@ int sage_ba_problem_evaluate(sage_ba_problem *p, int which)
   SAGE_PTRY(p)
   problem_build(p);
   cudaStream_t s = ctx__->stream;
-  if (p->world > 1)
-    SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->metas.size() * 2 * sizeof(float), s));
+  if (p->world > 1 && !p->comm)
+    SAGE_CUDA(cudaMemsetAsync(p->cbuf.p, 0, p->cseg * p->world * sizeof(float), s));
   refresh_factors(p, which ? 1 : 0, false);
   run_factors(p, false, p->cbuf.p);
   SAGE_PCATCH
@@ -1252,6 +1352,7 @@ int sage_ba_problem_accept(sage_ba_problem *p)
     const size_t nfl = q == 0 ? (size_t)p->K * 12 : (q == 1 ? (size_t)p->K * p->C : (size_t)p->K);
     SAGE_CUDA(cudaMemcpyAsync(p->state[0][q].p, p->state[1][q].p, sizeof(float) * nfl, cudaMemcpyDeviceToDevice, s));
   }
+  p->lin_valid = false;
   SAGE_PCATCH
 }
 
@@ -1314,17 +1415,21 @@ int sage_ba_problem_lm_step(sage_ba_problem *p, double *damp, double min_damp, d
   SAGE_CHECK(damp, "null damping");
   problem_build(p);
   cudaStream_t s = ctx__->stream;
-  // everything of the iteration is enqueued before the host looks at anything: linearise, assemble, solve, evaluate the
-  // candidate; ONE synchronisation then delivers both costs (the damping of this step does not depend on them)
-  SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
-  if (p->allreduce && p->world > 1)
-    SAGE_CHECK(p->allreduce(p->fbuf.p, p->fbuf_count, p->allreduce_user) == 0, "all-reduce callback failed");
-  SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, nullptr) == 0, ctx__->err);
+  // everything of the iteration is enqueued before the host looks at anything: linearise, exchange, assemble, solve, evaluate
+  // the candidate, exchange; ONE synchronisation then delivers both costs (the damping of this step does not depend on them).
+  // After a rejected step the state has not moved: the linearisation in the factor buffer is still the current one and is
+  // reused (the reference's own loop does the same, core/system/camera_tracker.cpp:1159) unless the caller asks for the full
+  // iteration every time (bench.py does: BASELINE's metric defines an iteration as including the linearisation).
+  if (!p->lin_valid || p->relinearize_always)
+  {
+    SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
+    exchange(p, p->fbuf.p, p->fseg);
+    SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, nullptr) == 0, ctx__->err);
+  }
   SAGE_CUDA(cudaMemcpyAsync(p->hcost.p, p->total_cost.p, sizeof(double), cudaMemcpyDeviceToHost, s));
   SAGE_CHECK(sage_ba_problem_solve(p, *damp, nullptr) == 0, ctx__->err);
   SAGE_CHECK(sage_ba_problem_evaluate(p, 1) == 0, ctx__->err);
-  if (p->allreduce && p->world > 1)
-    SAGE_CHECK(p->allreduce(p->cbuf.p, p->metas.size() * 2, p->allreduce_user) == 0, "all-reduce callback failed");
+  exchange(p, p->cbuf.p, p->cseg);
   double cand = 0.0;
   SAGE_CHECK(sage_ba_problem_cost(p, 1, &cand) == 0, ctx__->err); // the synchronisation
   const double cur = p->hcost.p[0];
@@ -1352,15 +1457,11 @@ int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_b
   problem_build(p);
   sage_ba_lm_report r;
   memset(&r, 0, sizeof(r));
-  auto reduce = [&](float *buf, size_t count) {
-    if (p->allreduce && p->world > 1)
-      SAGE_CHECK(p->allreduce(buf, count, p->allreduce_user) == 0, "all-reduce callback failed");
-  };
   auto clampd = [&](double d) { return std::min(std::max(opt->min_damp, d), opt->max_damp); };
   double damp = opt->init_damp;
   double cost = 0.0;
   SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
-  reduce(p->fbuf.p, p->fbuf_count);
+  exchange(p, p->fbuf.p, p->fseg);
   SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, &cost) == 0, ctx__->err);
   r.linearizations = 1;
   r.initial_cost = cost;
@@ -1374,7 +1475,7 @@ int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_b
     {
       SAGE_CHECK(sage_ba_problem_solve(p, damp, nullptr) == 0, ctx__->err);
       SAGE_CHECK(sage_ba_problem_evaluate(p, 1) == 0, ctx__->err);
-      reduce(p->cbuf.p, p->metas.size() * 2);
+      exchange(p, p->cbuf.p, p->cseg);
       SAGE_CHECK(sage_ba_problem_cost(p, 1, &cand) == 0, ctx__->err);
       r.evaluations++;
       const bool solved = p->hinfo.p[0] == 0 && p->hinfo.p[1] == 0;
@@ -1401,7 +1502,7 @@ int sage_ba_problem_lm(sage_ba_problem *p, const sage_ba_lm_options *opt, sage_b
     if (prev - cost < opt->min_rel_decrease * prev || it + 1 >= opt->max_iters)
       break;
     SAGE_CHECK(sage_ba_problem_linearize(p) == 0, ctx__->err);
-    reduce(p->fbuf.p, p->fbuf_count);
+    exchange(p, p->fbuf.p, p->fseg);
     SAGE_CHECK(sage_ba_problem_assemble(p, nullptr, nullptr, nullptr) == 0, ctx__->err);
     r.linearizations++;
   }

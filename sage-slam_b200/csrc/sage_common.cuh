@@ -209,10 +209,26 @@ __device__ __forceinline__ TapSet shfl_tapset(const TapSet &t, int src)
   return r;
 }
 
-// 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne)
+// 4-tap weighted sum of one float4 map in the reference's tap order (nw + se + sw + ne).  GENERIC: the pointers may address
+// shared memory (staged windows) or global memory -> generic loads instead of ld.global.nc
+template <bool GENERIC = false>
 __device__ __forceinline__ float4 gather4(const float *pnw, const float *pse, const float *psw, const float *pne, const float *w)
 {
-  const float4 a = ldg4(pnw), b = ldg4(pse), c = ldg4(psw), d = ldg4(pne);
+  float4 a, b, c, d;
+  if constexpr (GENERIC)
+  {
+    a = *reinterpret_cast<const float4 *>(pnw);
+    b = *reinterpret_cast<const float4 *>(pse);
+    c = *reinterpret_cast<const float4 *>(psw);
+    d = *reinterpret_cast<const float4 *>(pne);
+  }
+  else
+  {
+    a = ldg4(pnw);
+    b = ldg4(pse);
+    c = ldg4(psw);
+    d = ldg4(pne);
+  }
   float4 r;
   r.x = a.x * w[0] + b.x * w[1] + c.x * w[2] + d.x * w[3];
   r.y = a.y * w[0] + b.y * w[1] + c.y * w[2] + d.y * w[3];

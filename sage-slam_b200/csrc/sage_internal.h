@@ -141,7 +141,16 @@ struct sage_ba_keyframe
   float *sfeat = nullptr; // [L][N][F] features pre-sampled at the keyframe's own sample points (camera_tracker.cpp:1104-1123)
   float4 *dgm = nullptr;  // [HW] (D, dx, dy, mask) for the geometric factor, state dependent
   float *dscr = nullptr;  // [HW] scratch
+  // the same samples in TILE-MAJOR order (32 x 4 pixel tiles, raster inside a tile) for the staged photometric kernels of the
+  // batched problem; built on first use by sage::ensure_sorted_samples
+  int *loc1d_s = nullptr;
+  float4 *homo_s = nullptr;
+  float *sfeat_s = nullptr;
 };
+namespace sage
+{
+void ensure_sorted_samples(sage_ba_context *ctx, sage_ba_keyframe *kf);
+}
 
 // Every extern "C" entry point wraps its body in SAGE_TRY(ctx) ... SAGE_CATCH: exceptions become a non-zero return code
 // and the message is kept in the context for sage_ba_last_error().

@@ -10,9 +10,9 @@ enum { PH_MAP_JAC = 0, PH_MAP_ERR = 1, PH_TRK_JAC = 2, PH_TRK_ERR = 3 };
 // photometric.cu
 int photo_row_width(int mode, int C);
 int photo_samples_per_cta();
-int photo_ctas_per_sm(int mode, int F, int C);
+int photo_ctas_per_sm(int mode, int F, int C, bool staged = false);
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
-                 float *partE, float *out, int out_stride, int D, cudaStream_t stream);
+                 float *partE, float *out, int out_stride, int D, cudaStream_t stream, bool staged = false);
 
 // geometric.cu
 int geo_row_width(int C);
@@ -31,6 +31,7 @@ int launch_map_match_geom(bool jac, int C, const MapMatchGeomFactor *factors, in
 void launch_relayout_fg(const float *feat, const float *grad, float *fg, int F, long SP, cudaStream_t stream);
 void launch_relayout_basis(const float *jac, long stride_row, long stride_col, float *basis, int HW, int C, cudaStream_t stream);
 void launch_convert_loc(const int64_t *loc64, int *loc32, int N, cudaStream_t stream);
+void launch_permute_samples(const int *perm, const int *loc, const float4 *homo, int *loc_s, float4 *homo_s, int N, cudaStream_t stream);
 void launch_pack_homo(const float *homo3, float4 *homo4, int N, cudaStream_t stream);
 // dgm[HW] = (D, dD/dx, dD/dy, mask) with D = bias + basis . code (unscaled), central differences with replicate padding
 void launch_depth_maps(const float *bias, const float *basis, const float *code_dev, const float *mask, float4 *dgm, float *scratch,
@@ -38,10 +39,5 @@ void launch_depth_maps(const float *bias, const float *basis, const float *code_
 void launch_presample(const float *fg0, const float *bias0, const float *basis0, const int *loc1d, const float4 *homo,
                       const float *code_dev, float scale0, const CamPyr &cam, int F, int C, int N, float *out_dpts, float *out_homo,
                       float *out_feats, cudaStream_t stream);
-// banded.cu
-size_t banded_smem_bytes(int C, int b);
-size_t banded_workspace_doubles(int K, int C, int b);
-int launch_banded_solve(const double *Hd, const double *gd, double *band, double *delta, int *info, int n, int K, int C, int b,
-                        cudaStream_t stream);
 int launch_build_pyramid(const float *feat, const float *mask0, float *fg, float *mask_scratch, const CamPyr &cam, int F, cudaStream_t stream);
 } // namespace sage

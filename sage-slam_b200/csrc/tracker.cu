@@ -14,42 +14,128 @@ using namespace sage;
 namespace
 {
 
-// solve A x = b (n <= 8) by Gaussian elimination with partial pivoting in double; the reference uses
-// Eigen colPivHouseholderQr on the same 6x6 float system (:1182-1183)
+// x = (A).colPivHouseholderQr().solve(b) for n <= 8 in float -- the reference's solve of the damped 6x6 / 7x7 system
+// (core/system/camera_tracker.cpp:1182-1183, :1523-1524: Eigen::ColPivHouseholderQR<Matrix<float,n,n>>).  The algorithm of
+// Eigen 3.3.9 (QR/ColPivHouseholderQR.h computeInPlace / _solve_impl, Householder/Householder.h makeHouseholderInPlace) is
+// followed step by step -- column pivoting on the down-dated column norms with LAPACK's re-computation rule, the "nonzero
+// pivots" cut (exact-zero sense, NOT the fuzzy rank), zeros for the columns beyond it -- so that nearly rank-deficient systems
+// (textureless frames, damping at its floor) give the reference's step, not just well-conditioned ones.  Pinned by
+// tests/golden/host_pins.npz (produced by the reference's expression compiled against its vendored Eigen).
 bool solve_small(const float *A, const float *b, int n, float *x)
 {
-  double M[8][9];
+  float qr[8][8], hc[8], norm_upd[8], norm_dir[8], c[8];
+  int perm[8];
+  const float eps = 1.1920929e-07f, tiny = 1.17549435e-38f;
   for (int r = 0; r < n; ++r)
+    for (int k = 0; k < n; ++k)
+      qr[r][k] = A[r * n + k];
+  float maxnorm = 0.f;
+  for (int k = 0; k < n; ++k)
   {
-    for (int c = 0; c < n; ++c)
-      M[r][c] = A[r * n + c];
-    M[r][n] = b[r];
+    float s = 0.f;
+    for (int r = 0; r < n; ++r)
+      s += qr[r][k] * qr[r][k];
+    norm_dir[k] = norm_upd[k] = std::sqrt(s);
+    maxnorm = std::max(maxnorm, norm_upd[k]);
+    perm[k] = k;
   }
-  for (int c = 0; c < n; ++c)
+  const float threshold_helper = (maxnorm * eps) * (maxnorm * eps) / (float)n;
+  const float downdate_threshold = std::sqrt(eps);
+  int nonzero = n;
+  for (int k = 0; k < n; ++k)
   {
-    int piv = c;
-    for (int r = c + 1; r < n; ++r)
-      if (std::fabs(M[r][c]) > std::fabs(M[piv][c]))
-        piv = r;
-    if (M[piv][c] == 0.0)
-      return false;
-    if (piv != c)
-      for (int k = 0; k <= n; ++k)
-        std::swap(M[piv][k], M[c][k]);
-    for (int r = c + 1; r < n; ++r)
+    int big = k;
+    for (int j = k + 1; j < n; ++j)
+      if (norm_upd[j] > norm_upd[big])
+        big = j;
+    if (nonzero == n && norm_upd[big] * norm_upd[big] < threshold_helper * (float)(n - k))
+      nonzero = k;
+    if (big != k)
     {
-      const double f = M[r][c] / M[c][c];
-      for (int k = c; k <= n; ++k)
-        M[r][k] -= f * M[c][k];
+      for (int r = 0; r < n; ++r)
+        std::swap(qr[r][k], qr[r][big]);
+      std::swap(norm_upd[k], norm_upd[big]);
+      std::swap(norm_dir[k], norm_dir[big]);
+      std::swap(perm[k], perm[big]);
     }
+    // Householder vector of column k (rows k..n-1): essential part stored below the diagonal, beta on it
+    float tail2 = 0.f;
+    for (int r = k + 1; r < n; ++r)
+      tail2 += qr[r][k] * qr[r][k];
+    const float c0 = qr[k][k];
+    float tau, beta;
+    if (tail2 <= tiny)
+    {
+      tau = 0.f;
+      beta = c0;
+      for (int r = k + 1; r < n; ++r)
+        qr[r][k] = 0.f;
+    }
+    else
+    {
+      beta = std::sqrt(c0 * c0 + tail2);
+      if (c0 >= 0.f)
+        beta = -beta;
+      for (int r = k + 1; r < n; ++r)
+        qr[r][k] /= (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    hc[k] = tau;
+    qr[k][k] = beta;
+    for (int j = k + 1; j < n; ++j) // apply H_k to the trailing columns
+    {
+      float tmp = qr[k][j];
+      for (int r = k + 1; r < n; ++r)
+        tmp += qr[r][k] * qr[r][j];
+      qr[k][j] -= tau * tmp;
+      for (int r = k + 1; r < n; ++r)
+        qr[r][j] -= tau * qr[r][k] * tmp;
+    }
+    for (int j = k + 1; j < n; ++j) // norm down-date (LAPACK xGEQPF)
+      if (norm_upd[j] != 0.f)
+      {
+        float t = std::fabs(qr[k][j]) / norm_upd[j];
+        t = (1.f + t) * (1.f - t);
+        t = t < 0.f ? 0.f : t;
+        const float ratio = norm_upd[j] / norm_dir[j];
+        if (t * ratio * ratio <= downdate_threshold)
+        {
+          float s = 0.f;
+          for (int r = k + 1; r < n; ++r)
+            s += qr[r][j] * qr[r][j];
+          norm_dir[j] = norm_upd[j] = std::sqrt(s);
+        }
+        else
+          norm_upd[j] *= std::sqrt(t);
+      }
   }
-  for (int r = n - 1; r >= 0; --r)
+  for (int i = 0; i < n; ++i)
+    x[i] = 0.f;
+  if (nonzero == 0)
+    return true;
+  for (int r = 0; r < n; ++r)
+    c[r] = b[r];
+  for (int k = 0; k < nonzero; ++k) // c = Q^T b = H_{r-1} ... H_0 b
   {
-    double s = M[r][n];
-    for (int k = r + 1; k < n; ++k)
-      s -= M[r][k] * x[k];
-    x[r] = (float)(s / M[r][r]);
+    float tmp = c[k];
+    for (int r = k + 1; r < n; ++r)
+      tmp += qr[r][k] * c[r];
+    c[k] -= hc[k] * tmp;
+    for (int r = k + 1; r < n; ++r)
+      c[r] -= hc[k] * qr[r][k] * tmp;
   }
+  for (int r = nonzero - 1; r >= 0; --r) // R y = c on the leading nonzero x nonzero triangle
+  {
+    float s = c[r];
+    for (int k = r + 1; k < nonzero; ++k)
+      s -= qr[r][k] * c[k];
+    c[r] = s / qr[r][r];
+  }
+  for (int i = 0; i < nonzero; ++i)
+    x[perm[i]] = c[i];
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(x[i]))
+      return false;
   return true;
 }
 
@@ -443,3 +529,30 @@ extern "C" int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe 
     return 1;
   }
 }
+
+extern "C" {
+
+/* The tracker's linear solve, exposed for callers that keep their own LM loop and for the parity tests:
+ * x = (AtA + damp * diag(AtA)).colPivHouseholderQr().solve(Atb), n = 6 | 7, float (camera_tracker.cpp:1182-1183). */
+int sage_ba_tracker_solve(const float *AtA, const float *Atb, int n, float damp, float *x)
+{
+  if (!AtA || !Atb || !x || n < 1 || n > 8)
+    return 1;
+  float damped[64];
+  for (int i = 0; i < n * n; ++i)
+    damped[i] = AtA[i];
+  for (int i = 0; i < n; ++i)
+    damped[i * n + i] = AtA[i * n + i] + damp * AtA[i * n + i];
+  return solve_small(damped, Atb, n, x) ? 0 : 1;
+}
+
+/* se3_exp<float> (core/mapping/mapping_utils.h:316-346) as the tracker's update uses it: R [9] row-major, t [3]. */
+int sage_ba_se3_exp(const float *omega, const float *v, float *R, float *t)
+{
+  if (!omega || !v || !R || !t)
+    return 1;
+  se3_exp_host(omega, v, R, t);
+  return 0;
+}
+
+} // extern "C"

@@ -43,16 +43,149 @@ class Values(dict):
     """gtsam::Values stand-in: {pose_key: (R [3,3], t [3]), code_key: code [C] (double), scale_key: float}."""
 
 
+def _make_jacobi(x, y, z):
+    """JacobiRotation::makeJacobi(x, y, z) (Eigen 3.3.9, Jacobi/Jacobi.h:83-113): (c, s)."""
+    tiny = np.finfo(np.float64).tiny
+    deno = 2.0 * abs(y)
+    if deno < tiny:
+        return 1.0, 0.0
+    tau = (x - z) / deno
+    w = np.sqrt(tau * tau + 1.0)
+    t = 1.0 / (tau + w) if tau > 0 else 1.0 / (tau - w)
+    sign_t = 1.0 if t > 0 else -1.0
+    n = 1.0 / np.sqrt(t * t + 1.0)
+    return n, -sign_t * (y / abs(y)) * abs(t) * n
+
+
+def eigen_jacobi_svd_v(B):
+    """Singular values (descending) and V of a square real matrix exactly as Eigen 3.3.9's JacobiSVD<MatrixXd>(B, ComputeThinV)
+    produces them (SVD/JacobiSVD.h `compute`, misc/RealSvd2x2.h): two-sided Jacobi sweeps over (p, q), q < p, rotations
+    accumulated into V, selection sort by singular value.  The SIGNS of V's columns are the algorithm's, not a convention --
+    and the reference's NearestPsd depends on them (V^T S V is not invariant under column sign flips), which is why numpy's
+    LAPACK SVD cannot stand in for it."""
+    B = np.asarray(B, np.float64)
+    n = B.shape[0]
+    tiny = np.finfo(np.float64).tiny
+    precision = 2.0 * np.finfo(np.float64).eps
+    scale = np.abs(B).max()
+    if scale == 0:
+        scale = 1.0
+    W = B / scale
+    V = np.eye(n)
+    max_diag = np.abs(np.diag(W)).max()
+    finished = False
+    while not finished:
+        finished = True
+        for p in range(1, n):
+            for q in range(p):
+                thr = max(tiny, precision * max_diag)
+                if abs(W[p, q]) > thr or abs(W[q, p]) > thr:
+                    finished = False
+                    m00, m01, m10, m11 = W[p, p], W[p, q], W[q, p], W[q, q]
+                    t, d = m00 + m11, m10 - m01
+                    if abs(d) < tiny:
+                        rs, rc = 0.0, 1.0
+                    else:
+                        u = t / d
+                        tmp = np.sqrt(1.0 + u * u)
+                        rs, rc = 1.0 / tmp, u / tmp
+                    # m.applyOnTheLeft(0, 1, rot1): x' = c x + s y, y' = -s x + c y on the two rows
+                    a00, a01 = rc * m00 + rs * m10, rc * m01 + rs * m11
+                    a11 = -rs * m01 + rc * m11
+                    cr, sr = _make_jacobi(a00, a01, a11)          # j_right
+                    cl, sl = rc * cr + rs * sr, rs * cr - rc * sr  # j_left = rot1 * j_right.transpose()
+                    xp, xq = W[p, :].copy(), W[q, :].copy()        # applyOnTheLeft(p, q, j_left)
+                    W[p, :], W[q, :] = cl * xp + sl * xq, -sl * xp + cl * xq
+                    xp, xq = W[:, p].copy(), W[:, q].copy()        # applyOnTheRight(p, q, j_right): rotation (c, -s) on the columns
+                    W[:, p], W[:, q] = cr * xp - sr * xq, sr * xp + cr * xq
+                    xp, xq = V[:, p].copy(), V[:, q].copy()
+                    V[:, p], V[:, q] = cr * xp - sr * xq, sr * xp + cr * xq
+                    max_diag = max(max_diag, abs(W[p, p]), abs(W[q, q]))
+    sv = np.abs(np.diag(W)) * scale
+    for i in range(n):
+        pos = int(np.argmax(sv[i:]))
+        if sv[i + pos] == 0:
+            break
+        if pos:
+            pos += i
+            sv[[i, pos]] = sv[[pos, i]]
+            V[:, [i, pos]] = V[:, [pos, i]]
+    return sv, V
+
+
+def eigen_ldlt_is_positive(M):
+    """Eigen::LDLT<MatrixXd>(M).isPositive() (Eigen 3.3.9 Cholesky/LDLT.h `unblocked`): pivoted LDL^T of the lower triangle,
+    the sign is read off the pivots as they appear (no tolerance), so a rank-deficient PSD matrix can report `false`."""
+    mat = np.array(M, np.float64)
+    n = mat.shape[0]
+    if n == 0:
+        return True
+    if n == 1:
+        return mat[0, 0] >= 0
+    sign = 0  # 0 zero, +1 positive semi-definite, -1 negative semi-definite, 2 indefinite
+    for k in range(n):
+        b = k + int(np.argmax(np.abs(np.diag(mat)[k:])))
+        if b != k:
+            s = n - b - 1
+            mat[[k, b], :k] = mat[[b, k], :k]
+            if s:
+                mat[b + 1:, [k, b]] = mat[b + 1:, [b, k]]
+            mat[k, k], mat[b, b] = mat[b, b], mat[k, k]
+            for i in range(k + 1, b):
+                mat[i, k], mat[b, i] = mat[b, i], mat[i, k]
+        rs = n - k - 1
+        if k > 0:
+            temp = np.diag(mat)[:k] * mat[k, :k]
+            mat[k, k] -= mat[k, :k] @ temp
+            if rs > 0:
+                mat[k + 1:, k] -= mat[k + 1:, :k] @ temp
+        akk = mat[k, k]
+        valid = abs(akk) > 0
+        if k == 0 and not valid:
+            return True  # ZeroSign
+        if rs > 0 and valid:
+            mat[k + 1:, k] /= akk
+        if sign == 1:
+            if akk < 0:
+                sign = 2
+        elif sign == -1:
+            if akk > 0:
+                sign = 2
+        elif sign == 0:
+            sign = 1 if akk > 0 else (-1 if akk < 0 else 0)
+    return sign in (1, 0)
+
+
+def eigen_nearest_psd(M):
+    """df::NearestPsd (core/mapping/mapping_utils.h:104-128) with Eigen 3.3.9's JacobiSVD / LDLT behaviour restated, so that the
+    NUMBERS (not only the formula) are the reference's: pinned by tests/golden/host_pins.npz, which the reference's own code
+    compiled against its vendored Eigen produced (oracle/make_golden_host.py)."""
+    M = np.asarray(M, np.float64)
+    B = (M + M.T) / 2
+    sv, V = eigen_jacobi_svd_v(B)
+    H = V.T @ np.diag(sv) @ V  # sic: V^T S V (SURVEY.md quirk 12)
+    A2 = (B + H) / 2
+    A3 = (A2 + A2.T) / 2
+    k, I = 1, np.eye(M.shape[0])
+    while not eigen_ldlt_is_positive(A3):
+        A3 = A3 + I * (-np.linalg.eigvalsh(A3).min() * k + 1e-15)
+        k *= 2
+    return A3
+
+
 def nearest_psd(M, mode="reference"):
-    """NearestPsd (core/mapping/mapping_utils.h:104-128) in fp64."""
+    """NearestPsd (core/mapping/mapping_utils.h:104-128) in fp64.  mode "reference": the reference's numbers, V^T S V quirk and
+    Eigen's sign conventions included (eigen_nearest_psd, pinned by tests/golden/host_pins.npz); "exact": Higham's projection
+    V S V^T; "none": pass-through."""
     M = np.asarray(M, dtype=np.float64)
     if mode == "none":
         return M
+    if mode == "reference":
+        return eigen_nearest_psd(M)
     B = (M + M.T) / 2
     _, s, Vt = np.linalg.svd(B)
     V = Vt.T
-    Hm = (V.T @ np.diag(s) @ V) if mode == "reference" else (V @ np.diag(s) @ V.T)
-    A2 = (B + Hm) / 2
+    A2 = (B + V @ np.diag(s) @ V.T) / 2
     A3 = (A2 + A2.T) / 2
     k, I = 1, np.eye(M.shape[0])
     while True:

@@ -1,12 +1,14 @@
 """Batched local bundle adjustment over the C ABI's problem object, plus the multi-GPU plumbing.
 
-One process per GPU.  Factors (ordered keyframe pairs) are sharded round-robin by global factor index
-(`shard_factors`); every rank linearises its shard into the packed per-factor buffer
-[AtA | Atb | error | inliers]*, the buffer is all-reduced (sum; a factor's slot is non-zero on exactly
-one rank, so the reduced bits do not depend on the world size), and every rank assembles and solves the
-same normal equations redundantly (the Schur complement needs the fully summed
-code block).  The collective is torch.distributed (NCCL on GPUs, gloo in the CPU tests); the LM loop is
-the C++ one (sage_ba_problem_lm) calling back into `_allreduce` on the context's stream.
+One process per GPU.  The ordered pair (i -> j) belongs to the rank that owns keyframe i, keyframes are owned in
+contiguous ranges (`shard_owner`, the rule of sage_ba_shard_owner): a keyframe's maps are then read by one GPU for all of
+its pairs, and a rank uploads only the keyframes its factors touch (`needed_keyframes`).  Every rank linearises its factors
+into ITS segment of the packed per-factor buffer [AtA | Atb | error | inliers]*, one in-place all-gather completes the buffer
+everywhere, and every rank assembles (fixed order) and solves (block Cholesky over keyframes) the same normal equations --
+the elimination is a 32-step dependency chain over the band of the covisibility graph, cheaper to repeat than to distribute
+(DESIGN.md section 6).  The collective is issued by the library itself on the context's stream (NCCL bound at run time,
+`LocalBA.enable_nccl`); torch.distributed only distributes the 128-byte communicator id.  A callback-based sum all-reduce
+(`enable_allreduce`) remains for hosts without NCCL and for the gloo CPU tests.
 """
 import ctypes as C
 
@@ -18,21 +20,44 @@ from .ops import Context, DeviceKeyframe, SageError, _f, _p
 F32 = np.float32
 
 
-def shard_factors(num_factors, rank, world):
-    """Global factor indices owned by `rank`: f % world == rank (same rule as sage_ba_problem_set_shard)."""
-    return [f for f in range(num_factors) if f % world == rank]
+def shard_owner(num_keyframes, world, kf):
+    """Rank that owns keyframe `kf` (and every ordered pair kf -> j): contiguous ranges, kf * world // K
+    (the rule of sage_ba_shard_owner)."""
+    if world <= 1:
+        return 0
+    return min(max(kf * world // num_keyframes, 0), world - 1)
 
 
-def factor_layout(kinds, C_code):
-    """Offsets of each factor's [AtA D*D | Atb D | error | inliers] block in the packed buffer.
-    kinds: sequence of 'photo' | 'geo' | 'reproj'.  Returns (offsets, dims, total)."""
-    offs, dims, off = [], [], 0
-    for k in kinds:
+def shard_factors(factors, num_keyframes, rank, world):
+    """Indices of the factors (kind, i, j) owned by `rank`: owner(i) == rank."""
+    return [f for f, (_, i, _) in enumerate(factors) if shard_owner(num_keyframes, world, i) == rank]
+
+
+def needed_keyframes(pairs, num_keyframes, rank, world):
+    """Keyframes whose device data `rank` needs: hosts and targets of the ordered pairs it owns."""
+    need = set()
+    for i, j in pairs:
+        if shard_owner(num_keyframes, world, i) == rank:
+            need.update((i, j))
+    return need
+
+
+def factor_layout(kinds, C_code, owners=None, world=1):
+    """Offsets of each factor's [AtA D*D | Atb D | error | inliers] block in the packed buffer: `world` equal segments,
+    segment r holding rank r's factors in order of addition, segments padded to a multiple of 32 floats (world = 1: the
+    order of addition).  kinds: sequence of 'photo' | 'geo' | 'reproj'.  Returns (offsets, dims, total)."""
+    owners = [0] * len(kinds) if owners is None else list(owners)
+    used = [0] * world
+    local, dims = [], []
+    for k, o in zip(kinds, owners):
         D = 14 + 2 * C_code if k == "geo" else 13 + C_code
-        offs.append(off)
+        local.append(used[o])
         dims.append(D)
-        off += D * D + D + 2
-    return offs, dims, off
+        used[o] += D * D + D + 2
+    if world == 1:
+        return local, dims, used[0]
+    seg = (max(max(used), 4) + 31) // 32 * 32
+    return [o * seg + l for o, l in zip(owners, local)], dims, seg * world
 
 
 def pack_factor(buf, off, D, AtA, Atb, error, inliers):
@@ -61,12 +86,12 @@ def variable_index(kind, i, j, c, K, C_code):
     return cb_i + C_code
 
 
-def assemble_dense(buf, factors, K, C_code):
-    """Host restatement of the device assembly: dense fp64 (H, g, cost) from a packed factor buffer.
+def assemble_dense(buf, factors, K, C_code, world=1):
+    """Host restatement of the device assembly: dense fp64 (H, g, cost) from a packed factor buffer laid out for `world` ranks.
     factors: list of (kind, i, j).  Used by the gloo tests and as documentation of the layout."""
     n = K * (7 + C_code)
     H, g, cost = np.zeros((n, n)), np.zeros(n), 0.0
-    offs, dims, _ = factor_layout([f[0] for f in factors], C_code)
+    offs, dims, _ = factor_layout([f[0] for f in factors], C_code, [shard_owner(K, world, f[1]) for f in factors], world)
     for (kind, i, j), off, D in zip(factors, offs, dims):
         idx = np.array([variable_index(kind, i, j, c, K, C_code) for c in range(D)])
         A = np.asarray(buf[off:off + D * D], np.float64).reshape(D, D)
@@ -99,20 +124,24 @@ class LocalBA:
     without ISAM2.  State = (pose_wk [K] as (R,t), code [K,C], dpt_scale [K])."""
 
     def __init__(self, ctx: Context, keyframes, rank=0, world=1, solver="auto"):
+        """keyframes: DeviceKeyframe per keyframe; entries this rank's factors never touch may be None (see needed_keyframes)."""
         self.ctx = ctx
         self.kfs = list(keyframes)
         self.K = len(self.kfs)
-        self.C = self.kfs[0].C
-        self.L = self.kfs[0].L
-        arr = (C.c_void_p * self.K)(*[k.h for k in self.kfs])
+        any_kf = next(k for k in self.kfs if k is not None)
+        self.C = any_kf.C
+        self.L = any_kf.L
+        self._shape = (any_kf.H, any_kf.W)
+        arr = (C.c_void_p * self.K)(*[(k.h if k is not None else None) for k in self.kfs])
         h = C.c_void_p()
         ctx.check(ctx.lib.sage_ba_problem_create(ctx.h, self.K, arr, C.byref(h)))
         self.h = h
         self.rank, self.world = rank, world
         ctx.check(ctx.lib.sage_ba_problem_set_shard(self.h, rank, world))
-        ctx.check(ctx.lib.sage_ba_problem_set_solver(self.h, {"auto": 0, "schur": 1, "banded": 2}[solver]))
+        ctx.check(ctx.lib.sage_ba_problem_set_solver(self.h, {"auto": 0, "block": 0, "schur": 1, "dense": 1, "banded": 2, "natural": 2}[solver]))
         self.factors = []
         self._cb = None
+        self._comm = None
         self._views = {}
 
     # -- factor graph ------------------------------------------------------------------------------
@@ -160,7 +189,7 @@ class LocalBA:
         P = np.zeros((self.K, 12), F32)
         c = np.zeros((self.K, self.C), F32)
         s = np.zeros((self.K,), F32)
-        HW = self.kfs[0].H * self.kfs[0].W
+        HW = self._shape[0] * self._shape[1]
         d = np.zeros((self.K, HW), F32) if want_depth else None
         self.ctx.check(self.ctx.lib.sage_ba_problem_update_map(self.h, _p(P), _p(c), _p(s), _p(d), capi.HOST))
         return [(P[k, :9].reshape(3, 3).copy(), P[k, 9:].copy()) for k in range(self.K)], c, s, d
@@ -185,13 +214,73 @@ class LocalBA:
                                   torch.as_tensor(_DevPtr(ptr.value, cnt.value), device=torch.device("cuda", self.ctx.device)))
         return self._views[which]
 
+    def enable_nccl(self):
+        """Create the library's own NCCL communicator (one per LocalBA) and hand it to the problem: from then on the exchange of
+        the factor / cost buffers is issued from C++ on the context's stream.  torch.distributed only carries the 128-byte id."""
+        import torch
+        import torch.distributed as dist
+
+        if self.world <= 1 or self._comm is not None:
+            return
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            if self.ctx.lib.sage_ba_nccl_unique_id(buf) != 0:
+                raise SageError("sage_ba_nccl_unique_id failed (libnccl not loadable)")
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        dev = torch.device("cuda", self.ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        ident = ident.to(dev)
+        dist.broadcast(ident, 0)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.sage_ba_comm_create(self.ctx.h, raw, self.rank, self.world, C.byref(h)))
+        self._comm = h
+        self.ctx.check(self.ctx.lib.sage_ba_problem_set_comm(self.h, h))
+
+    def exchange(self, which="factor"):
+        """Complete the factor / cost buffer on every rank (library collective or callback; no-op for world = 1)."""
+        self.ctx.check(self.ctx.lib.sage_ba_problem_exchange(self.h, 0 if which == "factor" else 1))
+
+    def factor_offsets(self):
+        """(offsets, cost_offsets, owners) per factor in order of addition, as laid out by the library."""
+        n = len(self.factors)
+        a, b, c = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+        self.ctx.check(self.ctx.lib.sage_ba_problem_factor_offsets(self.h, a, b, c))
+        return list(a), list(b), list(c)
+
+    def solver_info(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.sage_ba_problem_solver_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"blocks": a.value, "fill_blocks": b.value, "depth": c.value}
+
+    def deterministic(self, on=True):
+        """CTA decomposition independent of the rank count: bit-identical LM trajectories for every number of GPUs."""
+        self.ctx.check(self.ctx.lib.sage_ba_problem_set_deterministic(self.h, int(on)))
+
+    def relinearize_always(self, always=True):
+        self.ctx.check(self.ctx.lib.sage_ba_problem_set_relinearize_always(self.h, int(always)))
+
+    def _ensure_collective(self):
+        if self.world > 1 and self._comm is None and self._cb is None:
+            import torch.distributed as dist
+
+            if dist.is_initialized() and dist.get_backend() == "nccl":
+                self.enable_nccl()
+            else:
+                self.enable_allreduce()
+
     def enable_allreduce(self):
         """Install the all-reduce callback the C++ LM loop calls once per linearisation and once per trial."""
         views = {self._buffer_view(w)[0]: self._buffer_view(w)[2] for w in ("factor", "cost")}
 
+        import torch
+
+        ext = torch.cuda.ExternalStream(self.ctx.stream_handle, device=torch.device("cuda", self.ctx.device))
+
         def cb(ptr, count, user):
             try:
-                allreduce_sum(views[ptr][:count])
+                with torch.cuda.stream(ext):  # the collective must be ordered with the library's kernels on the context's stream
+                    allreduce_sum(views[ptr][:count])
                 return 0
             except Exception as e:  # pragma: no cover
                 print("all-reduce callback failed:", e)
@@ -204,7 +293,8 @@ class LocalBA:
     def linearize(self, reduce=True):
         self.ctx.check(self.ctx.lib.sage_ba_problem_linearize(self.h))
         if reduce and self.world > 1:
-            allreduce_sum(self._buffer_view("factor")[2])
+            self._ensure_collective()
+            self.exchange("factor")
 
     def assemble(self, want_matrix=False):
         cost = C.c_double(0)
@@ -226,7 +316,8 @@ class LocalBA:
     def evaluate(self, candidate=True, reduce=True):
         self.ctx.check(self.ctx.lib.sage_ba_problem_evaluate(self.h, int(candidate)))
         if reduce and self.world > 1:
-            allreduce_sum(self._buffer_view("cost")[2])
+            self._ensure_collective()
+            self.exchange("cost")
         cost = C.c_double(0)
         self.ctx.check(self.ctx.lib.sage_ba_problem_cost(self.h, int(candidate), C.byref(cost)))
         return cost.value
@@ -244,8 +335,7 @@ class LocalBA:
         opt = capi.LMOptions(max_iters, init_damp, min_damp, max_damp, damp_dec_factor, damp_inc_factor, min_rel_decrease,
                              max_trials)
         rep = capi.LMReport()
-        if self.world > 1 and self._cb is None:
-            self.enable_allreduce()
+        self._ensure_collective()
         self.ctx.check(self.ctx.lib.sage_ba_problem_lm(self.h, C.byref(opt), C.byref(rep)))
         return {k: getattr(rep, k) for k, _ in capi.LMReport._fields_}
 
@@ -253,8 +343,7 @@ class LocalBA:
         """One LM iteration (linearise, assemble, solve, evaluate the candidate, accept / reject) with a single host
         synchronisation.  Returns (cost, candidate_cost, accepted, new_damp)."""
         d, c0, c1, acc = C.c_double(damp), C.c_double(0), C.c_double(0), C.c_int(0)
-        if self.world > 1 and self._cb is None:
-            self.enable_allreduce()
+        self._ensure_collective()
         self.ctx.check(self.ctx.lib.sage_ba_problem_lm_step(self.h, C.byref(d), min_damp, max_damp, damp_dec_factor, damp_inc_factor,
                                                             C.byref(c0), C.byref(c1), C.byref(acc)))
         return c0.value, c1.value, bool(acc.value), d.value
@@ -278,6 +367,9 @@ class LocalBA:
         if self.h:
             self.ctx.lib.sage_ba_problem_destroy(self.h)
             self.h = None
+        if self._comm is not None:
+            self.ctx.lib.sage_ba_comm_destroy(self._comm)
+            self._comm = None
 
     def __del__(self):
         try:

@@ -50,6 +50,11 @@ class Context:
     def launch_count(self):
         return int(self.lib.sage_ba_launch_count(self.h))
 
+    @property
+    def stream_handle(self):
+        """cudaStream_t (as int) every call of this context is enqueued on."""
+        return int(self.lib.sage_ba_stream(self.h) or 0)
+
     def close(self):
         if self.h:
             self.lib.sage_ba_destroy(self.h)

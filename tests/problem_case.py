@@ -46,9 +46,11 @@ def oracle_factor(kfs, factor, dtype=np.float32):
                                     homo, uv, a["scale0"], a["cam"], a["eps"], 0.03 * PRM["W"] ** 2, 0.1, dtype=dtype)
 
 
-def oracle_buffer(kfs, factors, owned=None):
-    """Packed fp32 factor buffer with only the `owned` factor indices filled (others zero), like one rank's shard."""
-    offs, dims, total = local_ba.factor_layout([f[0] for f in factors], PRM["C"])
+def oracle_buffer(kfs, factors, owned=None, world=1):
+    """Packed fp32 factor buffer (laid out for `world` ranks) with only the `owned` factor indices filled (others zero), like
+    one rank's shard before the exchange."""
+    owners = [local_ba.shard_owner(len(kfs), world, f[1]) for f in factors]
+    offs, dims, total = local_ba.factor_layout([f[0] for f in factors], PRM["C"], owners, world)
     buf = np.zeros(total, np.float32)
     for f, (fac, off, D) in enumerate(zip(factors, offs, dims)):
         if owned is not None and f not in owned:

@@ -1,5 +1,5 @@
-"""CPU, world_size 2, gloo: the multi-GPU host logic -- round-robin factor sharding, the packed factor buffer,
-the sum all-reduce and the redundant dense assembly -- with the CPU oracle standing in for the kernels."""
+"""CPU, world_size 2 and 4, gloo: the multi-GPU host logic -- keyframe-owner sharding, the segmented packed factor buffer,
+the exchange and the redundant assembly -- with the CPU oracle standing in for the kernels."""
 import os
 import socket
 
@@ -24,58 +24,75 @@ def _free_port():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    kfs, pairs, factors = pc.build(3)
-    owned = local_ba.shard_factors(len(factors), rank, world)
-    buf = torch.from_numpy(pc.oracle_buffer(kfs, factors, owned=set(owned)))
-    local_ba.allreduce_sum(buf)
-    H, g, cost = local_ba.assemble_dense(buf.numpy(), factors, len(kfs), pc.PRM["C"])
-    np.savez(os.path.join(out, f"rank{rank}.npz"), buf=buf.numpy(), H=H, g=g, cost=cost, owned=np.array(owned))
+    kfs, pairs, factors = pc.build(4)
+    K = len(kfs)
+    owned = local_ba.shard_factors(factors, K, rank, world)
+    need = local_ba.needed_keyframes(pairs, K, rank, world)
+    # a rank only ever reads the keyframes its own pairs touch
+    for f in owned:
+        assert factors[f][1] in need and factors[f][2] in need
+    buf = torch.from_numpy(pc.oracle_buffer(kfs, factors, owned=set(owned), world=world))
+    local_ba.allreduce_sum(buf)  # every slot is non-zero on exactly one rank: the sum is the gather
+    H, g, cost = local_ba.assemble_dense(buf.numpy(), factors, K, pc.PRM["C"], world=world)
+    np.savez(os.path.join(out, f"rank{rank}.npz"), buf=buf.numpy(), H=H, g=g, cost=cost, owned=np.array(owned), need=np.array(sorted(need)))
     dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_reproduces_single_rank(tmp_path):
-    world = 2
+def _check(world, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    kfs, pairs, factors = pc.build(3)
-    ref = pc.oracle_buffer(kfs, factors)
-    Href, gref, cref = local_ba.assemble_dense(ref, factors, len(kfs), pc.PRM["C"])
+    kfs, pairs, factors = pc.build(4)
+    K = len(kfs)
+    ref1 = pc.oracle_buffer(kfs, factors)  # single-rank layout
+    Href, gref, cref = local_ba.assemble_dense(ref1, factors, K, pc.PRM["C"])
+    refw = pc.oracle_buffer(kfs, factors, world=world)  # the same factors in the `world`-segment layout
     r = [dict(np.load(os.path.join(tmp_path, f"rank{k}.npz"))) for k in range(world)]
-    assert sorted(list(r[0]["owned"]) + list(r[1]["owned"])) == list(range(len(factors)))
+    assert sorted(f for x in r for f in x["owned"]) == list(range(len(factors)))
     for k in range(world):
-        np.testing.assert_array_equal(r[k]["buf"], ref)  # x + 0 == x: bit-identical to the single-rank buffer
-        np.testing.assert_array_equal(r[k]["H"], Href)
+        np.testing.assert_array_equal(r[k]["buf"], refw)  # x + 0 == x: bit-identical to one rank computing everything
+        np.testing.assert_array_equal(r[k]["H"], Href)  # and the assembled system does not depend on the world size
         np.testing.assert_array_equal(r[k]["g"], gref)
         assert float(r[k]["cost"]) == cref
 
 
+def test_two_rank_exchange_reproduces_single_rank(tmp_path):
+    _check(2, tmp_path)
+
+
+def test_four_rank_exchange_reproduces_single_rank(tmp_path):
+    _check(4, tmp_path)
+
+
 def test_sharding_is_a_partition_for_every_world_size():
-    """f % world == rank: every factor has exactly one owner, loads differ by at most one, for 1/2/3/4/8 ranks and the bench's
-    540 factors (180 pairs x 3 kinds) as well as awkward counts."""
-    for n in (540, 1, 7, 23):
+    """owner(i) = i * world // K: every factor has exactly one owner, keyframes are owned in contiguous ranges, a rank needs
+    only its own keyframes plus the band around them -- for the bench graph (32 keyframes, 3 back-connections, 180 ordered
+    pairs x 3 kinds) and awkward sizes."""
+    import sage_slam_b200 as sage
+
+    for K, back in ((32, 3), (5, 2), (7, 6), (3, 1)):
+        pairs = [(k, j) for k in range(K) for j in range(max(0, k - back), k)]
+        pairs = [p for (a, b) in pairs for p in ((a, b), (b, a))]
+        factors = [(kind, i, j) for kind in ("photo", "geo", "reproj") for (i, j) in pairs]
         for world in (1, 2, 3, 4, 8):
-            owned = [local_ba.shard_factors(n, r, world) for r in range(world)]
-            assert sorted(f for o in owned for f in o) == list(range(n))
-            sizes = [len(o) for o in owned]
-            assert max(sizes) - min(sizes) <= 1
-    # the packed layout the all-reduce carries: one [AtA | Atb | error | inliers] block per factor, geometric blocks wider
+            owned = [local_ba.shard_factors(factors, K, r, world) for r in range(world)]
+            assert sorted(f for o in owned for f in o) == list(range(len(factors)))
+            owners = [local_ba.shard_owner(K, world, k) for k in range(K)]
+            assert owners == sorted(owners) and owners[0] == 0 and owners[-1] == min(world, K) - 1 or K < world
+            for r in range(world):
+                need = local_ba.needed_keyframes(pairs, K, r, world)
+                mine = [k for k in range(K) if owners[k] == r]
+                if mine:
+                    assert need <= set(range(max(0, mine[0] - back), min(K, mine[-1] + back + 1)))
+    # K = 32 on 8 ranks: 4 keyframes each, at most 4 + 2 * 3 keyframes resident per rank instead of 32
+    pairs = [p for k in range(32) for j in range(max(0, k - 3), k) for p in ((k, j), (j, k))]
+    assert max(len(local_ba.needed_keyframes(pairs, 32, r, 8)) for r in range(8)) == 10
+    # the C library uses the same rule
+    lib = sage.capi.load()
+    for K, world in ((32, 8), (5, 3), (7, 2), (3, 4)):
+        assert [lib.sage_ba_shard_owner(K, world, k) for k in range(K)] == [local_ba.shard_owner(K, world, k) for k in range(K)]
+    # the packed layout: one [AtA | Atb | error | inliers] block per factor, geometric blocks wider; world > 1: equal segments
     offs, dims, total = local_ba.factor_layout(["photo", "geo", "reproj"], 32)
     assert dims == [45, 78, 45] and offs == [0, 45 * 45 + 45 + 2, 45 * 45 + 45 + 2 + 78 * 78 + 78 + 2]
     assert total == 2 * (45 * 45 + 47) + 78 * 78 + 80
-
-
-def _worker4(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    kfs, pairs, factors = pc.build(3)
-    owned = set(local_ba.shard_factors(len(factors), rank, world))
-    buf = torch.from_numpy(pc.oracle_buffer(kfs, factors, owned=owned))
-    local_ba.allreduce_sum(buf)
-    if rank == 0:
-        np.save(os.path.join(out, "buf4.npy"), buf.numpy())
-    dist.destroy_process_group()
-
-
-def test_four_rank_allreduce_reproduces_single_rank(tmp_path):
-    mp.spawn(_worker4, args=(4, _free_port(), str(tmp_path)), nprocs=4, join=True)
-    kfs, pairs, factors = pc.build(3)
-    np.testing.assert_array_equal(np.load(os.path.join(tmp_path, "buf4.npy")), pc.oracle_buffer(kfs, factors))
+    offs, dims, total = local_ba.factor_layout(["photo", "geo", "reproj"], 32, owners=[1, 0, 1], world=2)
+    seg = (max(2 * (45 * 45 + 47), 78 * 78 + 80) + 31) // 32 * 32
+    assert offs == [seg, 0, seg + 45 * 45 + 47] and total == 2 * seg

@@ -121,7 +121,8 @@ def test_factor_packing_and_dense_assembly_layout():
     # geometric 1->2 couples code_1 with code_2
     c1, c2 = 6 * K + 1 * (C + 1), 6 * K + 2 * (C + 1)
     np.testing.assert_allclose(H[c1:c1 + C, c2:c2 + C], mats[1][0][12:12 + C, 12 + C:12 + 2 * C], rtol=1e-6)
-    assert local_ba.shard_factors(7, 1, 3) == [1, 4]
+    # keyframe-owner sharding: with 3 keyframes on 3 ranks every rank owns the pairs hosted by its keyframe
+    assert [local_ba.shard_factors(factors, K, r, 3) for r in range(3)] == [[0], [1], [2]]
 
 
 def test_factor_partition_and_nearest_psd_match_oracle():
@@ -157,10 +158,16 @@ def test_bench_accounting_matches_the_survey():
     spec = importlib.util.spec_from_file_location("sage_bench", os.path.join(helpers.ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    photo, photo_err, geo = bench.algorithmic_bytes(bench.WORKLOAD)
+    wl = bench.CONFIGS[3]
+    photo, photo_err, geo = bench.algorithmic_bytes(wl)
     assert abs(photo / 1e6 - 68.2) < 0.1 and abs(photo_err / 1e6 - 40.3) < 0.1 and abs(geo / 1e6 - 23.9) < 0.1
-    wl = bench.WORKLOAD
     assert (wl["num_kf"], wl["W"], wl["H"], wl["F"], wl["C"], wl["L"]) == (32, 320, 256, 32, 32, 4)  # BASELINE configs[3]
+    # the other BASELINE configurations bench.py can run: configs[0] (2 KF, 128x96, F16, C8, photometric only: 4.87 MB per pair),
+    # configs[2] (16 KF, full covisibility), configs[4] (256 KF, average degree 8)
+    c0, c2, c4 = bench.CONFIGS[0], bench.CONFIGS[2], bench.CONFIGS[4]
+    assert (c0["num_kf"], c0["W"], c0["H"], c0["F"], c0["C"], c0["kinds"]) == (2, 128, 96, 16, 8, ("photo",))
+    assert abs(bench.algorithmic_bytes(c0)[0] / 1e6 - 4.87) < 0.02
+    assert (c2["num_kf"], c2["graph"]) == (16, "full") and (c4["num_kf"], c4["graph"]) == (256, "sparse8")
     s = bench.ClockSampler(0)
     s.start()
     s.mark_begin()
