@@ -364,6 +364,10 @@ int sage_ba_problem_factor_offsets(sage_ba_problem *p, int *offsets, int *cost_o
 /* symbolic factorisation of solver 0 / 2: blocks of the factor (diagonal + sub-diagonal incl. fill), fill blocks, and the
  * longest dependency chain of block columns (the critical path of the elimination) */
 int sage_ba_problem_solver_info(sage_ba_problem *p, int *num_blocks, int *fill_blocks, int *depth);
+/* tuning aid (environment SAGE_BA_SOLVER_TRACE=1 at solve time): per block column, in elimination order, the %globaltimer
+ * stamps (ns) [start, column loaded, updates done, diagonal factored, panel solved, published, ns waiting on flags, #dependencies];
+ * out [K][8], positions_to_keyframes [K] (may be NULL) */
+int sage_ba_problem_solver_trace(sage_ba_problem *p, long long *out, int *positions_to_keyframes);
 /* packed per-factor [error | inliers] buffer of the last cost evaluation (DEVICE, fp32) */
 int sage_ba_problem_cost_buffer(sage_ba_problem *p, float **device_ptr, size_t *count);
 

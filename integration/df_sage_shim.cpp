@@ -15,7 +15,9 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/torch.h>
 
+#include <algorithm>
 #include <array>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -76,6 +78,47 @@ std::vector<int32_t> hosti(const at::Tensor &t)
   const at::Tensor c = t.to(at::kCPU, at::kInt).contiguous();
   return std::vector<int32_t>(c.data_ptr<int32_t>(), c.data_ptr<int32_t>() + c.numel());
 }
+// Several small DEVICE tensors in ONE device-to-host transfer (one concatenation kernel + one blocking copy instead of one of
+// each per tensor): the reference's callers hand over 6-8 tensors of 3-32 floats per call (gtsam/photometric_factor.cpp:264-311).
+struct HostPack
+{
+  std::vector<float> buf;
+  std::vector<size_t> off;
+  const float *operator[](size_t i) const { return buf.data() + off[i]; }
+  size_t count(size_t i) const { return off[i + 1] - off[i]; }
+};
+HostPack hostpack(std::initializer_list<at::Tensor> ts)
+{
+  HostPack h;
+  std::vector<at::Tensor> flat;
+  size_t total = 0;
+  h.off.push_back(0);
+  bool all_cuda = true;
+  for (const at::Tensor &t : ts)
+  {
+    all_cuda = all_cuda && t.is_cuda();
+    total += (size_t)t.numel();
+    h.off.push_back(total);
+  }
+  h.buf.resize(total);
+  if (all_cuda && ts.size() > 1)
+  {
+    for (const at::Tensor &t : ts)
+      flat.push_back(t.to(at::kFloat).reshape({-1}));
+    const at::Tensor c = torch::cat(flat).to(at::kCPU);
+    std::copy(c.data_ptr<float>(), c.data_ptr<float>() + total, h.buf.begin());
+  }
+  else
+  {
+    size_t i = 0;
+    for (const at::Tensor &t : ts)
+    {
+      const at::Tensor c = t.to(at::kCPU, at::kFloat).contiguous();
+      std::copy(c.data_ptr<float>(), c.data_ptr<float>() + c.numel(), h.buf.begin() + h.off[i++]);
+    }
+  }
+  return h;
+}
 
 struct KfDeleter
 {
@@ -83,11 +126,61 @@ struct KfDeleter
   void operator()(sage_ba_keyframe *k) const { sage_ba_keyframe_destroy(c, k); }
 };
 using KfPtr = std::shared_ptr<sage_ba_keyframe>;
-using KfKey = std::tuple<const void *, const void *, const void *, const void *, const void *, long, long, long, long>;
+// identity of a cached keyframe: the frame's persistent tensors (data pointers) + shape.  The gradient pyramid is NOT part of
+// it (an entry built without gradients is upgraded in place when a caller needs them: one entry per frame and role, whichever
+// operator sees the frame first), and the code size only counts when the view carries a depth basis (the tracker and the
+// photometric operators see frame 1 without one).
+using KfKey = std::tuple<const void *, const void *, const void *, const void *, long, long, long, long, long, long>;
+using WeakStorage = c10::weak_intrusive_ptr<c10::StorageImpl>;
+struct KfEntry
+{
+  KfPtr kf;
+  bool has_grad = false;
+  // the caller's tensors by WEAK reference to their storage: the cache pins no memory, an entry is valid exactly as long as the
+  // storage it was built from is alive, and an address the allocator hands out again can never alias a stale entry (the storage
+  // object differs).  (Strong references would also defeat the liveness test under a Python host, where a tensor once seen by
+  // Python keeps use_count() == 2 for as long as any C++ handle exists.)
+  std::vector<WeakStorage> src;
+  std::vector<const void *> src_id;
+  uint64_t last_use = 0;
+};
 // Heap objects that are never destroyed: at process exit torch and the CUDA context may already be gone.
-std::map<KfKey, KfPtr> &g_cache = *new std::map<KfKey, KfPtr>();
-std::vector<at::Tensor> &g_keep = *new std::vector<at::Tensor>(); // source tensors stay alive, so a pointer is never reused
+std::map<KfKey, KfEntry> &g_cache = *new std::map<KfKey, KfEntry>();
+uint64_t g_tick = 0;
 std::mutex g_mutex;
+
+size_t cache_cap()
+{
+  static const size_t cap = [] {
+    const char *e = getenv("SAGE_SHIM_CACHE_MAX");
+    return e ? (size_t)std::max(4, atoi(e)) : (size_t)128;
+  }();
+  return cap;
+}
+
+// Drop the entries whose source tensors nobody but the cache references any more (the frame was released, or the tensor was a
+// per-call temporary), then the least recently used ones beyond the cap.  Called with g_mutex held, on every cache miss.
+void evict_dead_entries()
+{
+  for (auto it = g_cache.begin(); it != g_cache.end();)
+  {
+    bool dead = false;
+    for (const WeakStorage &w : it->second.src)
+      dead = dead || w.expired();
+    if (dead)
+      it = g_cache.erase(it); // a keyframe still in use by a running call lives on through its shared_ptr
+    else
+      ++it;
+  }
+  while (g_cache.size() >= cache_cap())
+  {
+    auto lru = g_cache.begin();
+    for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+      if (it->second.last_use < lru->second.last_use)
+        lru = it;
+    g_cache.erase(lru);
+  }
+}
 
 struct FrameView
 {
@@ -98,21 +191,47 @@ struct FrameView
 KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int levels, int F, int C, bool key_bias = true)
 {
   auto ptr = [](const at::Tensor &t) -> const void * { return t.defined() ? t.data_ptr() : nullptr; };
-  // identity = the frame's persistent tensors; the sample locations are a frame member too, but callers hand over per-call
-  // casts of them (geometric_factor.cpp:344), so only their count takes part.  key_bias lets a caller key a keyframe whose
-  // bias is state dependent (KF1 of the geometric operators) on its other tensors only.
-  const KfKey key{ptr(v.feat_pyramid), ptr(v.grad_pyramid), key_bias ? ptr(v.bias) : nullptr, ptr(v.jac), ptr(v.mask),
-                  v.homo.defined() ? (long)v.homo.size(0) : 0, (long)cam0.width(), (long)cam0.height(), (long)levels};
+  // the sample locations are a frame member too, but callers hand over per-call casts of them (geometric_factor.cpp:344), so
+  // only their count takes part.  key_bias lets a caller key a keyframe whose bias is state dependent (KF1 of the geometric
+  // operators) on its other tensors only.
+  const KfKey key{ptr(v.feat_pyramid), key_bias ? ptr(v.bias) : nullptr, ptr(v.jac), ptr(v.mask),
+                  v.homo.defined() ? (long)v.homo.size(0) : 0, (long)cam0.width(), (long)cam0.height(), (long)levels,
+                  v.feat_pyramid.defined() ? (long)F : 0, v.jac.defined() ? (long)C : 0};
+  const bool want_grad = v.grad_pyramid.defined();
+  // storages the entry depends on (identity + liveness)
+  std::vector<const void *> ids;
+  std::vector<WeakStorage> weak;
+  for (const at::Tensor *t : {&v.feat_pyramid, &v.jac, &v.mask, key_bias ? &v.bias : nullptr})
+    if (t && t->defined())
+    {
+      ids.push_back(t->storage().unsafeGetStorageImpl());
+      weak.push_back(t->storage().getWeakStorageImpl());
+    }
   std::lock_guard<std::mutex> lock(g_mutex);
   {
     auto it = g_cache.find(key);
     if (it != g_cache.end())
     {
-      if (!key_bias) // same frame, new state: refresh the depth map in place
-        SAGE_OK(sage_ba_keyframe_set_bias(ctx(), it->second.get(), v.bias.to(at::kFloat).contiguous().data_ptr<float>(), SAGE_BA_DEVICE));
-      return it->second;
+      bool same = it->second.src_id == ids;
+      for (const WeakStorage &w : it->second.src)
+        same = same && !w.expired();
+      if (!same)
+      {
+        g_cache.erase(it); // the address was handed out again for other data: not the same frame
+        it = g_cache.end();
+      }
     }
+    if (it != g_cache.end() && (it->second.has_grad || !want_grad))
+    {
+      it->second.last_use = ++g_tick;
+      if (!key_bias) // same frame, new state: refresh the depth map in place
+        SAGE_OK(sage_ba_keyframe_set_bias(ctx(), it->second.kf.get(), v.bias.to(at::kFloat).contiguous().data_ptr<float>(), SAGE_BA_DEVICE));
+      return it->second.kf;
+    }
+    if (it != g_cache.end())
+      g_cache.erase(it); // cached without gradients, needed with: rebuild below (the old copy dies with its last user)
   }
+  evict_dead_entries();
   sage_ba_keyframe_desc d{};
   d.memory = SAGE_BA_DEVICE;
   d.height = (int)cam0.height();
@@ -121,7 +240,7 @@ KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int lev
   d.feat_channels = F;
   d.code_size = C;
   d.camera = {cam0.fx(), cam0.fy(), cam0.u0(), cam0.v0(), cam0.width(), cam0.height()};
-  std::vector<at::Tensor> keep;
+  std::vector<at::Tensor> keep; // contiguous float copies, only needed until sage_ba_keyframe_create returns (it synchronises)
   auto cf = [&](const at::Tensor &t) -> const float * {
     if (!t.defined())
       return nullptr;
@@ -135,7 +254,6 @@ KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int lev
   if (v.jac.defined())
   {
     // the depth basis arrives as a strided [HW, C] view of the network's [C, H, W] output (code_depth_network.cpp:38-39)
-    keep.push_back(v.jac);
     d.dpt_jac_code = v.jac.data_ptr<float>();
     d.jac_stride_row = v.jac.stride(0);
     d.jac_stride_col = v.jac.stride(1);
@@ -154,14 +272,21 @@ KfPtr keyframe(const FrameView &v, const df::PinholeCamera<float> &cam0, int lev
   sage_ba_keyframe *kf = nullptr;
   sage_ba_context *c = ctx();
   SAGE_OK(sage_ba_keyframe_create(c, &d, &kf));
-  KfPtr out(kf, KfDeleter{c});
-  g_cache[key] = out;
-  for (const at::Tensor *t : {&v.feat_pyramid, &v.grad_pyramid, &v.jac, &v.mask})
-    if (t->defined())
-      g_keep.push_back(*t);
-  if (key_bias && v.bias.defined())
-    g_keep.push_back(v.bias);
+  KfEntry e;
+  e.kf = KfPtr(kf, KfDeleter{c});
+  e.has_grad = want_grad;
+  e.last_use = ++g_tick;
+  e.src = std::move(weak);
+  e.src_id = std::move(ids);
+  KfPtr out = e.kf;
+  g_cache[key] = std::move(e);
   return out;
+}
+
+long cache_size_locked()
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return (long)g_cache.size();
 }
 
 at::Tensor to_dev(const float *p, std::vector<int64_t> shape, const at::Tensor &like)
@@ -187,6 +312,9 @@ sage_ba_camera cam_of(const df::PinholeCamera<float> &c) { return {c.fx(), c.fy(
 
 } // namespace
 
+// test hook: number of cached keyframes (tests/test_shim_dropin.py checks that the cache does not grow with released frames)
+extern "C" __attribute__((visibility("default"))) long sage_shim_cache_size() { return cache_size_locked(); }
+
 namespace df
 {
 
@@ -204,9 +332,10 @@ float photometric_error_calculate(const at::Tensor rotation, const at::Tensor tr
                         sampled_locations_homo_0},
                        camera_pyramid[0], L, FS, C);
   KfPtr kf1 = keyframe({feat_map_pyramid_1, {}, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, C);
-  const auto R = hostf(rotation), t = hostf(translation), code = hostf(code_0), w = hostf(weights_tensor);
+  const HostPack h = hostpack({rotation, translation, code_0});
+  const auto w = hostf(weights_tensor); // a CPU tensor in the mapping path (photometric_factor.cpp:31-32)
   float err = 0.f;
-  SAGE_OK(sage_ba_photometric_error(ctx(), kf0.get(), kf1.get(), R.data(), t.data(), code.data(), scale_0, eps, w.data(), &err, nullptr));
+  SAGE_OK(sage_ba_photometric_error(ctx(), kf0.get(), kf1.get(), h[0], h[1], h[2], scale_0, eps, w.data(), &err, nullptr));
   return err;
 }
 
@@ -227,10 +356,10 @@ void photometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &er
   KfPtr kf1 = keyframe({feat_map_pyramid_1, feat_map_grad_pyramid_1, {}, {}, valid_mask_1, {}, {}}, camera_pyramid[0], L, FS, CS);
   constexpr int D = 13 + CS;
   std::vector<float> A(D * D), b(D);
-  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
-             t1 = hostf(translation1), code = hostf(code_0), w = hostf(weights_tensor);
-  SAGE_OK(sage_ba_photometric_jac_error(ctx(), kf0.get(), kf1.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(),
-                                        code.data(), scale_0, eps, w.data(), A.data(), b.data(), &error, nullptr));
+  const HostPack h = hostpack({rotation10, translation10, rotation0, translation0, rotation1, translation1, code_0});
+  const auto w = hostf(weights_tensor);
+  SAGE_OK(sage_ba_photometric_jac_error(ctx(), kf0.get(), kf1.get(), h[0], h[1], h[2], h[3], h[4], h[5], h[6], scale_0, eps, w.data(),
+                                        A.data(), b.data(), &error, nullptr));
   AtA = to_dev(A.data(), {D, D}, rotation10);
   Atb = to_dev(b.data(), {D, 1}, rotation10);
 }
@@ -342,12 +471,10 @@ void geometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &erro
   KfPtr kf1 = keyframe({{}, {}, unscaled, basis1, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*key_bias=*/false);
   constexpr int D = 14 + 2 * CS;
   std::vector<float> A(D * D), b(D);
-  const auto R10 = hostf(rotation10), t10 = hostf(translation10), R0 = hostf(rotation0), t0 = hostf(translation0), R1 = hostf(rotation1),
-             t1 = hostf(translation1), code = hostf(code_0);
+  const HostPack h = hostpack({rotation10, translation10, rotation0, translation0, rotation1, translation1, code_0});
   const std::vector<float> code1(CS, 0.f);
-  SAGE_OK(sage_ba_geometric_jac_error(ctx(), kf0.get(), kf1.get(), R10.data(), t10.data(), R0.data(), t0.data(), R1.data(), t1.data(),
-                                      code.data(), code1.data(), scale_0, scale_1, eps, loss_param, weight, A.data(), b.data(), &error,
-                                      nullptr));
+  SAGE_OK(sage_ba_geometric_jac_error(ctx(), kf0.get(), kf1.get(), h[0], h[1], h[2], h[3], h[4], h[5], h[6], code1.data(), scale_0, scale_1,
+                                      eps, loss_param, weight, A.data(), b.data(), &error, nullptr));
   AtA = to_dev(A.data(), {D, D}, rotation10);
   Atb = to_dev(b.data(), {D, 1}, rotation10);
 }

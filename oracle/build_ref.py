@@ -150,6 +150,24 @@ def build_shim(configs=CONFIGS, force=False, jobs=8):
     return True
 
 
+def check_mapper_header():
+    """Compile-only: include/sage_ba_mapper.hpp (BatchedLocalBA, SURVEY row f4) instantiated on the reference's own df::Map<float>
+    (core/mapping/keyframe_map.h) with the vendored Eigen / Sophus and the OpenCV stub.  Raises on failure."""
+    if not available():
+        return False
+    from torch.utils import cpp_extension as ce
+
+    root = os.path.dirname(HERE)
+    inc = []
+    for p in ce.include_paths("cuda") if hasattr(ce, "include_paths") else ce.include_paths(True):
+        inc += ["-isystem", p]
+    inc += ["-isystem", "/usr/local/cuda/include", "-I", os.path.join(HERE, "ref_shims"), "-I", os.path.join(REF, "sources", "core", "mapping"),
+            "-I", os.path.join(REF, "sources", "common"), "-isystem", os.path.join(REF, "thirdparty", "eigen"),
+            "-isystem", os.path.join(REF, "thirdparty", "Sophus"), "-I", os.path.join(root, "include")]
+    _run(["g++", "-std=c++17", "-fsyntax-only", "-w"] + inc + [os.path.join(HERE, "check_mapper_header.cpp")])
+    return True
+
+
 def load_shim(cs, fs):
     """Import the shim module (df:: symbols implemented by libsage_ba.so); needs a CUDA device to do anything."""
     import importlib.util
@@ -183,4 +201,5 @@ def load(cs, fs):
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     build_shim(force="--force" in sys.argv)
+    check_mapper_header()
     print("reference modules:", sorted(os.listdir(OUT)) if ok else "reference sources not present")

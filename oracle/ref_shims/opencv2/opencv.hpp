@@ -10,6 +10,7 @@ struct Mat
 {
   template <typename T>
   T at(int, int) const { throw std::runtime_error("opencv stub"); }
+  Mat clone() const { return *this; } // Frame's copy constructor (core/mapping/frame.h:37), reached by check_mapper_header.cpp
 };
 struct FileNode
 {

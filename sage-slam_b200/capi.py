@@ -108,6 +108,7 @@ SIGNATURES = {
     "sage_ba_problem_set_deterministic": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_factor_offsets": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
     "sage_ba_problem_solver_info": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    "sage_ba_problem_solver_trace": (C.c_int, [vp, vp, c_int_p]),
     "sage_ba_nccl_unique_id": (C.c_int, [vp]),
     "sage_ba_comm_create": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "sage_ba_comm_wrap": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),

@@ -105,7 +105,9 @@ static void fill_pose(float *dR, float *dt, const float *R, const float *t)
 static void check_pair(const sage_ba_keyframe *a, const sage_ba_keyframe *b)
 {
   SAGE_CHECK(a && b, "null keyframe");
-  SAGE_CHECK(a->H == b->H && a->W == b->W && a->L == b->L && a->F == b->F && a->C == b->C, "keyframes have different shapes");
+  // the code size only matters for keyframes that carry a depth basis (frame 1 of the photometric / tracker operators has none)
+  SAGE_CHECK(a->H == b->H && a->W == b->W && a->L == b->L && a->F == b->F && (a->C == b->C || !a->basis || !b->basis),
+             "keyframes have different shapes");
 }
 
 // Tile-major sample order for the staged photometric kernels: samples sorted by (32 x 4 pixel tile, row in tile, column), so
@@ -263,6 +265,7 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
   cudaStream_t s = ctx->stream;
   const bool host = d->memory == SAGE_BA_HOST;
   std::vector<void *> temps;
+  int *bad_locs = nullptr;
   auto stage = [&](const void *src, size_t bytes) -> const void * {
     if (!host || !src)
       return src;
@@ -334,7 +337,10 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
       {
         SAGE_CUDA(cudaMalloc(&kf->loc1d, sizeof(int) * N));
         const int64_t *l64 = (const int64_t *)stage(d->sampled_locations_1d, sizeof(int64_t) * N);
-        launch_convert_loc(l64, kf->loc1d, N, s);
+        SAGE_CUDA(cudaMalloc(&bad_locs, sizeof(int)));
+        temps.push_back(bad_locs);
+        SAGE_CUDA(cudaMemsetAsync(bad_locs, 0, sizeof(int), s));
+        launch_convert_loc(l64, kf->loc1d, N, (int)HW, bad_locs, s);
         ctx->launches += 1;
         if (kf->fg)
         {
@@ -347,6 +353,12 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
     }
     SAGE_CUDA(cudaGetLastError());
     SAGE_CUDA(cudaStreamSynchronize(s));
+    if (bad_locs)
+    {
+      int nbad = 0;
+      SAGE_CUDA(cudaMemcpy(&nbad, bad_locs, sizeof(int), cudaMemcpyDeviceToHost));
+      SAGE_CHECK(nbad == 0, "sampled_locations_1d holds indices outside the image");
+    }
   }
   catch (...)
   {
@@ -663,6 +675,9 @@ static void run_reproj_single(sage_ba_context *ctx, bool jac, bool tracker, cons
                               float eps, float loss_param, float weight, float *AtA, float *Atb, float *error, float *n_inl)
 {
   SAGE_CHECK(M >= 0 && M <= 4096, "num_matches out of range");
+  if (!tracker)
+    for (int m = 0; m < M; ++m) // bias / basis are gathered at these indices
+      SAGE_CHECK(loc1d[m] >= 0 && loc1d[m] < kf0->H * kf0->W, "matched location outside the image");
   cudaStream_t s = ctx->stream;
   const int C = tracker ? 8 : kf0->C;
   const int D = tracker ? 6 : 13 + C;

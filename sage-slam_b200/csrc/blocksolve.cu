@@ -21,6 +21,7 @@
 //    row per thread.  The forward substitution rides along (the gradient is one more panel row); bs_backward_kernel walks the
 //    tree in the opposite direction.  fp64 throughout: the damped system reaches condition numbers ~1e9.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -36,12 +37,13 @@ struct BsCfg
   static constexpr int SP = (S + 7) / 8 * 8; // 40 / 24 / 16
   static constexpr int SPP = SP + 1;         // row stride of the panel blocks (odd: conflict-free column access)
   static constexpr int NT = 256;
-  static constexpr int MAXS = C == 32 ? 8 : 16; // panel blocks resident in shared memory at a time
+  static constexpr int MAXS = C == 32 ? 7 : 16; // panel blocks resident in shared memory at a time
   static constexpr int TQ = SP / 4;
   static constexpr int TILES = TQ * TQ;
   static constexpr int NR = (SP + 31) / 32; // rows per lane in the warp-level factorisation
-  static constexpr size_t factor_smem() { return sizeof(double) * ((size_t)MAXS * SP * SPP + 4 * SP * SP + 4 * SP); }
-  static constexpr size_t backward_smem() { return sizeof(double) * ((size_t)SP * SPP + SP * SP + 2 * SP); }
+  static constexpr int BWS = C == 32 ? 12 : 16; // L(i, p) blocks of a column staged at once by the backward kernel
+  static constexpr size_t factor_smem() { return sizeof(double) * ((size_t)MAXS * SP * SPP + 6 * SP * SP + 4 * SP); }
+  static constexpr size_t backward_smem() { return sizeof(double) * ((size_t)SP * SPP + (size_t)BWS * SP * SP + (size_t)(BWS + 2) * SP); }
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p)
@@ -51,6 +53,25 @@ __device__ __forceinline__ int ld_acquire(const int *p)
   return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// 16-byte asynchronous global -> shared copies (LDGSTS, L2 only: the data was written by another SM in this launch)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// one SP x SP fp64 block, all threads of the CTA
+template <int BS, int NT>
+__device__ __forceinline__ void block_copy_async(double *dst, const double *src, int tid)
+{
+  for (int e = tid * 2; e < BS; e += NT * 2)
+    cp_async16(dst + e, src + e);
+}
 
 // column of factor `m` that holds variable `var` ([pose 6 | code C | scale]) of keyframe `unit`, or -1
 __device__ __forceinline__ int factor_col(const FactorMeta &m, int unit, int var, int C)
@@ -81,7 +102,8 @@ assemble_blocks_kernel(const float *__restrict__ fbuf, const FactorMeta *__restr
   const AsmBlock b = blocks[blockIdx.x];
   const int S = 7 + C;
   const bool diag = b.runit == b.cunit;
-  for (int e = threadIdx.x; e < SP * SP; e += blockDim.x)
+  // gridDim.y CTAs share the elements of a block (a diagonal block gathers from every factor of its keyframe)
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < SP * SP; e += blockDim.x * gridDim.y)
   {
     const int u = e / SP, v = e - u * SP;
     double sum = 0.0;
@@ -109,7 +131,7 @@ assemble_blocks_kernel(const float *__restrict__ fbuf, const FactorMeta *__restr
     }
     Hblk[(size_t)b.blk * SP * SP + e] = sum;
   }
-  if (diag)
+  if (diag && blockIdx.y == 0)
     for (int u = threadIdx.x; u < SP; u += blockDim.x)
     {
       double sum = 0.0;
@@ -180,92 +202,30 @@ struct TrsmStep<SP, SP>
   __device__ __forceinline__ static void run(double (&)[SP], const double *, const double *) {}
 };
 
-// One step of the warp-level Cholesky: lane r < RW keeps row r in registers (columns < RW); rows RW .. SP-1 (C = 32: 8 rows)
-// stay in the panel (shared memory, row stride SPP) and their trailing update is spread over all 32 lanes -- lane l updates
-// columns l and l + 32 of every such row -- so that no lane walks a row serially.
-template <int SP, int SPP, int RW, int c>
-struct PotrfStep
-{
-  __device__ __forceinline__ static void run(double (&a)[RW], double *P, double *colb, double *invd, int lane, bool &bad)
-  {
-    constexpr int XR = SP - RW;
-    double piv;
-    if constexpr (c < RW)
-      piv = __shfl_sync(0xffffffffu, a[c], c);
-    else
-      piv = P[c * SPP + c];
-    if (!(piv > 0.0))
-    {
-      bad = true;
-      piv = 1.0;
-    }
-    const double inv = rsqrt(piv), dg = piv * inv;
-    if constexpr (c < RW)
-    {
-      if (lane < RW)
-      {
-        const double v = lane == c ? dg : (lane > c ? a[c] * inv : 0.0);
-        a[c] = v;
-        colb[lane] = v;
-      }
-    }
-    if (XR > 0 && lane < XR)
-    {
-      const int r = RW + lane;
-      const double v = r == c ? dg : (r > c ? P[r * SPP + c] * inv : 0.0);
-      P[r * SPP + c] = v;
-      colb[r] = v;
-    }
-    if (lane == 0)
-      invd[c] = inv;
-    __syncwarp();
-    if constexpr (c < RW)
-    {
-#pragma unroll
-      for (int qq = c + 1; qq < RW; ++qq)
-        if (lane >= qq)
-          a[qq] = fma(-a[c], colb[qq], a[qq]);
-    }
-    if constexpr (XR > 0)
-    {
-#pragma unroll
-      for (int h = 0; h < (SP + 31) / 32; ++h)
-      {
-        const int qq = lane + 32 * h;
-        if (qq > c && qq < SP)
-        {
-          const double cq = colb[qq];
-#pragma unroll
-          for (int r = (c + 1 > RW ? c + 1 : RW); r < SP; ++r)
-            if (r >= qq)
-              P[r * SPP + qq] = fma(-colb[r], cq, P[r * SPP + qq]);
-        }
-      }
-    }
-    __syncwarp();
-    PotrfStep<SP, SPP, RW, c + 1>::run(a, P, colb, invd, lane, bad);
-  }
-};
-template <int SP, int SPP, int RW>
-struct PotrfStep<SP, SPP, RW, SP>
-{
-  __device__ __forceinline__ static void run(double (&)[RW], double *, double *, double *, int, bool &) {}
-};
-
 // Global storage of a factor block is TRANSPOSED (k-major): Lt[k * SP + r] = L[r][k], so that consumers stage it with a
 // straight copy and read 4 consecutive rows of one column with two LDS.128.
 template <int C>
 __global__ void __launch_bounds__(BsCfg<C>::NT, 1)
 bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *__restrict__ g, double *__restrict__ Lblk,
-                 double *__restrict__ ybuf, double *__restrict__ dinv, const double damp, int *__restrict__ sync)
+                 double *__restrict__ ybuf, double *__restrict__ dinv, const double damp, int *__restrict__ sync,
+                 long long *__restrict__ dbg)
 {
   using T = BsCfg<C>;
   constexpr int SP = T::SP, SPP = T::SPP, NT = T::NT, MAXS = T::MAXS, TQ = T::TQ, NR = T::NR;
-  extern __shared__ double sm[];
+  // optional phase timestamps (globaltimer, ns) per column: [start, loaded, deps done, factored, panel solved, published, wait ns, deps]
+  auto stamp = [&](int slot, int col) {
+    if (dbg && threadIdx.x == 0)
+    {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[(size_t)col * 8 + slot] = t;
+    }
+  };
+  extern __shared__ __align__(16) double sm[];
   double *P = sm;                          // [MAXS][SP][SPP] panel blocks, row-major
   double *Bt = P + (size_t)MAXS * SP * SPP; // [SP][SP] k-major L(p, j)
-  double *At = Bt + SP * SP;               // [2][SP][SP] k-major L(i, j)
-  double *Lt = At + 2 * SP * SP;           // [SP][SP] k-major L(p, p)
+  double *At = Bt + SP * SP;               // [2][2][SP][SP] k-major L(i, j): two pairs in use, two being prefetched
+  double *Lt = At + 4 * SP * SP;           // [SP][SP] k-major L(p, p)
   double *gv = Lt + SP * SP;               // [SP] gradient / forward-substituted y_p
   double *yj = gv + SP;                    // [SP]
   double *invd = yj + SP;                  // [SP] 1 / L(p,p)[c][c]
@@ -281,6 +241,33 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
   const int unit = d.unit_of_pos[p];
   const int cbeg = d.col_ptr[p], nslots = d.col_ptr[p + 1] - cbeg + 1;
   const size_t BS = (size_t)SP * SP;
+  stamp(0, p);
+  long long waited = 0;
+  // the column's dependency / pair lists, read many times below: keep them in shared memory when they fit
+  constexpr int MAXDEP = 64, MAXPAIR = 512;
+  __shared__ int s_dep_col[MAXDEP], s_dep_blk[MAXDEP], s_dep_pair[MAXDEP + 1], s_pair_src[MAXPAIR], s_pair_dst[MAXPAIR];
+  const int dep0 = d.dep_ptr[p], ndep = d.dep_ptr[p + 1] - dep0;
+  const int pair0 = d.dep_pair_ptr[dep0], npair = d.dep_pair_ptr[dep0 + ndep] - pair0;
+  const bool meta_smem = ndep <= MAXDEP && npair <= MAXPAIR;
+  if (meta_smem)
+  {
+    for (int e = tid; e < ndep; e += NT)
+    {
+      s_dep_col[e] = d.dep_col[dep0 + e];
+      s_dep_blk[e] = d.dep_blk[dep0 + e];
+    }
+    for (int e = tid; e <= ndep; e += NT)
+      s_dep_pair[e] = d.dep_pair_ptr[dep0 + e] - pair0;
+    for (int e = tid; e < npair; e += NT)
+    {
+      s_pair_src[e] = d.pair_src[pair0 + e];
+      s_pair_dst[e] = d.pair_dst[pair0 + e];
+    }
+  }
+  const int *m_dep_col = meta_smem ? s_dep_col : d.dep_col + dep0;
+  const int *m_dep_blk = meta_smem ? s_dep_blk : d.dep_blk + dep0;
+  const int *m_pair_src = meta_smem ? s_pair_src : d.pair_src + pair0;
+  const int *m_pair_dst = meta_smem ? s_pair_dst : d.pair_dst + pair0;
 
   for (int s0 = 0; s0 < nslots; s0 += MAXS)
   {
@@ -312,58 +299,81 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
     if (first && tid < SP)
       gv[tid] = d.fixed[unit * SP + tid] ? 0.0 : g[(size_t)unit * SP + tid];
     __syncthreads();
+    if (first)
+      stamp(1, p);
 
-    // ---- left-looking updates from every earlier column j with L(p, j) != 0
-    for (int dep = d.dep_ptr[p]; dep < d.dep_ptr[p + 1]; ++dep)
+    // ---- left-looking updates from every earlier column j with L(p, j) != 0.  Per dependency: wait for its flag, then ONE
+    // round trip brings L(p, j), y_j and the first two L(i, j) (cp.async); further pairs are prefetched into the other buffer
+    // pair while the current two are multiplied.
+    for (int dep = 0; dep < ndep; ++dep)
     {
-      const int j = d.dep_col[dep];
+      const int j = m_dep_col[dep];
       if (first)
       {
         if (tid == 0)
+        {
+          long long t0 = 0, t1 = 0;
+          if (dbg)
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
           while (ld_acquire(&flags[j]) == 0)
-            __nanosleep(40);
+            __nanosleep(20);
+          if (dbg)
+          {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            waited += t1 - t0;
+          }
+        }
         __syncthreads();
       }
-      const double *Bsrc = Lblk + (size_t)d.dep_blk[dep] * BS;
-      for (int e = tid; e < (int)BS; e += NT)
-        Bt[e] = __ldcg(Bsrc + e);
+      // pairs of this dependency whose destination lies in the resident chunk
+      const int pb = meta_smem ? s_dep_pair[dep] : d.dep_pair_ptr[dep0 + dep] - pair0;
+      const int pe = meta_smem ? s_dep_pair[dep + 1] : d.dep_pair_ptr[dep0 + dep + 1] - pair0;
+      int q = pb;
+      auto next_pair = [&]() -> int {
+        while (q < pe)
+        {
+          const int dst = m_pair_dst[q];
+          ++q;
+          if (dst >= s0 && dst < s1)
+            return q - 1;
+        }
+        return -1;
+      };
+      block_copy_async<SP * SP, NT>(Bt, Lblk + (size_t)m_dep_blk[dep] * BS, tid);
+      int cur[2] = {next_pair(), -1};
+      cur[1] = cur[0] >= 0 ? next_pair() : -1;
+      int buf = 0;
+      for (int h = 0; h < 2; ++h)
+        if (cur[h] >= 0)
+          block_copy_async<SP * SP, NT>(At + (size_t)(buf * 2 + h) * BS, Lblk + (size_t)m_pair_src[cur[h]] * BS, tid);
+      cp_async_commit();
       if (first && tid < SP)
         yj[tid] = __ldcg(ybuf + (size_t)j * SP + tid);
-      __syncthreads();
-      if (first && tid < SP)
+      bool first_round = true;
+      while (true)
       {
-        double a = 0.0;
-        for (int k = 0; k < SP; ++k)
-          a = fma(Bt[k * SP + tid], yj[k], a);
-        gv[tid] -= a; // g_p -= L(p, j) y_j
-      }
-      const int pe = d.dep_pair_ptr[dep + 1];
-      int q = d.dep_pair_ptr[dep];
-      while (q < pe)
-      {
-        int sel[2], nsel = 0;
-        while (q < pe && nsel < 2)
-        {
-          const int dst = d.pair_dst[q];
-          if (dst >= s0 && dst < s1)
-            sel[nsel++] = q;
-          ++q;
-        }
-        if (nsel == 0)
-          break;
-        for (int h = 0; h < nsel; ++h)
-        {
-          const double *Asrc = Lblk + (size_t)d.pair_src[sel[h]] * BS;
-          for (int e = tid; e < (int)BS; e += NT)
-            At[h * BS + e] = __ldcg(Asrc + e);
-        }
+        int nxt[2] = {cur[0] >= 0 && cur[1] >= 0 ? next_pair() : -1, -1};
+        nxt[1] = nxt[0] >= 0 ? next_pair() : -1;
+        for (int h = 0; h < 2; ++h)
+          if (nxt[h] >= 0)
+            block_copy_async<SP * SP, NT>(At + (size_t)((buf ^ 1) * 2 + h) * BS, Lblk + (size_t)m_pair_src[nxt[h]] * BS, tid);
+        cp_async_commit();
+        cp_async_wait<1>(); // everything but the prefetch just issued
         __syncthreads();
+        if (first_round && first && tid < SP)
+        {
+          double a = 0.0;
+          for (int k = 0; k < SP; ++k)
+            a = fma(Bt[k * SP + tid], yj[k], a);
+          gv[tid] -= a; // g_p -= L(p, j) y_j
+        }
+        first_round = false;
         {
           const int half = tid >> 7, t = tid & 127;
-          if (half < nsel && t < T::TILES)
+          if (cur[half] >= 0 && t < T::TILES)
           {
             const int tr = t / TQ, tc = t - tr * TQ;
-            const double *A = At + half * BS + tr * 4, *B = Bt + tc * 4;
+            const double *A = At + (size_t)(buf * 2 + half) * BS + tr * 4, *B = Bt + tc * 4;
             double acc[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -382,7 +392,7 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
                 for (int jj = 0; jj < 4; ++jj)
                   acc[i][jj] = fma(a[i], b[jj], acc[i][jj]);
             }
-            double *Cd = P + (size_t)(d.pair_dst[sel[half]] - s0) * SP * SPP + (tr * 4) * SPP + tc * 4;
+            double *Cd = P + (size_t)(m_pair_dst[cur[half]] - s0) * SP * SPP + (tr * 4) * SPP + tc * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -390,40 +400,85 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
                 Cd[i * SPP + jj] -= acc[i][jj]; // A(i, p) -= L(i, j) L(p, j)^T
           }
         }
-        __syncthreads();
+        __syncthreads(); // the buffers just read are overwritten by the next prefetch / the next dependency
+        if (nxt[0] < 0)
+          break;
+        cur[0] = nxt[0];
+        cur[1] = nxt[1];
+        buf ^= 1;
       }
-      __syncthreads(); // Bt / yj are overwritten by the next dependency
+      cp_async_wait<0>();
     }
 
-    // ---- factor the diagonal block: one warp, rows in registers, one column broadcast through shared memory per step
+    // ---- factor the diagonal block with the whole CTA.  Square-root-free elimination with ONE barrier per pivot: the trailing
+    // update a_rq -= a_rc a_qc / a_cc needs only the (unscaled) pivot column, which step c never writes, so scaling the columns
+    // by 1 / sqrt(pivot) is deferred to one parallel pass at the end.  The serial chain per pivot is barrier + reciprocal + one
+    // fused multiply-add (~250 cycles) instead of a warp walking the whole trailing block (2200 cycles measured).
     if (first)
     {
-      if (warp == 0)
+      stamp(2, p);
+      // every thread keeps its share of the lower triangle (SP (SP + 1) / 2 elements, 4 per thread) in REGISTERS for the whole
+      // elimination; per pivot the owners of column c publish it through a double-buffered shared-memory column, one barrier,
+      // and everybody applies a_rq -= a_rc a_qc / a_cc to the elements it owns.
+      constexpr int NE = SP * (SP + 1) / 2, EPT = (NE + NT - 1) / NT;
+      double *D = P; // slot 0, row stride SPP
+      double *colbuf = At; // [2][SP]: free until the next dependency round (none follows: the updates of this column are done)
+      double *pivs = At + 2 * SP; // [SP]
+      double av[EPT];
+      int er[EPT], eq[EPT];
+#pragma unroll
+      for (int k = 0; k < EPT; ++k)
       {
-        constexpr int RW = SP < 32 ? SP : 32, XR = SP - RW;
-        double a[RW];
-        const double *xrow = P + (RW + (lane < XR ? lane : 0)) * SPP;
-#pragma unroll
-        for (int c = 0; c < RW; ++c)
-          a[c] = lane < RW ? P[lane * SPP + c] : 0.0;
-        bool bad = false;
-        PotrfStep<SP, SPP, RW, 0>::run(a, P, colb, invd, lane, bad);
-        __syncwarp();
-        if (bad && lane == 0)
-          atomicMax(&sync[1], p + 1);
-        if (lane < RW)
-        {
-#pragma unroll
-          for (int k = 0; k < RW; ++k)
-            Lt[k * SP + lane] = k <= lane ? a[k] : 0.0;
-          for (int k = RW; k < SP; ++k)
-            Lt[k * SP + lane] = 0.0;
-        }
-        if (XR > 0 && lane < XR)
-          for (int k = 0; k < SP; ++k)
-            Lt[k * SP + RW + lane] = k <= RW + lane ? xrow[k] : 0.0;
+        const int e = tid + k * NT;
+        // e -> (r, q), q <= r: row r starts at r (r + 1) / 2
+        int r = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        while ((r + 1) * (r + 2) / 2 <= e)
+          ++r;
+        while (r * (r + 1) / 2 > e)
+          --r;
+        er[k] = e < NE ? r : -1;
+        eq[k] = e < NE ? e - r * (r + 1) / 2 : -1;
+        av[k] = e < NE ? D[r * SPP + eq[k]] : 0.0;
       }
+      bool bad = false;
+#pragma unroll 1
+      for (int c = 0; c < SP; ++c)
+      {
+        double *cb = colbuf + (c & 1) * SP;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k)
+          if (eq[k] == c)
+            cb[er[k]] = av[k];
+        __syncthreads();
+        double piv = cb[c];
+        if (!(piv > 0.0))
+        {
+          bad = true;
+          piv = 1.0;
+        }
+        if (tid == 0)
+          pivs[c] = piv;
+        const double rcp = __drcp_rn(piv);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k)
+          if (eq[k] > c)
+            av[k] = fma(-cb[er[k]] * rcp, cb[eq[k]], av[k]);
+      }
+      if (bad && tid == 0)
+        atomicMax(&sync[1], p + 1);
       __syncthreads();
+      if (tid < SP)
+        invd[tid] = rsqrt(pivs[tid]);
+      for (int e = tid; e < SP * SP; e += NT)
+        Lt[e] = 0.0;
+      __syncthreads();
+      // L[r][q] = a_rq / sqrt(pivot_q) (the diagonal: pivot / sqrt(pivot)), stored k-major
+#pragma unroll
+      for (int k = 0; k < EPT; ++k)
+        if (er[k] >= 0)
+          Lt[eq[k] * SP + er[k]] = (er[k] == eq[k] ? pivs[eq[k]] : av[k]) * invd[eq[k]];
+      __syncthreads();
+      stamp(3, p);
     }
 
     // ---- panel: X L(p,p)^T = A, one row per thread; the gradient is one more row (y_p = L(p,p)^-1 g_p)
@@ -445,6 +500,8 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
       }
     }
     __syncthreads();
+    if (first)
+      stamp(4, p);
 
     // ---- publish the chunk (k-major)
     for (int idx = tid; idx < (s1 - s0) * (int)BS; idx += NT)
@@ -464,6 +521,12 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
   __syncthreads();
   if (tid == 0)
     st_release(&flags[p], 1);
+  stamp(5, p);
+  if (dbg && tid == 0)
+  {
+    dbg[(size_t)p * 8 + 6] = waited;
+    dbg[(size_t)p * 8 + 7] = ndep;
+  }
 }
 
 // x_p = L(p,p)^-T (y_p - sum_{i in struct(p)} L(i,p)^T x_i), columns in reverse order, same flag protocol
@@ -474,11 +537,11 @@ bs_backward_kernel(const BsDev d, const double *__restrict__ Lblk, const double 
 {
   using T = BsCfg<C>;
   constexpr int S = T::S, SP = T::SP, SPP = T::SPP, NT = T::NT, NR = T::NR;
-  extern __shared__ double sm[];
-  double *Lrow = sm;           // [SP][SPP] L(p,p) row-major
-  double *Bt = Lrow + SP * SPP; // [SP][SP] k-major L(i, p)
-  double *acc = Bt + SP * SP;   // [SP]
-  double *xr = acc + SP;        // [SP]
+  extern __shared__ __align__(16) double sm[];
+  double *Lrow = sm;                             // [SP][SPP] L(p,p) row-major
+  double *Bt = Lrow + SP * SPP;                  // [BWS][SP][SP] k-major L(i, p)
+  double *acc = Bt + (size_t)T::BWS * SP * SP;   // [SP]
+  double *xr = acc + SP;                         // [BWS][SP] x of the ancestors (then partial sums)
   __shared__ int s_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = d.K;
@@ -490,46 +553,76 @@ bs_backward_kernel(const BsDev d, const double *__restrict__ Lblk, const double 
   const int unit = d.unit_of_pos[p];
   const int cbeg = d.col_ptr[p], nr = d.col_ptr[p + 1] - cbeg;
   const size_t BS = (size_t)SP * SP;
-  for (int e = tid; e < (int)BS; e += NT)
+  // the factor is final (the forward kernel ended): stage L(p,p) and the column's sub-diagonal blocks BEFORE looking at any flag
+  constexpr int BWS = T::BWS;
+  for (int c0 = 0; c0 < max(nr, 1); c0 += BWS)
   {
-    const int k = e / SP, r = e - k * SP;
-    Lrow[r * SPP + k] = __ldcg(Lblk + (size_t)p * BS + e);
-  }
-  if (tid < SP)
-    acc[tid] = __ldcg(ybuf + (size_t)p * SP + tid);
-  __syncthreads();
-  for (int s = 0; s < nr; ++s)
-  {
-    const int rp = d.col_rowpos[cbeg + s];
-    if (tid == 0)
-      while (ld_acquire(&flags[rp]) == 0)
-        __nanosleep(40);
-    __syncthreads();
-    const double *src = Lblk + (size_t)d.col_blk[cbeg + s] * BS;
-    for (int e = tid; e < (int)BS; e += NT)
-      Bt[e] = __ldcg(src + e);
-    if (tid < SP)
-      xr[tid] = __ldcg(xbuf + (size_t)rp * SP + tid);
-    __syncthreads();
-    if (tid < SP)
+    const int c1 = min(nr, c0 + BWS);
+    if (c0 == 0)
     {
-      double a = 0.0;
-      for (int r = 0; r < SP; ++r)
-        a = fma(Bt[tid * SP + r], xr[r], a); // (L(i,p)^T x_i)[k] = sum_r L[r][k] x[r]
-      acc[tid] -= a;
+      for (int e = tid; e < (int)BS; e += NT)
+      {
+        const int k = e / SP, r = e - k * SP;
+        Lrow[r * SPP + k] = __ldcg(Lblk + (size_t)p * BS + e);
+      }
+      if (tid < SP)
+        acc[tid] = __ldcg(ybuf + (size_t)p * SP + tid);
     }
+    for (int s = c0; s < c1; ++s)
+      block_copy_async<SP * SP, NT>(Bt + (size_t)(s - c0) * BS, Lblk + (size_t)d.col_blk[cbeg + s] * BS, tid);
+    cp_async_commit();
+    // x of the ancestors: wait for each flag (they complete top-down; usually all but the last are long done)
+    for (int s = c0 + warp; s < c1; s += NT / 32)
+    {
+      const int rp = d.col_rowpos[cbeg + s];
+      if (lane == 0)
+        while (ld_acquire(&flags[rp]) == 0)
+          __nanosleep(20);
+      __syncwarp();
+      for (int r = lane; r < SP; r += 32)
+        xr[(size_t)(s - c0) * SP + r] = __ldcg(xbuf + (size_t)rp * SP + r);
+    }
+    cp_async_wait<0>();
     __syncthreads();
+    // acc[k] -= sum_s sum_r L_s[r][k] x_s[r]: thread (k, part) sums its share of the slots, the parts are folded in a fixed order
+    {
+      constexpr int PARTS = NT / SP; // 6 for SP = 40
+      const int k = tid % SP, part = tid / SP;
+      double a = 0.0;
+      if (part < PARTS)
+        for (int s = c0 + part; s < c1; s += PARTS)
+        {
+          const double *B = Bt + (size_t)(s - c0) * BS + k * SP, *x = xr + (size_t)(s - c0) * SP;
+          for (int r = 0; r < SP; ++r)
+            a = fma(B[r], x[r], a);
+        }
+      __syncthreads(); // xr is reused as the partial-sum scratch: [PARTS][SP]
+      if (part < PARTS)
+        xr[part * SP + k] = a;
+      __syncthreads();
+      if (tid < SP)
+      {
+        double t = 0.0;
+        for (int q = 0; q < PARTS; ++q)
+          t += xr[q * SP + tid];
+        acc[tid] -= t;
+      }
+      __syncthreads();
+    }
   }
   if (warp == 0)
   {
-    double a[NR];
+    double a[NR], di[NR];
 #pragma unroll
     for (int rr = 0; rr < NR; ++rr)
+    {
       a[rr] = lane + 32 * rr < SP ? acc[lane + 32 * rr] : 0.0;
+      di[rr] = lane + 32 * rr < SP ? __ldcg(dinv + (size_t)p * SP + lane + 32 * rr) : 0.0;
+    }
 #pragma unroll
     for (int c = SP - 1; c >= 0; --c)
     {
-      const double xc = __shfl_sync(0xffffffffu, a[c >> 5], c & 31) * __ldcg(dinv + (size_t)p * SP + c);
+      const double xc = __shfl_sync(0xffffffffu, a[c >> 5] * di[c >> 5], c & 31);
 #pragma unroll
       for (int rr = 0; rr < NR; ++rr)
       {
@@ -687,6 +780,10 @@ void BlockSystem::build(int K_, int C_, const std::vector<FactorMeta> &metas, co
   depth = K ? 1 : 0;
   for (int q = 0; q < K; ++q)
   {
+    // a column consumes its dependencies in a FIXED order (the order of the floating-point updates must not depend on timing);
+    // sorting them by the length of their own dependency chain puts the ones that finish last at the end, so the column does not
+    // sit behind a late dependency while ten finished ones are queued after it
+    std::stable_sort(rowlist[q].begin(), rowlist[q].end(), [&](int a, int b) { return chain[a] < chain[b]; });
     for (int j : rowlist[q])
     {
       h_dep_col.push_back(j);
@@ -782,7 +879,7 @@ void BlockSystem::assemble(const float *fbuf, const FactorMeta *metas_d, const P
 {
   if (norig <= 0)
     return;
-  assemble_blocks_kernel<<<norig, 256, 0, s>>>(fbuf, metas_d, asm_blocks.p, asm_factors.p, priors_d, asm_priors.p, codes, scales, Hblk.p,
+  assemble_blocks_kernel<<<dim3(norig, 6), 256, 0, s>>>(fbuf, metas_d, asm_blocks.p, asm_factors.p, priors_d, asm_priors.p, codes, scales, Hblk.p,
                                                g.p, C, SP);
   if (launches)
     *launches += 1;
@@ -799,7 +896,10 @@ static void solve_t(BlockSystem &b, double damp, double *delta_d, cudaStream_t s
     cudaFuncSetAttribute(bs_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::backward_smem());
     once = true;
   }
-  bs_factor_kernel<C><<<b.K, T::NT, T::factor_smem(), s>>>(b.dev(), b.Hblk.p, b.g.p, b.Lblk.p, b.y.p, b.dinv.p, damp, b.sync.p);
+  long long *dbg = nullptr;
+  if (getenv("SAGE_BA_SOLVER_TRACE"))
+    dbg = reinterpret_cast<long long *>(b.dbg.ensure((size_t)b.K * 8));
+  bs_factor_kernel<C><<<b.K, T::NT, T::factor_smem(), s>>>(b.dev(), b.Hblk.p, b.g.p, b.Lblk.p, b.y.p, b.dinv.p, damp, b.sync.p, dbg);
   bs_backward_kernel<C><<<b.K, T::NT, T::backward_smem(), s>>>(b.dev(), b.Lblk.p, b.y.p, b.dinv.p, b.x.p, delta_d, C, b.sync.p);
 }
 
@@ -817,6 +917,17 @@ void BlockSystem::solve(double damp, double *delta_d, int *info_d, cudaStream_t 
     SAGE_CUDA(cudaMemcpyAsync(info_d, sync.p + 1, sizeof(int), cudaMemcpyDeviceToDevice, s));
   if (launches)
     *launches += 2;
+}
+
+// phase timestamps of the last factorisation (ns since the first column started), row = elimination position:
+// [start, loaded, deps done, factored, panel solved, published, ns spent waiting on flags, number of dependencies]
+int BlockSystem::read_trace(long long *out, cudaStream_t s)
+{
+  if (!dbg.p)
+    return 0;
+  SAGE_CUDA(cudaMemcpyAsync(out, dbg.p, sizeof(long long) * K * 8, cudaMemcpyDeviceToHost, s));
+  SAGE_CUDA(cudaStreamSynchronize(s));
+  return K;
 }
 
 void BlockSystem::expand_dense(double *H, double *gd, int n, cudaStream_t s, long *launches)

@@ -74,6 +74,7 @@ struct BlockSystem
   DevBuf<AsmBlock> asm_blocks;
   DevBuf<unsigned char> fixed;
   DevBuf<double> Hblk, Lblk, g, y, x, dinv;
+  DevBuf<long long> dbg; // SAGE_BA_SOLVER_TRACE=1: per-column phase timestamps of the factorisation
 
   BsDev dev() const;
   // links: keyframe pairs that share a factor; fixed_vars: global variable order of include/sage_ba.h
@@ -86,6 +87,7 @@ struct BlockSystem
   void solve(double damp, double *delta_d, int *info_d, cudaStream_t s, long *launches);
   // dense n x n copy of H (both triangles) and g in the global variable order (tests, the dense cross-check solver)
   void expand_dense(double *H, double *g, int n, cudaStream_t s, long *launches);
+  int read_trace(long long *out, cudaStream_t s);
 };
 
 } // namespace sage

@@ -80,16 +80,23 @@ void launch_relayout_basis(const float *jac, long stride_row, long stride_col, f
   transpose_strided_kernel<<<grid, block, 0, stream>>>(jac, stride_row, stride_col, basis, HW, C);
 }
 
-__global__ void convert_loc_kernel(const int64_t *__restrict__ a, int *__restrict__ b, int N)
+// int64 -> int32; an index outside [0, HW) can only come from a corrupt caller array: it is clamped (never dereferenced out of
+// bounds) and counted, the keyframe constructor turns a non-zero count into an error
+__global__ void convert_loc_kernel(const int64_t *__restrict__ a, int *__restrict__ b, int N, int HW, int *__restrict__ bad)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N)
-    b[i] = (int)a[i];
+  {
+    const int64_t v = a[i];
+    if (v < 0 || v >= HW)
+      atomicAdd(bad, 1);
+    b[i] = (int)(v < 0 ? 0 : (v >= HW ? HW - 1 : v));
+  }
 }
-void launch_convert_loc(const int64_t *loc64, int *loc32, int N, cudaStream_t stream)
+void launch_convert_loc(const int64_t *loc64, int *loc32, int N, int HW, int *bad, cudaStream_t stream)
 {
   if (N > 0)
-    convert_loc_kernel<<<(N + 255) / 256, 256, 0, stream>>>(loc64, loc32, N);
+    convert_loc_kernel<<<(N + 255) / 256, 256, 0, stream>>>(loc64, loc32, N, HW, bad);
 }
 
 __global__ void pack_homo_kernel(const float *__restrict__ h3, float4 *__restrict__ h4, int N)

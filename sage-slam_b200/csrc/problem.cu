@@ -128,7 +128,7 @@ __global__ void depth_unscaled_batched_kernel(const KfMaps *maps, const float *c
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW)
     return;
-  const KfMaps m = maps[k];
+  const KfMaps m = maps[blockIdx.y];
   float acc = 0.f;
   const float4 *row = reinterpret_cast<const float4 *>(m.basis + (size_t)p * C);
   for (int q = 0; q < C / 4; ++q)
@@ -151,7 +151,7 @@ __global__ void update_depth_batched_kernel(const KfMaps *maps, const float *cod
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW)
     return;
-  const KfMaps m = maps[k];
+  const KfMaps m = maps[blockIdx.y];
   float acc = 0.f;
   const float4 *row = reinterpret_cast<const float4 *>(m.basis + (size_t)p * C);
   for (int c = 0; c < C / 4; ++c)
@@ -1138,6 +1138,18 @@ int sage_ba_problem_solver_info(sage_ba_problem *p, int *num_blocks, int *fill_b
     *fill_blocks = (int)p->bs.fill_blocks;
   if (depth)
     *depth = p->bs.depth;
+  SAGE_PCATCH
+}
+
+int sage_ba_problem_solver_trace(sage_ba_problem *p, long long *out, int *positions_to_keyframes)
+{
+  SAGE_PTRY(p)
+  problem_build(p);
+  SAGE_CHECK(out, "null output");
+  SAGE_CHECK(p->bs.read_trace(out, ctx__->stream) == p->K, "no trace: set SAGE_BA_SOLVER_TRACE=1 before the solve");
+  if (positions_to_keyframes)
+    for (int q = 0; q < p->K; ++q)
+      positions_to_keyframes[q] = p->bs.order[q];
   SAGE_PCATCH
 }
 

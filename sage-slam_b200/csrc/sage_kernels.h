@@ -30,7 +30,7 @@ int launch_map_match_geom(bool jac, int C, const MapMatchGeomFactor *factors, in
 // prep.cu
 void launch_relayout_fg(const float *feat, const float *grad, float *fg, int F, long SP, cudaStream_t stream);
 void launch_relayout_basis(const float *jac, long stride_row, long stride_col, float *basis, int HW, int C, cudaStream_t stream);
-void launch_convert_loc(const int64_t *loc64, int *loc32, int N, cudaStream_t stream);
+void launch_convert_loc(const int64_t *loc64, int *loc32, int N, int HW, int *bad, cudaStream_t stream);
 void launch_permute_samples(const int *perm, const int *loc, const float4 *homo, int *loc_s, float4 *homo_s, int N, cudaStream_t stream);
 void launch_pack_homo(const float *homo3, float4 *homo4, int N, cudaStream_t stream);
 // dgm[HW] = (D, dD/dx, dD/dy, mask) with D = bias + basis . code (unscaled), central differences with replicate padding

@@ -49,6 +49,15 @@ class Map:
     links: List[Tuple[int, int]] = field(default_factory=list)
 
 
+def avg_squared_dpt_bias(kf: Keyframe) -> float:
+    """Frame::avg_squared_dpt_bias as Mapper::BuildKeyframe sets it (mapper.cpp:1376-1378): the MASKED mean
+    sum((dpt_map_bias * mask)^2) / sum(mask) in fp32 -- with an endoscope mask this differs from the plain mean over all pixels,
+    and it scales the robust loss of every geometric factor."""
+    m = np.asarray(kf.video_mask, F32).reshape(-1)
+    b = np.asarray(kf.dpt_map_bias, F32).reshape(-1)
+    return float(np.sum(np.square(b * m, dtype=F32), dtype=F32) / np.sum(m, dtype=F32))
+
+
 class BatchedMapper:
     def __init__(self, ctx: ops.Context, opts: MapperOptions = None):
         self.ctx = ctx
@@ -106,7 +115,7 @@ class BatchedMapper:
                     self._factors.append(("reproj", i, j, m))
             if o.use_geometric and geo:
                 kf = self.map.keyframes[a]
-                loss = o.geo_loss_param_factor * float(np.mean(np.square(kf.dpt_map_bias, dtype=np.float64)))  # avg_squared_dpt_bias
+                loss = o.geo_loss_param_factor * avg_squared_dpt_bias(kf)
                 self._factors.append(("geo", i, j, loss))
 
     def _match(self, i, j):

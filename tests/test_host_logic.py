@@ -224,3 +224,18 @@ def test_std_shuffle_reproduces_libstdcxx():
     assert n_cases == 7
     old = frames.std_shuffle(1000, 42, libstdcxx="9")  # GCC <= 10 variant: a permutation, different draw
     assert sorted(old.tolist()) == list(range(1000)) and list(old[:8]) != list(frames.std_shuffle(1000, 42)[:8])
+
+
+def test_avg_squared_dpt_bias_is_the_masked_mean():
+    """Mapper::BuildKeyframe (core/mapping/mapper.cpp:1376-1378): sum((bias * mask)^2) / sum(mask), not the mean over all pixels --
+    the two differ under an endoscope mask, and the value scales the robust loss of every geometric factor."""
+    from sage_slam_b200 import mapper
+
+    kfs = sage.synthetic.make_scene(num_kf=1, W=64, H=48, L=2, F=16, C=8, mask="ellipse", seed=3)
+    kf = kfs[0]
+    m = kf.video_mask.reshape(-1).astype(np.float64)
+    b = kf.dpt_map_bias.astype(np.float64)
+    want = np.sum((b * m) ** 2) / np.sum(m)
+    got = mapper.avg_squared_dpt_bias(kf)
+    assert abs(got - want) <= 1e-5 * want
+    assert abs(np.mean(b ** 2) - want) > 1e-2 * want  # the plain mean is something else here
