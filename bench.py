@@ -204,7 +204,7 @@ def measure_config(args, wl, torch, dist, sage, rank, world, local, stream, want
     kfs, pairs = build_scene(wl)
     K = len(kfs)
     ctx = sage.Context(local, stream=stream.cuda_stream)
-    need = local_ba.needed_keyframes(pairs, K, rank, world)
+    need = local_ba.needed_keyframes(pairs, rank, world)
     t_up = time.perf_counter()
     dkfs = [sage.DeviceKeyframe(ctx, k) if i in need else None for i, k in enumerate(kfs)]
     torch.cuda.synchronize()
@@ -232,11 +232,9 @@ def measure_config(args, wl, torch, dist, sage, rank, world, local, stream, want
     costs = []
     for _ in range(args.warmup):
         costs.append(lm_iteration())
-    # ---- device-resident timing
+    # ---- device-resident timing (factor kinds overlapping on forked streams: the product's normal mode)
     ba.set_state(poses0, codes0, scales0, EPS)
     state["damp"] = 1e-4
-    ba.profile(True)
-    ba.profile_read(reset=True)
     l0 = ctx.launch_count
     if sampler is not None and rank == 0:
         sampler.start()
@@ -254,6 +252,15 @@ def measure_config(args, wl, torch, dist, sage, rank, world, local, stream, want
     clocks = sampler.stop() if (sampler is not None and rank == 0) else None
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - l0
+    # ---- per-kind kernel times (CUDA events inside the library; the kinds run one after the other while profiling is on, so
+    # that the roofline of the photometric lineariser is that kernel's own duration): same state trajectory, separate pass
+    ba.set_state(poses0, codes0, scales0, EPS)
+    state["damp"] = 1e-4
+    ba.profile(True)
+    ba.profile_read(reset=True)
+    prof_steps = min(args.steps, 5)
+    for _ in range(prof_steps):
+        lm_iteration()
     prof = ba.profile_read(reset=True)
     ba.profile(False)
     # ---- end to end: state from / to pinned host memory every step
@@ -291,6 +298,7 @@ def measure_config(args, wl, torch, dist, sage, rank, world, local, stream, want
         dist.all_reduce(ll)
         launches = int(ll[0])
     return dict(ctx=ctx, ba=ba, kfs=kfs, dkfs=dkfs, pairs=pairs, ms=ms, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, launches=launches, prof=prof,
+                prof_steps=prof_steps,
                 clocks=clocks, costs=costs, shard=ba.shard_counts(), residuals=ba.num_residuals, upload_ms=upload_ms,
                 resident_keyframes=len(need), solver=ba.solver_info())
 
@@ -319,7 +327,7 @@ def summarize(wl, m, steps):
     out = {"workload": wl["name"], "value": 1e3 / ms_per_step, "unit": "LM iters/s", "ms_per_step": ms_per_step,
            "mresiduals_per_s": m["residuals"] / (ms_per_step * 1e-3) / 1e6, "residuals_per_iter": m["residuals"],
            "keyframes": wl["num_kf"], "ordered_pairs": len(m["pairs"]),
-           "kernel_ms_per_step": {k: v[0] / steps for k, v in m["prof"].items()},
+           "kernel_ms_per_step": {k: v[0] / m["prof_steps"] for k, v in m["prof"].items()},
            "solver": m["solver"], "lm_trace": [(float(a), float(b)) for a, b in m["costs"][-steps:]][:4]}
     if m["e2e_ms"]:
         out["e2e_value"] = 1e3 / (m["e2e_ms"] / steps)
@@ -393,7 +401,9 @@ def run_ours(args):
                             "CUDA Frame tensors"},
             "gpu_launches": m["launches"],
             "roofline": roofline_of(wl, m, args.steps, hbm, src),
-            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in m["prof"].items()},
+            "kernel_ms_per_step": {k: v[0] / m["prof_steps"] for k, v in m["prof"].items()},
+            "kernel_ms_note": "CUDA events inside the library in a separate pass with the factor kinds serialised (in the timed "
+                              "region they overlap on forked streams, so the sum here exceeds ms_per_step)",
             "solver": m["solver"],
             "clocks": m["clocks"],
             "lm_trace": [(float(a), float(b)) for a, b in m["costs"][-args.steps:]][:6],

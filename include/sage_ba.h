@@ -328,13 +328,15 @@ int sage_ba_problem_fix(sage_ba_problem *p, int kf, int fix_pose, int fix_scale)
  *   6K x 6K pose block forms in the trailing sub-matrix) -- O(dim^2) memory, library kernels;
  * 2 as 0 with the natural (temporal) elimination order. */
 int sage_ba_problem_set_solver(sage_ba_problem *p, int solver);
-/* Multi-GPU sharding, one process per GPU: the ordered pair (kf0 -> kf1) belongs to the rank that owns kf0, and keyframes are
- * owned in contiguous ranges, sage_ba_shard_owner(K, world, kf) = kf * world / K.  Call before adding factors.  Every rank adds
- * EVERY factor (the list defines the normal equations); a rank needs the device data only of the keyframes its own factors
- * touch (host of an owned pair: depth + samples + features; target: features + mask (+ depth for geometric factors)) and may
- * pass NULL for the others in sage_ba_problem_create. */
+/* Multi-GPU sharding, one process per GPU.  The distinct ordered pairs (kf0 -> kf1) of the factor list, sorted by (kf0, kf1), are
+ * cut into `world` equal runs and every factor of a pair belongs to the pair's rank (sage_ba_shard_plan): a keyframe's pairs are
+ * consecutive in that order, so its maps are read by one GPU (two at a cut), and the ranks' loads differ by at most one pair.
+ * Every rank adds EVERY factor (the list defines the normal equations); a rank needs the device data only of the keyframes its
+ * own pairs touch (host of an owned pair: depth + samples + features; target: features + mask (+ depth for geometric factors))
+ * and may pass NULL for the others in sage_ba_problem_create.  Call set_shard before the first linearisation. */
 int sage_ba_problem_set_shard(sage_ba_problem *p, int rank, int world);
-int sage_ba_shard_owner(int num_keyframes, int world, int kf);
+/* owner rank of each of `num_pairs` ordered pairs (any order, duplicates allowed) under the rule above */
+int sage_ba_shard_plan(int num_pairs, const int *pair_kf0, const int *pair_kf1, int world, int *owner);
 /* sage_ba_problem_lm_step re-uses the linearisation after a rejected step (the state did not move); always != 0 forces the full
  * iteration every time (what BASELINE's "LM iteration" metric counts). */
 int sage_ba_problem_set_relinearize_always(sage_ba_problem *p, int always);
@@ -388,7 +390,9 @@ int sage_ba_problem_cost(sage_ba_problem *p, int which, double *cost);
 int sage_ba_problem_accept(sage_ba_problem *p);
 
 /* CUDA-event timing of the launches inside linearize / evaluate / assemble / solve, per kind (ms summed and
- * launch counts since the last reset).  Used by bench.py for the roofline line; off by default. */
+ * launch counts since the last reset).  Used by bench.py for the roofline line; off by default.  While it is on, the three
+ * factor kinds run one after the other on the context's stream (they normally overlap on forked streams), so that a kind's
+ * time is its own. */
 enum
 {
   SAGE_BA_PROF_PHOTO_JAC = 0,

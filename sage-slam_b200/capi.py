@@ -103,7 +103,7 @@ SIGNATURES = {
     "sage_ba_problem_fix": (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
     "sage_ba_problem_set_solver": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_set_shard": (C.c_int, [vp, C.c_int, C.c_int]),
-    "sage_ba_shard_owner": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "sage_ba_shard_plan": (C.c_int, [C.c_int, c_int_p, c_int_p, C.c_int, c_int_p]),
     "sage_ba_problem_set_relinearize_always": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_set_deterministic": (C.c_int, [vp, C.c_int]),
     "sage_ba_problem_factor_offsets": (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),

@@ -226,6 +226,15 @@ void sage_ba_destroy(sage_ba_context *ctx)
     cublasDestroy(ctx->cublas);
   if (ctx->cusolver)
     cusolverDnDestroy(ctx->cusolver);
+  for (int q = 0; q < 2; ++q)
+  {
+    if (ctx->aux[q])
+      cudaStreamDestroy(ctx->aux[q]);
+    if (ctx->ev_join[q])
+      cudaEventDestroy(ctx->ev_join[q]);
+  }
+  if (ctx->ev_fork)
+    cudaEventDestroy(ctx->ev_fork);
   if (ctx->own_stream)
     cudaStreamDestroy(ctx->stream);
   delete ctx;

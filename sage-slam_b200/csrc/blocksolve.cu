@@ -369,35 +369,31 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
         }
         first_round = false;
         {
-          const int half = tid >> 7, t = tid & 127;
-          if (cur[half] >= 0 && t < T::TILES)
+          // A(i, p) -= L(i, j) L(p, j)^T on the fp64 tensor cores: mma.sync m8n8k4, one 8x8 tile of the destination at a time.
+          // Four warps per pair; a warp walks its tiles, SP / 4 DMMAs each.  Fragments straight from the k-major staging:
+          //   a (row g, k t) = At[(k0 + t) * SP + r0 + g],  b (k t, col g) = Bt[(k0 + t) * SP + c0 + g],  c (row g, cols 2t, 2t+1)
+          const int half = tid >> 7, w4 = (tid >> 5) & 3, g = lane >> 2, t4 = lane & 3;
+          if (cur[half] >= 0)
           {
-            const int tr = t / TQ, tc = t - tr * TQ;
-            const double *A = At + (size_t)(buf * 2 + half) * BS + tr * 4, *B = Bt + tc * 4;
-            double acc[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                acc[i][jj] = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < SP; ++k)
+            constexpr int T8 = SP / 8;
+            const double *A = At + (size_t)(buf * 2 + half) * BS;
+            double *Cd = P + (size_t)(m_pair_dst[cur[half]] - s0) * SP * SPP;
+            for (int tile = w4; tile < T8 * T8; tile += 4)
             {
-              const double2 a01 = *reinterpret_cast<const double2 *>(A + k * SP), a23 = *reinterpret_cast<const double2 *>(A + k * SP + 2);
-              const double2 b01 = *reinterpret_cast<const double2 *>(B + k * SP), b23 = *reinterpret_cast<const double2 *>(B + k * SP + 2);
-              const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+              const int r0 = (tile / T8) * 8, c0 = (tile % T8) * 8;
+              double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                  acc[i][jj] = fma(a[i], b[jj], acc[i][jj]);
+              for (int k0 = 0; k0 < SP; k0 += 4)
+              {
+                const double av = A[(k0 + t4) * SP + r0 + g], bv = Bt[(k0 + t4) * SP + c0 + g];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(d0), "+d"(d1)
+                             : "d"(av), "d"(bv));
+              }
+              double *c = Cd + (r0 + g) * SPP + c0 + 2 * t4;
+              c[0] -= d0;
+              c[1] -= d1;
             }
-            double *Cd = P + (size_t)(m_pair_dst[cur[half]] - s0) * SP * SPP + (tr * 4) * SPP + tc * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                Cd[i * SPP + jj] -= acc[i][jj]; // A(i, p) -= L(i, j) L(p, j)^T
           }
         }
         __syncthreads(); // the buffers just read are overwritten by the next prefetch / the next dependency

@@ -106,6 +106,10 @@ struct sage_ba_context
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // side streams of the batched problem: the three factor kinds of an iteration are independent launches, forked off the main
+  // stream and joined before the exchange / assembly (events without timing)
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
   std::string err;

@@ -1,8 +1,8 @@
 """Batched local bundle adjustment over the C ABI's problem object, plus the multi-GPU plumbing.
 
-One process per GPU.  The ordered pair (i -> j) belongs to the rank that owns keyframe i, keyframes are owned in
-contiguous ranges (`shard_owner`, the rule of sage_ba_shard_owner): a keyframe's maps are then read by one GPU for all of
-its pairs, and a rank uploads only the keyframes its factors touch (`needed_keyframes`).  Every rank linearises its factors
+One process per GPU.  The distinct ordered pairs (i -> j), sorted by (i, j), are cut into equal runs, one per rank
+(`shard_owners`, the rule of sage_ba_shard_plan): a keyframe's pairs are consecutive, so its maps are read by one GPU (two at a
+cut), the loads differ by at most one pair, and a rank uploads only the keyframes its pairs touch (`needed_keyframes`).  Every rank linearises its factors
 into ITS segment of the packed per-factor buffer [AtA | Atb | error | inliers]*, one in-place all-gather completes the buffer
 everywhere, and every rank assembles (fixed order) and solves (block Cholesky over keyframes) the same normal equations --
 the elimination is a 32-step dependency chain over the band of the covisibility graph, cheaper to repeat than to distribute
@@ -20,25 +20,30 @@ from .ops import Context, DeviceKeyframe, SageError, _f, _p
 F32 = np.float32
 
 
-def shard_owner(num_keyframes, world, kf):
-    """Rank that owns keyframe `kf` (and every ordered pair kf -> j): contiguous ranges, kf * world // K
-    (the rule of sage_ba_shard_owner)."""
-    if world <= 1:
-        return 0
-    return min(max(kf * world // num_keyframes, 0), world - 1)
+def shard_owners(pairs, world):
+    """Owner rank of every ordered pair (i, j): the distinct pairs, sorted by (i, j), are cut into `world` equal runs
+    (the rule of sage_ba_shard_plan).  Returns {(i, j): rank}."""
+    uniq = sorted(set((int(i), int(j)) for i, j in pairs))
+    P = len(uniq)
+    return {pr: (0 if world <= 1 else idx * world // P) for idx, pr in enumerate(uniq)}
 
 
-def shard_factors(factors, num_keyframes, rank, world):
-    """Indices of the factors (kind, i, j) owned by `rank`: owner(i) == rank."""
-    return [f for f, (_, i, _) in enumerate(factors) if shard_owner(num_keyframes, world, i) == rank]
+def shard_factors(factors, rank, world):
+    """Indices of the factors (kind, i, j) owned by `rank`."""
+    own = shard_owners([(i, j) for _, i, j in factors], world)
+    return [f for f, (_, i, j) in enumerate(factors) if own[(i, j)] == rank]
 
 
-def needed_keyframes(pairs, num_keyframes, rank, world):
-    """Keyframes whose device data `rank` needs: hosts and targets of the ordered pairs it owns."""
+def needed_keyframes(pairs, rank, world):
+    """Keyframes whose device data `rank` needs: hosts and targets of the ordered pairs it owns (at least one keyframe, so that
+    a rank without any pair still knows the shapes)."""
+    own = shard_owners(pairs, world)
     need = set()
-    for i, j in pairs:
-        if shard_owner(num_keyframes, world, i) == rank:
-            need.update((i, j))
+    for pr, r in own.items():
+        if r == rank:
+            need.update(pr)
+    if not need and own:
+        need.add(min(own)[0])
     return need
 
 
@@ -91,7 +96,8 @@ def assemble_dense(buf, factors, K, C_code, world=1):
     factors: list of (kind, i, j).  Used by the gloo tests and as documentation of the layout."""
     n = K * (7 + C_code)
     H, g, cost = np.zeros((n, n)), np.zeros(n), 0.0
-    offs, dims, _ = factor_layout([f[0] for f in factors], C_code, [shard_owner(K, world, f[1]) for f in factors], world)
+    own = shard_owners([(i, j) for _, i, j in factors], world)
+    offs, dims, _ = factor_layout([f[0] for f in factors], C_code, [own[(f[1], f[2])] for f in factors], world)
     for (kind, i, j), off, D in zip(factors, offs, dims):
         idx = np.array([variable_index(kind, i, j, c, K, C_code) for c in range(D)])
         A = np.asarray(buf[off:off + D * D], np.float64).reshape(D, D)

@@ -25,7 +25,7 @@ def run(rank, world, local, out, deterministic=True):
     stream = torch.cuda.Stream(device=local)
     with torch.cuda.stream(stream):
         ctx = sage.Context(local, stream=stream.cuda_stream)
-        need = local_ba.needed_keyframes(pairs, K, rank, world)
+        need = local_ba.needed_keyframes(pairs, rank, world)
         dk = [sage.DeviceKeyframe(ctx, k) if i in need else None for i, k in enumerate(kfs)]
         ba = sage.LocalBA(ctx, dk, rank=rank, world=world)
         ba.deterministic(deterministic)

@@ -49,7 +49,8 @@ def oracle_factor(kfs, factor, dtype=np.float32):
 def oracle_buffer(kfs, factors, owned=None, world=1):
     """Packed fp32 factor buffer (laid out for `world` ranks) with only the `owned` factor indices filled (others zero), like
     one rank's shard before the exchange."""
-    owners = [local_ba.shard_owner(len(kfs), world, f[1]) for f in factors]
+    own = local_ba.shard_owners([(i, j) for _, i, j in factors], world)
+    owners = [own[(f[1], f[2])] for f in factors]
     offs, dims, total = local_ba.factor_layout([f[0] for f in factors], PRM["C"], owners, world)
     buf = np.zeros(total, np.float32)
     for f, (fac, off, D) in enumerate(zip(factors, offs, dims)):

@@ -26,8 +26,8 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     kfs, pairs, factors = pc.build(4)
     K = len(kfs)
-    owned = local_ba.shard_factors(factors, K, rank, world)
-    need = local_ba.needed_keyframes(pairs, K, rank, world)
+    owned = local_ba.shard_factors(factors, rank, world)
+    need = local_ba.needed_keyframes(pairs, rank, world)
     # a rank only ever reads the keyframes its own pairs touch
     for f in owned:
         assert factors[f][1] in need and factors[f][2] in need
@@ -63,32 +63,41 @@ def test_four_rank_exchange_reproduces_single_rank(tmp_path):
 
 
 def test_sharding_is_a_partition_for_every_world_size():
-    """owner(i) = i * world // K: every factor has exactly one owner, keyframes are owned in contiguous ranges, a rank needs
-    only its own keyframes plus the band around them -- for the bench graph (32 keyframes, 3 back-connections, 180 ordered
-    pairs x 3 kinds) and awkward sizes."""
+    """Pairs sorted by (host, target) cut into equal runs: every factor has exactly one owner, all kinds of a pair share it, loads
+    differ by at most one pair, a rank needs only a band of keyframes -- for the bench graph (32 keyframes, 3 back-connections,
+    180 ordered pairs x 3 kinds) and awkward sizes, and the C library applies the same rule."""
+    import ctypes as C
+
     import sage_slam_b200 as sage
 
+    lib = sage.capi.load()
     for K, back in ((32, 3), (5, 2), (7, 6), (3, 1)):
         pairs = [(k, j) for k in range(K) for j in range(max(0, k - back), k)]
         pairs = [p for (a, b) in pairs for p in ((a, b), (b, a))]
         factors = [(kind, i, j) for kind in ("photo", "geo", "reproj") for (i, j) in pairs]
         for world in (1, 2, 3, 4, 8):
-            owned = [local_ba.shard_factors(factors, K, r, world) for r in range(world)]
+            owned = [local_ba.shard_factors(factors, r, world) for r in range(world)]
             assert sorted(f for o in owned for f in o) == list(range(len(factors)))
-            owners = [local_ba.shard_owner(K, world, k) for k in range(K)]
-            assert owners == sorted(owners) and owners[0] == 0 and owners[-1] == min(world, K) - 1 or K < world
+            own = local_ba.shard_owners(pairs, world)
+            loads = [sum(1 for r in own.values() if r == q) for q in range(world)]
+            assert max(loads) - min(loads) <= 1, (K, world, loads)
+            for f, (_, i, j) in enumerate(factors):  # all kinds of a pair on one rank
+                assert f in owned[own[(i, j)]]
             for r in range(world):
-                need = local_ba.needed_keyframes(pairs, K, r, world)
-                mine = [k for k in range(K) if owners[k] == r]
-                if mine:
-                    assert need <= set(range(max(0, mine[0] - back), min(K, mine[-1] + back + 1)))
-    # K = 32 on 8 ranks: 4 keyframes each, at most 4 + 2 * 3 keyframes resident per rank instead of 32
+                need = local_ba.needed_keyframes(pairs, r, world)
+                hosts = sorted({i for (i, j), q in own.items() if q == r})
+                if hosts:
+                    assert need <= set(range(max(0, hosts[0] - back), min(K, hosts[-1] + back + 1)))
+            pi = (C.c_int * len(pairs))(*[p[0] for p in pairs])
+            pj = (C.c_int * len(pairs))(*[p[1] for p in pairs])
+            out = (C.c_int * len(pairs))()
+            assert lib.sage_ba_shard_plan(len(pairs), pi, pj, world, out) == 0
+            assert list(out) == [own[p] for p in pairs]
+    # K = 32 on 8 ranks: 22 or 23 pairs each (180 / 8), at most 11 keyframes resident per rank instead of 32
     pairs = [p for k in range(32) for j in range(max(0, k - 3), k) for p in ((k, j), (j, k))]
-    assert max(len(local_ba.needed_keyframes(pairs, 32, r, 8)) for r in range(8)) == 10
-    # the C library uses the same rule
-    lib = sage.capi.load()
-    for K, world in ((32, 8), (5, 3), (7, 2), (3, 4)):
-        assert [lib.sage_ba_shard_owner(K, world, k) for k in range(K)] == [local_ba.shard_owner(K, world, k) for k in range(K)]
+    own = local_ba.shard_owners(pairs, 8)
+    assert sorted(set(sum(1 for r in own.values() if r == q) for q in range(8))) == [22, 23]
+    assert max(len(local_ba.needed_keyframes(pairs, r, 8)) for r in range(8)) <= 11
     # the packed layout: one [AtA | Atb | error | inliers] block per factor, geometric blocks wider; world > 1: equal segments
     offs, dims, total = local_ba.factor_layout(["photo", "geo", "reproj"], 32)
     assert dims == [45, 78, 45] and offs == [0, 45 * 45 + 45 + 2, 45 * 45 + 45 + 2 + 78 * 78 + 78 + 2]

@@ -95,7 +95,7 @@ def test_sharded_factor_buffers_equal_the_single_rank_buffer(sage_ctx, world):
     roffs, rdims, _ = local_ba.factor_layout([f[0] for f in factors], C)
     seen = set()
     for r in range(world):
-        need = local_ba.needed_keyframes(pairs, K, r, world)
+        need = local_ba.needed_keyframes(pairs, r, world)
         dk = [sage.DeviceKeyframe(sage_ctx, k) if i in need else None for i, k in enumerate(kfs)]
         ba = sage.LocalBA(sage_ctx, dk, rank=r, world=world)
         ba.deterministic(True)
@@ -110,7 +110,7 @@ def test_sharded_factor_buffers_equal_the_single_rank_buffer(sage_ctx, world):
         ba.linearize(reduce=False)
         part = ba.factor_buffer().copy()
         offs, _, owners = ba.factor_offsets()
-        owned = set(local_ba.shard_factors(factors, K, r, world))
+        owned = set(local_ba.shard_factors(factors, r, world))
         assert owned == {f for f, o in enumerate(owners) if o == r}
         lay, _, total = local_ba.factor_layout([f[0] for f in factors], C, owners, world)
         assert lay == offs and total == len(part)

@@ -121,8 +121,8 @@ def test_factor_packing_and_dense_assembly_layout():
     # geometric 1->2 couples code_1 with code_2
     c1, c2 = 6 * K + 1 * (C + 1), 6 * K + 2 * (C + 1)
     np.testing.assert_allclose(H[c1:c1 + C, c2:c2 + C], mats[1][0][12:12 + C, 12 + C:12 + 2 * C], rtol=1e-6)
-    # keyframe-owner sharding: with 3 keyframes on 3 ranks every rank owns the pairs hosted by its keyframe
-    assert [local_ba.shard_factors(factors, K, r, 3) for r in range(3)] == [[0], [1], [2]]
+    # pair sharding: three distinct pairs on 3 ranks, one each (sorted by host keyframe)
+    assert [local_ba.shard_factors(factors, r, 3) for r in range(3)] == [[0], [1], [2]]
 
 
 def test_factor_partition_and_nearest_psd_match_oracle():
