@@ -377,8 +377,12 @@ def run_ours(args):
                                             "(scene generation for 256 keyframes takes minutes on the host)"
                 except Exception:
                     pass
-                incumbent = incumbent_extras(args, m["kfs"], wl)
+                pass
 
+    if rank == 0 and world == 1 and not args.small and args.config == 3 and not args.no_extras:
+        # after the CUDA work of this process is done (the arms run in child processes on the same GPU)
+        torch.cuda.synchronize()
+        incumbent = incumbent_extras(args, m["kfs"], wl)
     if rank == 0:
         ms_per_step = m["ms"] / args.steps
         line = {
@@ -604,7 +608,7 @@ def _ref_gpu_pairs(kfs, wl, mod, impl, steps, warmup):
                             R["loc64"].to(torch.int32), R["homo"], a["scale0"], cam, a["eps"], a["geo_loss"], a["geo_weight"])
 
     preps = [prep(p) for p in pairs[:4]]
-    for i in range(max(warmup, 1)):
+    for i in range(max(warmup, len(preps))):  # every pair once: per-frame setup (the shim's keyframe cache) is not per-pair cost
         one_pair(*preps[i % len(preps)])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -629,30 +633,27 @@ def _subsample(kfs, n, seed=4321):
 
 
 def incumbent_extras(args, kfs, wl):
-    """The incumbent beside the headline, in the same process right after it (N = 1 only): the reference's OWN CUDA kernels
-    (oracle/_ref, compiled unmodified from the reference's sources) and the df:: shim over libsage_ba.so, pair by pair as
-    core/gtsam/*_factor.cpp calls them, dense and at the reference's native 3072 sample points.  Skipped with a note when the
+    """The incumbent beside the headline (N = 1 only): the reference's OWN CUDA kernels (oracle/_ref, compiled unmodified from the
+    reference's sources) and the df:: shim over libsage_ba.so, pair by pair as core/gtsam/*_factor.cpp calls them, dense and at
+    the reference's native 3072 sample points.  Each arm runs in its OWN process (`bench.py --impl reference-gpu|shim`): both
+    modules define the same df:: symbols, loaded together the second would bind to the first one's.  Skipped with a note when the
     prebuilt modules are not in the tree (they are built where /root/reference exists and travel with the snapshot)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     out = {}
     try:
-        import build_ref
-
-        sub = kfs[:4]
-        sparse = _subsample(sub, 3072)
-        npairs = 180
-        for label, loader in (("ref_gpu", build_ref.load), ("shim", build_ref.load_shim)):
-            mod = loader(wl["C"], wl["F"])
-            d = _ref_gpu_pairs(sub, wl, mod, label, 10, 2)
-            n = _ref_gpu_pairs(sparse, wl, mod, label, 20, 3)
-            out[f"{label}_ms_per_pair"] = d
-            out[f"{label}_ms_per_pair_n3072"] = n
-        out["ref_gpu_lm_iters_per_s"] = 1e3 / (out["ref_gpu_ms_per_pair"] * npairs)
+        for label, impl in (("ref_gpu", "reference-gpu"), ("shim", "shim")):
+            for key, extra, steps in (("ms_per_pair", [], "10"), ("ms_per_pair_n3072", ["--ref-samples", "3072"], "20")):
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", impl, "--steps", steps, "--warmup", "2"] + extra,
+                                   capture_output=True, text=True, timeout=600)
+                line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                if r.returncode != 0 or not line:
+                    raise RuntimeError((r.stderr or r.stdout)[-300:])
+                out[f"{label}_{key}"] = json.loads(line[-1])["ms_per_pair"]
+        out["ref_gpu_lm_iters_per_s"] = 1e3 / (out["ref_gpu_ms_per_pair"] * 180)
         out["incumbent_note"] = ("ref_gpu = the reference's own CUDA kernels on this GPU, one ordered pair per call (photo+geo "
                                  "linearisation + error evaluation; no solve), x180 pairs for an iteration; shim = the same calls "
-                                 "through integration/df_sage_shim.cpp")
+                                 "through integration/df_sage_shim.cpp; each in its own process")
     except Exception as e:  # prebuilt modules absent or not loadable: say so, never fail the bench line
-        out["incumbent_note"] = f"reference-GPU / shim arms unavailable: {type(e).__name__}: {e}"
+        out["incumbent_note"] = f"reference-GPU / shim arms unavailable: {type(e).__name__}: {str(e)[:200]}"
     return out
 
 

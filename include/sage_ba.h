@@ -85,6 +85,10 @@ typedef struct sage_ba_keyframe_desc
   const int64_t *sampled_locations_1d; /* [N] int64    Frame::sampled_locations_1d (may be NULL)  */
   const float *sampled_locations_homo; /* [N, 3]       Frame::sampled_locations_homo              */
   int num_samples;                     /* N                                                       */
+  int borrow_depth;                    /* != 0 (DEVICE memory, dpt_jac_code already pixel-major: strides (C, 1)): dpt_map_bias,
+                                          dpt_jac_code and video_mask are used IN PLACE, nothing is copied or allocated; the caller
+                                          keeps them alive and unchanged while the handle is used.  For per-call views such as KF1
+                                          of the reference's geometric operators (geometric_factor.cpp:340-342).               */
 } sage_ba_keyframe_desc;
 
 int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *desc, sage_ba_keyframe **kf);

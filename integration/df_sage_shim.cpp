@@ -289,6 +289,31 @@ long cache_size_locked()
   return (long)g_cache.size();
 }
 
+// KF1 of the geometric operators arrives as per-call tensors (a state-dependent depth map and a fresh pixel-major copy of the
+// basis, gtsam/geometric_factor.cpp:340-342): a handle that BORROWS them (no copy, no allocation, not cached) lives for the call
+KfPtr borrowed_depth_keyframe(const at::Tensor &bias, const at::Tensor &basis_hwc, const at::Tensor &mask, const df::PinholeCamera<float> &cam0,
+                              int C)
+{
+  sage_ba_keyframe_desc d{};
+  d.memory = SAGE_BA_DEVICE;
+  d.height = (int)cam0.height();
+  d.width = (int)cam0.width();
+  d.levels = 1;
+  d.feat_channels = 16;
+  d.code_size = C;
+  d.camera = {cam0.fx(), cam0.fy(), cam0.u0(), cam0.v0(), cam0.width(), cam0.height()};
+  d.dpt_map_bias = bias.data_ptr<float>();
+  d.dpt_jac_code = basis_hwc.data_ptr<float>();
+  d.jac_stride_row = C;
+  d.jac_stride_col = 1;
+  d.video_mask = mask.data_ptr<float>();
+  d.borrow_depth = 1;
+  sage_ba_keyframe *kf = nullptr;
+  sage_ba_context *c = ctx();
+  SAGE_OK(sage_ba_keyframe_create(c, &d, &kf));
+  return KfPtr(kf, KfDeleter{c});
+}
+
 at::Tensor to_dev(const float *p, std::vector<int64_t> shape, const at::Tensor &like)
 {
   return torch::from_blob(const_cast<float *>(p), shape, at::kFloat).clone().to(like.device());
@@ -445,7 +470,8 @@ float geometric_error_calculate(const at::Tensor rotation, const at::Tensor tran
   static thread_local at::Tensor zero_basis; // the error-only operator needs no basis of KF1
   if (!zero_basis.defined() || zero_basis.size(0) != HW || zero_basis.device() != dpt_map_1.device())
     zero_basis = torch::zeros({HW, (long)CS}, dpt_map_1.options());
-  KfPtr kf1 = keyframe({{}, {}, dpt_map_1.reshape({-1}), zero_basis, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*key_bias=*/false);
+  const at::Tensor bias1 = dpt_map_1.to(at::kFloat).reshape({-1}).contiguous(), mask1 = valid_mask_1.to(at::kFloat).contiguous();
+  KfPtr kf1 = borrowed_depth_keyframe(bias1, zero_basis, mask1, camera, CS);
   const auto R = hostf(rotation), t = hostf(translation), code = hostf(code_0);
   const std::vector<float> code1(CS, 0.f);
   float err = 0.f;
@@ -466,9 +492,10 @@ void geometric_jac_error_calculate(at::Tensor &AtA, at::Tensor &Atb, float &erro
 {
   KfPtr kf0 = keyframe({{}, {}, flatten_dpt_map_bias_0, flatten_dpt_jac_code_0, {}, sampled_locations_1d_0, sampled_locations_homo_0}, camera,
                        1, 16, CS);
-  const at::Tensor unscaled = (dpt_map_1 / scale_1).reshape({-1}).contiguous();
-  const at::Tensor basis1 = dpt_jac_code_1.reshape({-1, (long)CS}); // [H, W, C] -> [HW, C]
-  KfPtr kf1 = keyframe({{}, {}, unscaled, basis1, valid_mask_1, {}, {}}, camera, 1, 16, CS, /*key_bias=*/false);
+  const at::Tensor unscaled = (dpt_map_1 / scale_1).to(at::kFloat).reshape({-1}).contiguous();
+  const at::Tensor basis1 = dpt_jac_code_1.to(at::kFloat).reshape({-1, (long)CS}).contiguous(); // [H, W, C] -> [HW, C], as handed over
+  const at::Tensor mask1 = valid_mask_1.to(at::kFloat).contiguous();
+  KfPtr kf1 = borrowed_depth_keyframe(unscaled, basis1, mask1, camera, CS);
   constexpr int D = 14 + 2 * CS;
   std::vector<float> A(D * D), b(D);
   const HostPack h = hostpack({rotation10, translation10, rotation0, translation0, rotation1, translation1, code_0});

@@ -24,7 +24,7 @@ class KeyframeDesc(C.Structure):
                 ("feat_channels", C.c_int), ("code_size", C.c_int), ("camera", Camera),
                 ("feat_map", vp), ("feat_map_pyramid", vp), ("feat_map_grad_pyramid", vp), ("dpt_map_bias", vp), ("dpt_jac_code", vp),
                 ("jac_stride_row", C.c_long), ("jac_stride_col", C.c_long), ("video_mask", vp),
-                ("sampled_locations_1d", vp), ("sampled_locations_homo", vp), ("num_samples", C.c_int)]
+                ("sampled_locations_1d", vp), ("sampled_locations_homo", vp), ("num_samples", C.c_int), ("borrow_depth", C.c_int)]
 
 
 class TrackerConfig(C.Structure):

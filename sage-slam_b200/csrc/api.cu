@@ -290,6 +290,18 @@ int sage_ba_keyframe_create(sage_ba_context *ctx, const sage_ba_keyframe_desc *d
     // INTEGRATION.md builds partial keyframes from what one call is given); the entry points check for what they need
     SAGE_CHECK(d->feat_map_pyramid || d->feat_map || d->dpt_map_bias, "a keyframe needs feature maps or depth data");
     SAGE_CHECK(!d->feat_map || d->video_mask, "building the pyramid on the device needs video_mask");
+    if (d->borrow_depth)
+    {
+      SAGE_CHECK(!host && d->dpt_map_bias && d->dpt_jac_code && d->video_mask && d->jac_stride_row == C && d->jac_stride_col == 1 &&
+                     !d->feat_map && !d->feat_map_pyramid && N == 0,
+                 "borrow_depth needs device bias / pixel-major basis / mask and nothing else");
+      kf->bias = const_cast<float *>(d->dpt_map_bias);
+      kf->basis = const_cast<float *>(d->dpt_jac_code);
+      kf->mask = const_cast<float *>(d->video_mask);
+      kf->borrowed_depth = true;
+      *out = kf;
+      return 0;
+    }
     if (d->feat_map_pyramid || d->feat_map)
       SAGE_CUDA(cudaMalloc(&kf->fg, sizeof(float) * SP * 3 * F));
     if (d->video_mask)
@@ -401,9 +413,12 @@ void sage_ba_keyframe_destroy(sage_ba_context *ctx, sage_ba_keyframe *kf)
   if (ctx)
     cudaSetDevice(ctx->device);
   cudaFree(kf->fg);
-  cudaFree(kf->bias);
-  cudaFree(kf->basis);
-  cudaFree(kf->mask);
+  if (!kf->borrowed_depth)
+  {
+    cudaFree(kf->bias);
+    cudaFree(kf->basis);
+    cudaFree(kf->mask);
+  }
   cudaFree(kf->loc1d);
   cudaFree(kf->homo);
   cudaFree(kf->sfeat);

@@ -339,8 +339,10 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
         }
         return -1;
       };
-      block_copy_async<SP * SP, NT>(Bt, Lblk + (size_t)m_dep_blk[dep] * BS, tid);
       int cur[2] = {next_pair(), -1};
+      if (!first && cur[0] < 0)
+        continue; // nothing of this dependency lands in the resident chunk (uniform: every thread reads the same lists)
+      block_copy_async<SP * SP, NT>(Bt, Lblk + (size_t)m_dep_blk[dep] * BS, tid);
       cur[1] = cur[0] >= 0 ? next_pair() : -1;
       int buf = 0;
       for (int h = 0; h < 2; ++h)
@@ -708,37 +710,126 @@ void BlockSystem::build(int K_, int C_, const std::vector<FactorMeta> &metas, co
     if (links.insert({a, b}).second)
       span.push_back(b - a);
   }
-  // ---- elimination order
-  order.clear();
-  if (order_mode == 1 || span.empty())
-    for (int u = 0; u < K; ++u)
-      order.push_back(u);
-  else
+  // ---- elimination order: three candidates -- natural (temporal), nested dissection over the keyframe index line (band
+  // graphs: separators are b consecutive keyframes, subtrees run concurrently) and minimum degree (graphs with long-range
+  // links: far less fill) -- compared by a model of the critical path of the factorisation (per column: a fixed cost, the rows
+  // it solves, and the update rounds it must wait for from its last dependency); the cheapest wins.
+  auto symbolic = [&](const std::vector<int> &ord, std::vector<std::set<int>> &cs_out, double &crit) {
+    std::vector<int> ps(K);
+    for (int q = 0; q < K; ++q)
+      ps[ord[q]] = q;
+    cs_out.assign(K, {});
+    for (const auto &l : links)
+    {
+      const int a = ps[l.first], b = ps[l.second];
+      cs_out[std::min(a, b)].insert(std::max(a, b));
+    }
+    for (int q = 0; q < K; ++q)
+      if (!cs_out[q].empty())
+      {
+        auto it = cs_out[q].begin();
+        const int parent = *it;
+        for (++it; it != cs_out[q].end(); ++it)
+          cs_out[parent].insert(*it);
+      }
+    std::vector<std::vector<int>> dp(K);
+    for (int j = 0; j < K; ++j)
+      for (int r : cs_out[j])
+        dp[r].push_back(j);
+    std::vector<double> cost(K, 0.0);
+    crit = 0.0;
+    for (int q = 0; q < K; ++q)
+    {
+      double before = 0.0;
+      int pairs_last = 0;
+      for (int j : dp[q])
+      {
+        if (cost[j] > before)
+        {
+          before = cost[j];
+          pairs_last = 0;
+          for (int i : cs_out[j])
+            pairs_last += i >= q ? 1 : 0;
+        }
+      }
+      const int chunks = ((int)cs_out[q].size() + 7) / 7; // a column wider than the resident panel walks its dependencies again
+      cost[q] = before + 16.0 + 0.5 * (double)cs_out[q].size() + 1.4 * ((pairs_last + 1) / 2) + 3.0 * (chunks - 1) * (double)dp[q].size();
+      crit = std::max(crit, cost[q]);
+    }
+  };
+  std::vector<std::vector<int>> candidates;
   {
-    std::sort(span.begin(), span.end());
-    const int b = std::max(1, span[std::min(span.size() - 1, (size_t)(0.9 * span.size()))]); // band of the temporal links
-    nested_dissection(0, K, b, order);
+    std::vector<int> nat(K);
+    for (int u = 0; u < K; ++u)
+      nat[u] = u;
+    candidates.push_back(nat);
+    if (order_mode != 1 && !span.empty())
+    {
+      std::vector<int> sp = span;
+      std::sort(sp.begin(), sp.end());
+      const int b = std::max(1, sp[std::min(sp.size() - 1, (size_t)(0.9 * sp.size()))]); // band of the temporal links
+      std::vector<int> ndo;
+      nested_dissection(0, K, b, ndo);
+      candidates.push_back(ndo);
+      // minimum degree on the keyframe graph (exact, with explicit fill; K is a few hundred at most)
+      std::vector<std::set<int>> adj(K);
+      for (const auto &l : links)
+      {
+        adj[l.first].insert(l.second);
+        adj[l.second].insert(l.first);
+      }
+      std::vector<char> gone(K, 0);
+      std::vector<int> md;
+      for (int step = 0; step < K; ++step)
+      {
+        int best = -1;
+        for (int u = 0; u < K; ++u)
+          if (!gone[u] && (best < 0 || adj[u].size() < adj[best].size()))
+            best = u;
+        const std::vector<int> nb(adj[best].begin(), adj[best].end());
+        for (int a : nb)
+        {
+          adj[a].erase(best);
+          for (int b2 : nb)
+            if (a != b2)
+              adj[a].insert(b2);
+        }
+        gone[best] = 1;
+        md.push_back(best);
+      }
+      candidates.push_back(md);
+    }
+  }
+  std::vector<std::set<int>> cs;
+  {
+    double best = 0.0;
+    int pick = 0;
+    for (size_t c = 0; c < candidates.size(); ++c)
+    {
+      std::vector<std::set<int>> tmp;
+      double crit = 0.0;
+      symbolic(candidates[c], tmp, crit);
+      if (c == 0 || crit < best)
+      {
+        best = crit;
+        pick = (int)c;
+      }
+    }
+    order = candidates[pick];
+    order_mode = order_mode == 1 ? 1 : pick; // 0 natural won, 1 forced natural, 2 nested dissection, ... reported by solver_info
+    double crit = 0.0;
+    symbolic(order, cs, crit);
+    model_us = crit;
   }
   pos.assign(K, 0);
   for (int q = 0; q < K; ++q)
     pos[order[q]] = q;
-  // ---- symbolic factorisation in position space
-  std::vector<std::set<int>> cs(K);
   std::set<std::pair<int, int>> orig; // (row pos, col pos) of assembled sub-diagonal blocks
   for (const auto &l : links)
   {
     const int a = pos[l.first], b = pos[l.second];
-    cs[std::min(a, b)].insert(std::max(a, b));
     orig.insert({std::max(a, b), std::min(a, b)});
   }
-  for (int q = 0; q < K; ++q)
-    if (!cs[q].empty())
-    {
-      auto it = cs[q].begin();
-      const int parent = *it;
-      for (++it; it != cs[q].end(); ++it)
-        cs[parent].insert(*it);
-    }
   std::vector<int> h_col_ptr(K + 1, 0), h_rowpos, h_blk;
   for (int q = 0; q < K; ++q)
   {

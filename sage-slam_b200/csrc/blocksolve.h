@@ -62,7 +62,8 @@ struct BlockSystem
   int K = 0, C = 0, S = 0, SP = 0;
   int nblocks = 0;          // K diagonal + sub-diagonal blocks including fill
   int norig = 0;            // assembled blocks (diagonal + one per linked keyframe pair)
-  int order_mode = 0;       // 0 nested dissection over the keyframe index line, 1 natural order
+  int order_mode = 0;       // in: 1 forces the natural order; out: the candidate that won (0 natural, 1 forced, 2.. see build)
+  double model_us = 0.0;    // modelled critical path of the factorisation with the chosen order
   int depth = 0;            // longest dependency chain of the elimination (critical path in block columns)
   long fill_blocks = 0;
   std::vector<int> order, pos;

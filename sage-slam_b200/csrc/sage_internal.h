@@ -150,6 +150,7 @@ struct sage_ba_keyframe
   int *loc1d_s = nullptr;
   float4 *homo_s = nullptr;
   float *sfeat_s = nullptr;
+  bool borrowed_depth = false; // bias / basis / mask alias the caller's device memory (sage_ba_keyframe_desc.borrow_depth)
 };
 namespace sage
 {
