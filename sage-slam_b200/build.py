@@ -49,6 +49,10 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, objdir=None):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(run, jobs))
+    probe_src, probe = os.path.join(CSRC, "tc_probe.cu"), os.path.join(LIBDIR, "tc_probe")
+    if lib == LIB and (force or _newer(probe_src, probe) or os.path.getmtime(probe) < hdr_time):
+        # known-answer test binary of the tcgen05 conventions (tests/test_gpu_tcgen05.py runs it on the B200)
+        run(["nvcc"] + [f for f in NVCC_FLAGS if f not in ("-Xcompiler", "-fPIC", "-fvisibility=default")] + ["-I" + CSRC, "-o", probe, probe_src])
     if jobs or not os.path.exists(lib):
         run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lcublas", "-lcusolver", "-lcudart", "-ldl"])
     return lib

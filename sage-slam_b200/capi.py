@@ -65,6 +65,7 @@ SIGNATURES = {
     "sage_ba_launch_count": (C.c_long, [vp]),
     "sage_ba_synchronize": (C.c_int, [vp]),
     "sage_ba_stream": (vp, [vp]),
+    "sage_ba_set_geometric_tcgen05": (C.c_int, [C.c_int]),
     "sage_ba_keyframe_create": (C.c_int, [vp, C.POINTER(KeyframeDesc), C.POINTER(vp)]),
     "sage_ba_keyframe_destroy": (None, [vp, vp]),
     "sage_ba_keyframe_set_bias": (C.c_int, [vp, vp, vp, C.c_int]),

@@ -58,6 +58,8 @@ CamPyr make_campyr(const sage_ba_camera &cam, int levels, sage_ba_camera *cams_o
 static int pick_slices(const sage_ba_context *ctx, int N, int samples_per_step)
 {
   const int steps = (N + samples_per_step - 1) / samples_per_step;
+  if (const char *e = getenv("SAGE_BA_SLICES")) // diagnostics: accumulation-length studies
+    return std::max(1, std::min(steps, atoi(e)));
   return std::max(1, std::min(steps, 3 * ctx->num_sms));
 }
 
@@ -70,7 +72,7 @@ static void run_photo_single(sage_ba_context *ctx, int mode, int F, int C, const
   // every warp of a CTA should see a few 32-sample batches so the end-of-CTA reduction is amortised
   const int slices = pick_slices(ctx, f.N, 4 * photo_samples_per_cta());
   const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
-  float *partH = ctx->partH.ensure(jac ? (size_t)slices * WP * WP : 4);
+  float *partH = ctx->partH.ensure((size_t)slices * photo_partial_floats(mode, C));
   float *partE = ctx->partE.ensure((size_t)slices * 2);
   float *out = ctx->out.ensure(nout);
   PhotoFactor *df = reinterpret_cast<PhotoFactor *>(ctx->factor.ensure(sizeof(PhotoFactor) > 1024 ? sizeof(PhotoFactor) : 1024));
@@ -243,6 +245,7 @@ void sage_ba_destroy(sage_ba_context *ctx)
 const char *sage_ba_last_error(const sage_ba_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 long sage_ba_launch_count(const sage_ba_context *ctx) { return ctx ? ctx->launches : 0; }
 void *sage_ba_stream(const sage_ba_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int sage_ba_set_geometric_tcgen05(int on) { return sage::geo_set_tc(on); }
 
 int sage_ba_synchronize(sage_ba_context *ctx)
 {
@@ -642,7 +645,7 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
   const int sps = (32 / (C / 4)) * (SAGE_CTA / 32);
   const int slices = pick_slices(ctx, f.N, sps);
   const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
-  float *partH = ctx->partH.ensure(jac ? (size_t)slices * WP * WP : 4);
+  float *partH = ctx->partH.ensure((size_t)slices * geo_partial_floats(jac, C));
   float *partE = ctx->partE.ensure((size_t)slices * 2);
   float *out = ctx->out.ensure(nout);
   GeoFactor *df = reinterpret_cast<GeoFactor *>(ctx->factor.ensure(1024));

@@ -117,6 +117,9 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
 #ifndef PH_UNROLL_ERR
 #define PH_UNROLL_ERR 8 // error-only kernels fetch 5 lines per sample-level instead of 13: twice the samples in flight (2.67 -> 2.50 ms)
 #endif
+#ifndef PH_FLUSH
+#define PH_FLUSH 4 // batches of 32 samples per warp between two flushes of the tensor-core accumulators (MmaSyrk::flush_tiles)
+#endif
 #ifndef PH_ILV
 #define PH_ILV 1 // gather step i serves samples i*NG + q (x-adjacent samples in ONE instruction: their taps share 128-byte lines at levels >= 1)
 #endif
@@ -137,7 +140,7 @@ __device__ __forceinline__ void reduce_scatter8(float (&v)[8], int gl, float (&o
 // serve both, there is no second code path.
 // ------------------------------------------------------------------------------------------------
 #ifndef PH_WIN_KB_JAC
-#define PH_WIN_KB_JAC (PH_HALF ? 48 : 64) // window bytes per CTA: 3 CTAs/SM with the half-size row staging, 2 with the full one
+#define PH_WIN_KB_JAC 48 // window bytes per CTA: with the row staging and the second-level accumulators two CTAs fit an SM
 #endif
 #ifndef PH_WIN_KB_ERR
 #define PH_WIN_KB_ERR 52 // error-only kernels have no row staging: 4 CTAs/SM
@@ -256,6 +259,19 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
   if constexpr (T::kJac)
     syrk.init();
   float err_acc = 0.f, inl_acc = 0.f;
+  // second-level accumulator of this warp (fragment order, dynamic shared memory behind the staged variant's window): the
+  // tensor-core accumulators are folded into it every PH_FLUSH batches, see MmaSyrk::flush_frag
+  constexpr int kAccF4 = MmaSyrk<WP>::NTILES * 32;
+  float4 *acc_s = reinterpret_cast<float4 *>(win + (STG ? WIN_PX * 3 * F : 0));
+  float4 *acc_w = acc_s + (size_t)warp * kAccF4;
+  int nacc = 0;
+  if constexpr (T::kJac)
+  {
+    for (int i = lane; i < kAccF4; i += 32)
+      acc_w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+  }
+  (void)acc_w;
 
   // per-level scale of the value(s) this lane accumulates: [Gxx Gxy Gyy bx by e - -] -> w_l * {fx fx, fx fy, fy fy, fx, fy, 1}
   int selA[VPL], selB[VPL]; // 0: 1, 1: fx_l, 2: fy_l
@@ -606,13 +622,23 @@ photo_kernel(const PhotoFactor *__restrict__ factors, const __grid_constant__ Ca
         __syncwarp();
       }
     }
+    if constexpr (T::kJac)
+    {
+      if (++nacc == PH_FLUSH) // 3 * ROWS / 8 mma per tile, level and batch since the last flush
+      {
+        syrk.flush_frag(acc_w, lane);
+        nacc = 0;
+      }
+    }
   }
 
   const size_t slot = (size_t)blockIdx.y * gridDim.x + blockIdx.x; // partials are indexed by launch-local factor
   if constexpr (T::kJac)
   {
+    if (nacc)
+      syrk.flush_frag(acc_w, lane);
     __syncthreads();
-    syrk.store_cta(Y, partH + slot * (WP * WP), warp, lane, PH_WARPS);
+    MmaSyrk<WP>::store_frags(acc_s, partH + slot * (WP * WP), PH_WARPS); // upper triangle of the CTA's WP x WP partial
   }
   const float e = block_sum(err_acc, red);
   const float c = block_sum(inl_acc, red);
@@ -709,18 +735,27 @@ constexpr size_t photo_window_bytes()
   return (size_t)((MODE == PH_MAP_JAC || MODE == PH_TRK_JAC) ? PH_WIN_KB_JAC : PH_WIN_KB_ERR) * 1024;
 }
 
+// dynamic shared memory: the staged variant's window, then (lineariser modes) the warps' second-level accumulators
+template <int F, int C, int MODE, bool STG>
+constexpr size_t photo_dyn_bytes()
+{
+  constexpr bool jac = (MODE == PH_MAP_JAC || MODE == PH_TRK_JAC);
+  constexpr int WP = (MODE == PH_MAP_JAC || MODE == PH_MAP_ERR) ? 8 + C : 8;
+  return (STG ? photo_window_bytes<F, C, MODE>() : 0) + (jac ? (size_t)PH_WARPS * MmaSyrk<WP>::NTILES * 32 * sizeof(float4) : 0);
+}
+
 template <int F, int C, int MODE, bool STG>
 static void launch_photo_t(const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH, float *partE,
                            float *out, int out_stride, int D, cudaStream_t stream)
 {
   dim3 grid(slices, nfactors);
-  const size_t dyn = STG ? photo_window_bytes<F, C, MODE>() : 0;
-  if constexpr (STG)
+  constexpr size_t dyn = photo_dyn_bytes<F, C, MODE, STG>();
+  if constexpr (dyn != 0)
   {
     static bool once = false; // per instantiation; the attribute is per device function, setting it twice is harmless
     if (!once)
     {
-      cudaFuncSetAttribute(photo_kernel<F, C, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+      cudaFuncSetAttribute(photo_kernel<F, C, MODE, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
       once = true;
     }
   }
@@ -753,6 +788,12 @@ static void launch_photo_fc(int mode, bool staged, const PhotoFactor *factors, i
 
 int photo_row_width(int mode, int C) { return (mode == PH_MAP_JAC || mode == PH_MAP_ERR) ? 8 + C : 8; }
 int photo_samples_per_cta() { return PH_WARPS * 32; }
+// floats of one CTA's J^T J partial
+size_t photo_partial_floats(int mode, int C)
+{
+  const size_t WP = photo_row_width(mode, C);
+  return (mode == PH_MAP_JAC || mode == PH_TRK_JAC) ? WP * WP : 4;
+}
 
 // resident CTAs per SM of the kernel the given configuration launches (occupancy API); 0 for an unsupported (F, C)
 int photo_ctas_per_sm(int mode, int F, int C, bool staged)
@@ -763,11 +804,16 @@ int photo_ctas_per_sm(int mode, int F, int C, bool staged)
     if (staged && (MM == PH_MAP_JAC || MM == PH_MAP_ERR))                                                                       \
     {                                                                                                                           \
       cudaFuncSetAttribute(photo_kernel<FF, CC, MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,                         \
-                           (int)photo_window_bytes<FF, CC, MM>());                                                              \
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, true>, PH_CTA, photo_window_bytes<FF, CC, MM>()); \
+                           (int)photo_dyn_bytes<FF, CC, MM, true>());                                                           \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, true>, PH_CTA, photo_dyn_bytes<FF, CC, MM, true>()); \
     }                                                                                                                           \
     else                                                                                                                        \
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, false>, PH_CTA, 0);                            \
+    {                                                                                                                           \
+      if (photo_dyn_bytes<FF, CC, MM, false>() != 0)                                                                            \
+        cudaFuncSetAttribute(photo_kernel<FF, CC, MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                             (int)photo_dyn_bytes<FF, CC, MM, false>());                                                        \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, photo_kernel<FF, CC, MM, false>, PH_CTA, photo_dyn_bytes<FF, CC, MM, false>()); \
+    }                                                                                                                           \
   }
 #define SAGE_OCC(FF, CC)                                     \
   if (F == FF && C == CC)                                    \

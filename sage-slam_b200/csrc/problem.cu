@@ -724,9 +724,12 @@ static void problem_build(sage_ba_problem *p)
     if (const char *e = getenv("SAGE_BA_SLICES_GEO_ERR"))
       p->slices_geo_err = std::max(1, atoi(e));
   }
-  const int WPp = 8 + C, WPg = 16 + 2 * C;
-  p->partH.ensure(std::max<size_t>((size_t)p->n_photo * p->slices_photo * WPp * WPp, 4));
-  p->partHg.ensure(std::max<size_t>((size_t)p->n_geo * p->slices_geo * WPg * WPg, 4));
+  if (getenv("SAGE_BA_DEBUG"))
+    fprintf(stderr, "[sage_ba] slices: photo %d / %d (err), geo %d / %d (err); CTAs per SM: photo %d, geo %d (tcgen05 %d)\n", p->slices_photo,
+            p->slices_photo_err, p->slices_geo, p->slices_geo_err, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), geo_ctas_per_sm(true, C),
+            (int)geo_uses_tc(true, C));
+  p->partH.ensure(std::max<size_t>((size_t)p->n_photo * p->slices_photo * photo_partial_floats(PH_MAP_JAC, C), 4));
+  p->partHg.ensure(std::max<size_t>((size_t)p->n_geo * p->slices_geo * geo_partial_floats(true, C), 4));
   p->partE.ensure(std::max<size_t>(2 * (size_t)p->n_photo * std::max(p->slices_photo, p->slices_photo_err), 4));
   p->partEg.ensure(std::max<size_t>(2 * (size_t)p->n_geo * std::max(p->slices_geo, p->slices_geo_err), 4));
   const int n = p->dim();

@@ -487,6 +487,91 @@ struct MmaSyrk
       }
   }
 
+  // Cut the accumulation chain.  The tensor core adds into the fp32 accumulator with truncation, not round-to-nearest: every
+  // mma loses about a third of an ulp of the running sum, a bias of -3e-8 per instruction that does not average out (measured on
+  // sm_100a: 30720 chained instructions put -1e-3 on the diagonal of J^T J against the fp64 sum).  So every few hundred
+  // instructions the tiles are added, with ordinary fp32 adds, to a second accumulator that only this warp touches and the
+  // tensor-core accumulators restart from zero.
+  //  * flush_frag: the second accumulator is a fragment-ordered array in shared memory (TPW x 32 float4 per warp, zeroed by the
+  //    caller; lane-contiguous 16-byte accesses, conflict-free); store_frags sums the warps' arrays into the CTA's partial.
+  //  * flush_tiles: it is the WP x WP partial in global memory itself (first: nothing is there yet, plain stores).
+  // Only the tiles of the upper triangle exist.
+  __device__ __forceinline__ void flush_frag(float4 *S, int lane)
+  {
+    static_assert(NSPLIT == 1, "every warp holds all tiles");
+#pragma unroll
+    for (int ti = 0; ti < NTILES; ++ti)
+    {
+      float4 v = S[ti * 32 + lane];
+      v.x += acc[ti][0], v.y += acc[ti][1], v.z += acc[ti][2], v.w += acc[ti][3];
+      S[ti * 32 + lane] = v;
+      acc[ti][0] = acc[ti][1] = acc[ti][2] = acc[ti][3] = 0.f;
+    }
+  }
+  // all threads of the CTA, after a block barrier: dst[r][c] = sum over the nwarps fragment arrays (S: [nwarps][NTILES * 32] float4)
+  static __device__ __forceinline__ void store_frags(const float4 *S, float *dst, int nwarps)
+  {
+    const float *Sf = reinterpret_cast<const float *>(S);
+    for (int e = threadIdx.x; e < NTILES * 128; e += blockDim.x)
+    {
+      const int ti = e >> 7, l = (e >> 2) & 31, k = e & 3;
+      int mi = 0, first = 0; // tile ti = (mi, nj): tiles are numbered row by row, row mi holds nj = 2 mi .. NT8 - 1
+      while (ti >= first + NT8 - 2 * mi)
+      {
+        first += NT8 - 2 * mi;
+        ++mi;
+      }
+      const int nj = 2 * mi + (ti - first);
+      const int r = 16 * mi + (l >> 2) + ((k & 2) ? 8 : 0), c = 8 * nj + 2 * (l & 3) + (k & 1);
+      float v = 0.f;
+      for (int w = 0; w < nwarps; ++w)
+        v += Sf[(size_t)w * NTILES * 128 + e];
+      if (r < WP)
+        dst[r * WP + c] = v;
+    }
+  }
+  template <int PART = 0>
+  __device__ __forceinline__ void flush_tiles(float *dst, int lane, bool first)
+  {
+    const int g = lane >> 2, t = lane & 3;
+    int ti = 0;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+      for (int nj = 2 * mi; nj < NT8; ++nj)
+      {
+        if (ti % NSPLIT == PART)
+        {
+          float(&d)[4] = acc[ti / NSPLIT];
+          const int r = 16 * mi + g, c = 8 * nj + 2 * t;
+          if (r < WP)
+          {
+            float2 *p = reinterpret_cast<float2 *>(dst + r * WP + c);
+            float2 o = make_float2(d[0], d[1]);
+            if (!first)
+            {
+              const float2 q = *p;
+              o.x += q.x, o.y += q.y;
+            }
+            *p = o;
+          }
+          if (r + 8 < WP)
+          {
+            float2 *p = reinterpret_cast<float2 *>(dst + (r + 8) * WP + c);
+            float2 o = make_float2(d[2], d[3]);
+            if (!first)
+            {
+              const float2 q = *p;
+              o.x += q.x, o.y += q.y;
+            }
+            *p = o;
+          }
+          d[0] = d[1] = d[2] = d[3] = 0.f;
+        }
+        ++ti;
+      }
+  }
+
   // NSPLIT == 1: sum the warps' full accumulators in shared memory (Hs: WP*WP floats, may alias the staging buffer once
   // every warp is done with it) and write the CTA's WP x WP partial (upper triangle valid) to dst.  Called by all threads.
   __device__ __forceinline__ void store_cta(float *Hs, float *dst, int warp, int lane, int nwarps)

@@ -10,6 +10,7 @@ enum { PH_MAP_JAC = 0, PH_MAP_ERR = 1, PH_TRK_JAC = 2, PH_TRK_ERR = 3 };
 // photometric.cu
 int photo_row_width(int mode, int C);
 int photo_samples_per_cta();
+size_t photo_partial_floats(int mode, int C); // floats of one CTA's partial (lineariser modes: one WP x WP matrix per warp)
 int photo_ctas_per_sm(int mode, int F, int C, bool staged = false);
 int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactors, const CamPyr &cam, int slices, float *partH,
                  float *partE, float *out, int out_stride, int D, cudaStream_t stream, bool staged = false);
@@ -17,6 +18,9 @@ int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactor
 // geometric.cu
 int geo_row_width(int C);
 int geo_ctas_per_sm(bool jac, int C);
+bool geo_uses_tc(bool jac, int C);
+int geo_set_tc(int on); // -1: query; returns the previous setting
+size_t geo_partial_floats(bool jac, int C); // floats of one CTA's partial (the tcgen05 lineariser writes [WP][2 WP])
 int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, int H, float fx, float fy, float cx, float cy,
                int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream);
 
