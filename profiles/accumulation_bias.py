@@ -1,7 +1,8 @@
 """Which lineariser is closer to the fp64 truth as the number of sequential accumulations grows?"""
 import os, sys
 import numpy as np
-sys.path[:0] = ["/root/repo", "/root/repo/tests", "/root/repo/oracle"]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
 import helpers, oracle as O
 import sage_slam_b200 as sage
 from sage_slam_b200 import capi, ops
