@@ -714,6 +714,24 @@ static void problem_build(sage_ba_problem *p)
     p->slices_photo = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), 5, 2048);
     p->slices_photo_err = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_ERR, p->F, C, p->staged), 5, 2048);
     p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C), 7, 1024);
+    if (geo_uses_tc(true, C) && p->n_geo > 0)
+    {
+      // The tcgen05 lineariser's CTAs cost a fixed amount to start and to finish (tensor-memory allocation, a cold first round, a
+      // 57 KB partial the finalize kernel reads back) and its time follows the wave efficiency (sweeps of 3..23 slices at 1 and 2
+      // GPUs, 67 slices of 9 rounds at 8 GPUs: +60 %).  Choose the slice count that maximises
+      // (filled fraction of the last wave) x (useful fraction of a CTA's life), with at least 32 rounds per CTA.
+      const int slots = std::max(1, geo_ctas_per_sm(true, C)) * ctx->num_sms;
+      const int cap = std::max(1, p->N / 4096);
+      double best = -1.0;
+      for (int w = 1; w <= 7; ++w)
+      {
+        const int sl = std::min(cap, std::max(1, w * slots / p->n_geo));
+        const double waves = (double)sl * p->n_geo / slots, rounds = (double)p->N / sl / 128.0;
+        const double score = waves / std::ceil(waves) * rounds / (rounds + 1.5);
+        if (score > best + 1e-9)
+          best = score, p->slices_geo = sl;
+      }
+    }
     p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C), 8, 512);
     if (const char *e = getenv("SAGE_BA_SLICES_PHOTO"))
       p->slices_photo = std::max(1, atoi(e));
