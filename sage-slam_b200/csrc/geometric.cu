@@ -3,6 +3,8 @@
 // Replaces geometric_jac_error_calculate_kernel (cuda/geometric_factor_kernels.cpp:472-720),
 // geometric_error_calculate_kernel (:127-218) and the ATen reductions after them (:931-947, :870-879).
 //
+// Two linearisers (see launch_geo_c): geo_tc_kernel -- tcgen05.mma with the accumulators in tensor memory, code size 32 -- further
+// down, and geo_kernel (mma.sync; also the error-only pass) right here:
 // A CTA is a pair of warps; each warp takes batches of 32 samples.
 //  * lane == sample: depth of the sample, warp into KF1, nearest mask lookup, the bilinear taps of KF1's
 //    (depth, d/dx, d/dy, mask) float4 map, Cauchy weight and the 9 "small" columns of the Jacobian row
@@ -12,7 +14,8 @@
 //    2C code columns of the row.
 //  * The staged rows (width 16 + 2C, one per sample) of both warps are folded into J^T J | J^T r on the
 //    tensor cores (mma.sync m16n8k8, 3xTF32, fp32 accumulate), the upper-triangular tiles split between
-//    the two warps.  Nothing is written to HBM except one partial per CTA.
+//    the two warps.  Nothing is written to HBM except one partial per CTA (updated every GEO_FLUSH rounds, see
+//    MmaSyrk::flush_tiles for why).
 #include "sage_common.cuh"
 #include "sage_kernels.h"
 #include "tcgen05.cuh"
