@@ -976,12 +976,11 @@ template <int C>
 static void solve_t(BlockSystem &b, double damp, double *delta_d, cudaStream_t s)
 {
   using T = BsCfg<C>;
-  static bool once = false;
-  if (!once)
+  static unsigned long long done = 0;
+  if (first_use_on_device(done))
   {
     cudaFuncSetAttribute(bs_factor_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::factor_smem());
     cudaFuncSetAttribute(bs_backward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::backward_smem());
-    once = true;
   }
   long long *dbg = nullptr;
   if (getenv("SAGE_BA_SOLVER_TRACE"))

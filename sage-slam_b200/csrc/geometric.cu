@@ -717,11 +717,9 @@ static void launch_geo_tc(const GeoFactor *factors, int nfactors, const GeoCam &
 {
   if constexpr (C == 32)
   {
-    static const bool once = [] {
+    static unsigned long long done = 0;
+    if (first_use_on_device(done))
       cudaFuncSetAttribute(geo_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, GeoTc<C>::STAGE);
-      return true;
-    }();
-    (void)once;
     geo_tc_kernel<C><<<dim3(slices, nfactors), GTC_THREADS, GeoTc<C>::STAGE, stream>>>(factors, cam, partH, partE);
     geo_finalize_kernel<C, true, true><<<dim3(nfactors, 6), 256, 0, stream>>>(factors, slices, partH, partE, out, out_stride);
   }

@@ -752,12 +752,9 @@ static void launch_photo_t(const PhotoFactor *factors, int nfactors, const CamPy
   constexpr size_t dyn = photo_dyn_bytes<F, C, MODE, STG>();
   if constexpr (dyn != 0)
   {
-    static bool once = false; // per instantiation; the attribute is per device function, setting it twice is harmless
-    if (!once)
-    {
+    static unsigned long long done = 0; // per instantiation and device
+    if (first_use_on_device(done))
       cudaFuncSetAttribute(photo_kernel<F, C, MODE, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-      once = true;
-    }
   }
   photo_kernel<F, C, MODE, STG><<<grid, PH_CTA, dyn, stream>>>(factors, cam, partH, partE);
   photo_finalize_kernel<C, MODE><<<nfactors, 256, 0, stream>>>(factors, cam.L, slices, partH, partE, out, out_stride, D);

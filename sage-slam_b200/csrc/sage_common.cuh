@@ -589,3 +589,16 @@ struct MmaSyrk
       dst[i] = Hs[i];
   }
 };
+
+// Opt-in attributes such as cudaFuncAttributeMaxDynamicSharedMemorySize live per device function PER DEVICE (context): a process
+// that drives several GPUs must set them once on each.  Returns true the first time it is called for `mask` on the current device.
+inline bool first_use_on_device(unsigned long long &mask)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit)
+    return false;
+  mask |= bit;
+  return true;
+}
