@@ -23,7 +23,7 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__cycles_elapsed.max"]
 NAMES = {"photo_kernel<32, 32, 0": "photo_jac", "photo_kernel<32, 32, 1": "photo_err", "geo_kernel<32, 1>": "geo_jac",
-         "geo_kernel<32, 0>": "geo_err"}
+         "geo_tc_kernel<32>": "geo_jac", "geo_kernel<32, 0>": "geo_err"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
