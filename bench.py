@@ -408,6 +408,10 @@ def run_ours(args):
             "kernel_ms_per_step": {k: v[0] / m["prof_steps"] for k, v in m["prof"].items()},
             "kernel_ms_note": "CUDA events inside the library in a separate pass with the factor kinds serialised (in the timed "
                               "region they overlap on forked streams, so the sum here exceeds ms_per_step)",
+            "kernel_variants": {"geometric_lineariser": "geo_tc_kernel (tcgen05.mma kind::tf32, accumulators in tensor memory)"
+                                if wl.get("C", 0) == 32 and sage.capi.load().sage_ba_set_geometric_tcgen05(-1) else
+                                "geo_kernel (mma.sync m16n8k8 tf32)",
+                                "rank_k_update": "3xTF32, accumulation chains cut every few hundred tensor-core instructions"},
             "solver": m["solver"],
             "clocks": m["clocks"],
             "lm_trace": [(float(a), float(b)) for a, b in m["costs"][-args.steps:]][:6],
