@@ -36,3 +36,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(src), f
+
+
+def test_lineariser_choice_is_a_process_wide_switch_that_needs_no_gpu():
+    """sage_ba_set_geometric_tcgen05: query with a negative argument, set returns the previous value (include/sage_ba.h)."""
+    lib = sage.capi.load()
+    prev = lib.sage_ba_set_geometric_tcgen05(-1)
+    assert prev in (0, 1)
+    assert lib.sage_ba_set_geometric_tcgen05(0) == prev
+    assert lib.sage_ba_set_geometric_tcgen05(-1) == 0
+    assert lib.sage_ba_set_geometric_tcgen05(1) == 0
+    assert lib.sage_ba_set_geometric_tcgen05(prev) == 1
+    assert lib.sage_ba_set_geometric_tcgen05(-1) == prev
