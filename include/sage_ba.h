@@ -64,8 +64,8 @@ void *sage_ba_stream(const sage_ba_context *ctx);
 /* Process-wide choice of the geometric lineariser (the kernel behind df::geometric_jac_error_calculate,
  * cuda/geometric_factor_kernels.cpp:472-720): 1 = tcgen05.mma kind::tf32 with the accumulators in tensor memory (code sizes 16
  * and 32), 0 = mma.sync.  on < 0 only queries.  Returns the previous setting; the environment variable SAGE_BA_GEO_TC gives the
- * initial one.  Both produce the same J^T J to fp32 round-off (3xTF32 split either way).  Set it before sage_ba_problem_create:
- * slice counts and partial buffers of a problem depend on it. */
+ * initial one.  Both produce the same J^T J to fp32 round-off (3xTF32 split either way).  A problem keeps the choice that was in
+ * force when it was created (slice counts and partial buffers depend on it); single-factor calls read it per call. */
 int sage_ba_set_geometric_tcgen05(int on);
 
 /* ------------------------------------------------------------------------------------------

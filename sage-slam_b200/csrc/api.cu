@@ -182,7 +182,6 @@ int sage_ba_create(sage_ba_context **out, int device, void *stream)
     return 1;
   *out = nullptr;
   sage_ba_context *ctx = new sage_ba_context();
-  sage_ba_context *ctx__ = ctx;
   try
   {
     int count = 0;
@@ -213,7 +212,6 @@ int sage_ba_create(sage_ba_context **out, int device, void *stream)
   {
     fprintf(stderr, "sage_ba_create: %s\n", e.msg.c_str());
     delete ctx;
-    (void)ctx__;
     return 1;
   }
 }
@@ -645,7 +643,8 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
   const int sps = (32 / (C / 4)) * (SAGE_CTA / 32);
   const int slices = pick_slices(ctx, f.N, sps);
   const size_t nout = (jac ? (size_t)D * D + D : 0) + 2;
-  float *partH = ctx->partH.ensure((size_t)slices * geo_partial_floats(jac, C));
+  const bool tc = geo_uses_tc(jac, C);
+  float *partH = ctx->partH.ensure((size_t)slices * geo_partial_floats(jac, C, tc));
   float *partE = ctx->partE.ensure((size_t)slices * 2);
   float *out = ctx->out.ensure(nout);
   GeoFactor *df = reinterpret_cast<GeoFactor *>(ctx->factor.ensure(1024));
@@ -654,7 +653,7 @@ static void run_geo_single(sage_ba_context *ctx, bool jac, const sage_ba_keyfram
   *hf = f;
   SAGE_CUDA(cudaMemcpyAsync(df, hf, sizeof(GeoFactor), cudaMemcpyHostToDevice, s));
   const sage_ba_camera &cam = kf1->cams[0];
-  SAGE_CHECK(launch_geo(jac, C, df, 1, kf1->W, kf1->H, cam.fx, cam.fy, cam.u0, cam.v0, slices, partH, partE, out, 1, s) == 0,
+  SAGE_CHECK(launch_geo(jac, C, df, 1, kf1->W, kf1->H, cam.fx, cam.fy, cam.u0, cam.v0, slices, partH, partE, out, 1, s, tc) == 0,
              "unsupported code_size");
   ctx->launches += 2;
   SAGE_CUDA(cudaGetLastError());

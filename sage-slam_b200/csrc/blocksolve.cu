@@ -211,7 +211,7 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
                  long long *__restrict__ dbg)
 {
   using T = BsCfg<C>;
-  constexpr int SP = T::SP, SPP = T::SPP, NT = T::NT, MAXS = T::MAXS, TQ = T::TQ, NR = T::NR;
+  constexpr int SP = T::SP, SPP = T::SPP, NT = T::NT, MAXS = T::MAXS;
   // optional phase timestamps (globaltimer, ns) per column: [start, loaded, deps done, factored, panel solved, published, wait ns, deps]
   auto stamp = [&](int slot, int col) {
     if (dbg && threadIdx.x == 0)
@@ -229,9 +229,8 @@ bs_factor_kernel(const BsDev d, const double *__restrict__ Hblk, const double *_
   double *gv = Lt + SP * SP;               // [SP] gradient / forward-substituted y_p
   double *yj = gv + SP;                    // [SP]
   double *invd = yj + SP;                  // [SP] 1 / L(p,p)[c][c]
-  double *colb = invd + SP;                // [SP] column broadcast of the warp-level factorisation
   __shared__ int s_p;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   // columns are handed out in the order the CTAs actually start: a CTA only ever waits for columns that are already running
   if (tid == 0)
     s_p = atomicAdd(&sync[0], 1);

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(GTC_THREADS, 2)
 geo_tc_kernel(const GeoFactor *__restrict__ factors, const GeoCam cam, float *__restrict__ partH, float *__restrict__ partE)
 {
   using T = GeoTc<C>;
-  constexpr int WP = T::WP, KSTEP = T::KSTEP, LO = T::LO, NCOL = T::NCOL;
+  constexpr int KSTEP = T::KSTEP, LO = T::LO, NCOL = T::NCOL;
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ GeoFactor fs;
   __shared__ float red[32];
@@ -701,12 +701,12 @@ int geo_set_tc(int on)
 static bool geo_tc_enabled() { return geo_tc_flag() != 0; }
 bool geo_uses_tc(bool jac, int C) { return jac && C == 32 && geo_tc_enabled(); }
 // floats of one CTA's partial
-size_t geo_partial_floats(bool jac, int C)
+size_t geo_partial_floats(bool jac, int C, bool tc)
 {
   const size_t WP = 16 + 2 * (size_t)C;
   if (!jac)
     return 4;
-  if (geo_uses_tc(true, C))
+  if (tc && C == 32)
     return GeoTc<32>::PART;
   return WP * WP;
 }
@@ -726,11 +726,11 @@ static void launch_geo_tc(const GeoFactor *factors, int nfactors, const GeoCam &
 }
 
 template <int C>
-static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const GeoCam &cam, int slices, float *partH, float *partE,
-                         float *out, int out_stride, cudaStream_t stream)
+static void launch_geo_c(bool jac, bool tc, const GeoFactor *factors, int nfactors, const GeoCam &cam, int slices, float *partH,
+                         float *partE, float *out, int out_stride, cudaStream_t stream)
 {
   dim3 grid(slices, nfactors);
-  if (geo_uses_tc(jac, C))
+  if (jac && tc && C == 32)
     launch_geo_tc<C>(factors, nfactors, cam, slices, partH, partE, out, out_stride, stream);
   else if (jac)
   {
@@ -745,10 +745,10 @@ static void launch_geo_c(bool jac, const GeoFactor *factors, int nfactors, const
 }
 
 // resident CTAs per SM of the kernel the given configuration launches (occupancy API); 0 for an unsupported C
-int geo_ctas_per_sm(bool jac, int C)
+int geo_ctas_per_sm(bool jac, int C, bool tc)
 {
   int n = 0;
-  if (geo_uses_tc(jac, C))
+  if (jac && tc && C == 32)
   {
     // registers, shared memory (stage + static + 1 KB the driver reserves per CTA) and tensor-memory columns (512 per SM)
     cudaFuncAttributes fa{};
@@ -775,16 +775,16 @@ int geo_ctas_per_sm(bool jac, int C)
 }
 
 int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, int H, float fx, float fy, float cx, float cy,
-               int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream)
+               int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream, bool tc)
 {
   if (nfactors <= 0)
     return 0;
   GeoCam cam{fx, fy, cx, cy, W, H};
   switch (C)
   {
-  case 32: launch_geo_c<32>(jac, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
-  case 16: launch_geo_c<16>(jac, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
-  case 8: launch_geo_c<8>(jac, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
+  case 32: launch_geo_c<32>(jac, tc, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
+  case 16: launch_geo_c<16>(jac, tc, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
+  case 8: launch_geo_c<8>(jac, tc, factors, nfactors, cam, slices, partH, partE, out, out_stride, stream); return 0;
   default: return -1;
   }
 }

@@ -399,6 +399,7 @@ struct sage_ba_problem
   bool relinearize_always = false; // lm_step: linearise even when the state did not change since the last linearisation
   bool deterministic = false;      // CTA decomposition independent of the rank count (bit-identical results for any world size)
   bool concurrent_factors = true;  // photometric / geometric / reprojection launches on forked streams
+  bool geo_tc = false;             // the geometric lineariser this problem was built for (snapshot of the process-wide switch)
   BlockSystem bs;
   int slices_photo = 32, slices_geo = 32, slices_photo_err = 32, slices_geo_err = 32; // CTAs per factor (linearise / error-only)
 
@@ -702,6 +703,7 @@ static void problem_build(sage_ba_problem *p)
     }
     return std::max(1, std::min(cap, slots / nfac));
   };
+  p->geo_tc = geo_uses_tc(true, C);
   if (p->deterministic)
   {
     p->slices_photo = per_cta("SAGE_BA_SPC_PHOTO", 2048);
@@ -713,14 +715,14 @@ static void problem_build(sage_ba_problem *p)
   {
     p->slices_photo = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), 5, 2048);
     p->slices_photo_err = pick(p->n_photo, photo_ctas_per_sm(PH_MAP_ERR, p->F, C, p->staged), 5, 2048);
-    p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C), 7, 1024);
-    if (geo_uses_tc(true, C) && p->n_geo > 0)
+    p->slices_geo = pick(p->n_geo, geo_ctas_per_sm(true, C, p->geo_tc), 7, 1024);
+    if (p->geo_tc && p->n_geo > 0)
     {
       // The tcgen05 lineariser's CTAs cost a fixed amount to start and to finish (tensor-memory allocation, a cold first round, a
       // 57 KB partial the finalize kernel reads back) and its time follows the wave efficiency (sweeps of 3..23 slices at 1 and 2
       // GPUs, 67 slices of 9 rounds at 8 GPUs: +60 %).  Choose the slice count that maximises
       // (filled fraction of the last wave) x (useful fraction of a CTA's life), with at least 32 rounds per CTA.
-      const int slots = std::max(1, geo_ctas_per_sm(true, C)) * ctx->num_sms;
+      const int slots = std::max(1, geo_ctas_per_sm(true, C, true)) * ctx->num_sms;
       const int cap = std::max(1, p->N / 4096);
       double best = -1.0;
       for (int w = 1; w <= 7; ++w)
@@ -732,7 +734,7 @@ static void problem_build(sage_ba_problem *p)
           best = score, p->slices_geo = sl;
       }
     }
-    p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C), 8, 512);
+    p->slices_geo_err = pick(p->n_geo, geo_ctas_per_sm(false, C, false), 8, 512);
     if (const char *e = getenv("SAGE_BA_SLICES_PHOTO"))
       p->slices_photo = std::max(1, atoi(e));
     if (const char *e = getenv("SAGE_BA_SLICES_GEO"))
@@ -744,10 +746,10 @@ static void problem_build(sage_ba_problem *p)
   }
   if (getenv("SAGE_BA_DEBUG"))
     fprintf(stderr, "[sage_ba] slices: photo %d / %d (err), geo %d / %d (err); CTAs per SM: photo %d, geo %d (tcgen05 %d)\n", p->slices_photo,
-            p->slices_photo_err, p->slices_geo, p->slices_geo_err, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), geo_ctas_per_sm(true, C),
-            (int)geo_uses_tc(true, C));
+            p->slices_photo_err, p->slices_geo, p->slices_geo_err, photo_ctas_per_sm(PH_MAP_JAC, p->F, C, p->staged), geo_ctas_per_sm(true, C, p->geo_tc),
+            (int)p->geo_tc);
   p->partH.ensure(std::max<size_t>((size_t)p->n_photo * p->slices_photo * photo_partial_floats(PH_MAP_JAC, C), 4));
-  p->partHg.ensure(std::max<size_t>((size_t)p->n_geo * p->slices_geo * geo_partial_floats(true, C), 4));
+  p->partHg.ensure(std::max<size_t>((size_t)p->n_geo * p->slices_geo * geo_partial_floats(true, C, p->geo_tc), 4));
   p->partE.ensure(std::max<size_t>(2 * (size_t)p->n_photo * std::max(p->slices_photo, p->slices_photo_err), 4));
   p->partEg.ensure(std::max<size_t>(2 * (size_t)p->n_geo * std::max(p->slices_geo, p->slices_geo_err), 4));
   const int n = p->dim();
@@ -819,7 +821,7 @@ static void run_factors(sage_ba_problem *p, int which, bool jac, float *out)
     const sage_ba_camera &cam = k0->cams[0];
     ProfScope ps(p, jac ? SAGE_BA_PROF_GEO_JAC : SAGE_BA_PROF_GEO_ERR, sg);
     SAGE_CHECK(launch_geo(jac, p->C, p->geo_d.p, p->n_geo, p->W, p->H, cam.fx, cam.fy, cam.u0, cam.v0, jac ? p->slices_geo : p->slices_geo_err,
-                          p->partHg.p, p->partEg.p, out, 1, sg) == 0,
+                          p->partHg.p, p->partEg.p, out, 1, sg, p->geo_tc) == 0,
                "unsupported code_size");
     ctx->launches += 5;
   }

@@ -17,12 +17,14 @@ int launch_photo(int mode, int F, int C, const PhotoFactor *factors, int nfactor
 
 // geometric.cu
 int geo_row_width(int C);
-int geo_ctas_per_sm(bool jac, int C);
+// tc: the caller's snapshot of geo_uses_tc(jac, C) -- partial size, slice count and launch must agree on the lineariser even if
+// another thread flips the process-wide switch in between
 bool geo_uses_tc(bool jac, int C);
 int geo_set_tc(int on); // -1: query; returns the previous setting
-size_t geo_partial_floats(bool jac, int C); // floats of one CTA's partial (the tcgen05 lineariser writes [WP][2 WP])
+int geo_ctas_per_sm(bool jac, int C, bool tc);
+size_t geo_partial_floats(bool jac, int C, bool tc); // floats of one CTA's partial (the tcgen05 lineariser writes [128][112])
 int launch_geo(bool jac, int C, const GeoFactor *factors, int nfactors, int W, int H, float fx, float fy, float cx, float cy,
-               int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream);
+               int slices, float *partH, float *partE, float *out, int out_stride, cudaStream_t stream, bool tc);
 
 // reprojection.cu
 int launch_reproj(bool jac, bool tracker, int C, const ReprojFactor *factors, int nfactors, float *out, int out_stride,

@@ -87,6 +87,7 @@ def test_tcgen05_lineariser_in_the_batched_problem(sage_ctx, tcgen05, num_sample
         for i, j in pairs:
             ba.add_geometric(i, j, 0.1, 1.0)
         ba.set_state([k.pose_wk for k in kfs], np.stack([k.code for k in kfs]), [k.dpt_scale for k in kfs], helpers.EPS)
+        tcgen05(not on)  # flipping the process-wide switch after creation must not touch this problem (its buffers are sized)
         ba.linearize()
         bufs.append(ba.factor_buffer().copy())
         ba.close()
