@@ -10,6 +10,9 @@
  *
  * Conventions
  *   - All arithmetic is fp32 (the reference hard-codes <float>, photometric_factor_kernels.cpp:1111).
+ *     J^T J | J^T r are reduced on the tensor cores with a 3xTF32 split and bounded accumulation chains: against sums of
+ *     the same fp32 rows in fp64 every block agrees to about 1e-5 relative (Jacobi-scaled), independent of the sample count
+ *     and of how a factor is split over CTAs; the reference (materialised J, cuBLAS sgemm) sits at about 1e-6.
  *   - Rotations are row-major float[9], translations float[3]; poses are keyframe->world
  *     (pose_wk); T10 = T1^-1 T0 (gtsam/photometric_factor.cpp:280-281).
  *   - AtA is row-major [D,D], Atb is [D]; variable order inside a factor is the reference's:
