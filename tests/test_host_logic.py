@@ -239,3 +239,37 @@ def test_avg_squared_dpt_bias_is_the_masked_mean():
     got = mapper.avg_squared_dpt_bias(kf)
     assert abs(got - want) <= 1e-5 * want
     assert abs(np.mean(b ** 2) - want) > 1e-2 * want  # the plain mean is something else here
+
+
+def test_tcgen05_operand_order_and_finalize_algebra():
+    """csrc/geometric.cu, geo_tc_kernel: operand columns [loB | hi | loA], ONE product D = A^T B with A = [hi | loA] (128 columns) and
+    B = [loB | hi] (112 columns); the finalize kernel rebuilds J^T J = hi^T hi + X + X^T (X = hi^T lo) from D alone.  Restated in
+    numpy with the kernel's index formulas: the result must equal the 3xTF32 sum hi^T hi + hi^T lo + lo^T hi exactly (fp64)."""
+    rng = np.random.default_rng(3)
+    WP, L1 = 80, 48
+    L2 = WP - L1
+    NC = WP + L2
+    rows = rng.standard_normal((256, WP)).astype(np.float32)
+    hi = (rows.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = ((rows - hi).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    assert np.abs(rows - hi - lo).max() <= 2.0 ** -20 * np.abs(rows).max()  # what the split drops
+    hi, lo = hi.astype(np.float64), lo.astype(np.float64)
+    stage = np.concatenate([lo[:, L1:], hi, lo[:, :L1]], axis=1)  # [loB | hi | loA]: 160 operand columns per sample
+    A, B = stage[:, L2:L2 + 128], stage[:, :NC]
+    assert A.shape[1] == 128 and B.shape[1] == 112
+    P = A.T @ B  # the accumulator image the CTA flushes: [128][112]
+
+    def xt(a, b):  # X^T[a][b] = (lo^T hi)[a][b], as in geo_finalize_kernel<.., TCP = true>
+        return P[WP + a, L2 + b] if a < L1 else P[b, a - L1]
+
+    S = np.empty((WP, WP))
+    for r in range(WP):
+        for c in range(WP):
+            lo_i, hi_i = min(r, c), max(r, c)
+            S[r, c] = P[lo_i, L2 + hi_i] + (xt(lo_i, hi_i) + xt(hi_i, lo_i))
+    want = hi.T @ hi + hi.T @ lo + lo.T @ hi
+    np.testing.assert_allclose(S, want, rtol=1e-12, atol=1e-12)
+    # and the staging address formula: 32 four-byte stores of one instruction (4 consecutive samples x 8 channel quads) hit 32 banks
+    SBO, LBO = 272, 144
+    banks = {(((2 + (gl >> 1)) * SBO + (gl & 1) * 64 + q * 4) // 4) % 32 for q in range(4) for gl in range(8)}
+    assert len(banks) == 32 and (20 * SBO // 4) % 32 == 16 and LBO + 128 <= SBO
