@@ -313,6 +313,16 @@ int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe *frame0, co
 int sage_ba_tracker_solve(const float *AtA, const float *Atb, int n, float damp, float *x);
 int sage_ba_se3_exp(const float *omega, const float *v, float *R, float *t);
 
+/* The LM loop behind sage_ba_track_new_frame (dof = 6; core/system/camera_tracker.cpp:1156-1279) and sage_ba_track_frame
+ * (dof = 7; :1479-1630) over a caller-supplied cost: jac fills AtA [dof*dof] row-major, Atb [dof] and the error at (R, t, scale),
+ * err returns the error.  Host code only (no context, no GPU): for callers with their own factors, and the hook through which the
+ * loop itself is pinned against the reference's loops (tests/golden/loop_pins.npz, tests/test_loop_pins.py).  Only the LM fields
+ * of cfg are read.  R, t (and scale, dof = 7): in = initial guess, out = estimate.  Returns 0. */
+typedef void (*sage_ba_lm_jac_callback)(void *user, const float *R, const float *t, float scale, float *AtA, float *Atb, float *error);
+typedef float (*sage_ba_lm_err_callback)(void *user, const float *R, const float *t, float scale);
+int sage_ba_tracker_lm_callbacks(int dof, const sage_ba_tracker_config *cfg, float *R, float *t, float *scale, sage_ba_lm_jac_callback jac,
+                                 sage_ba_lm_err_callback err, void *user, sage_ba_tracker_report *report);
+
 /* ------------------------------------------------------------------------------------------
  * Batched local bundle adjustment (new; the reference delegates this to GTSAM ISAM2,
  * core/mapping/mapper.cpp:544).  A problem owns K keyframes' states (pose_wk, code, scale) on

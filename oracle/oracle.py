@@ -693,6 +693,10 @@ def tracker_lm7(jac_fn, err_fn, R, t, scale, init_damp=1e-4, min_damp=1e-6, max_
     """CameraTracker::TrackFrame 7-DoF LM loop (core/system/camera_tracker.cpp:1479-1630): relative pose + scale_0.
     jac_fn(R,t,s)->(AtA 7x7, Atb 7, err), err_fn(R,t,s)->err."""
     f = np.float32
+    # the reference's options are floats (camera_tracker.h:54-63): compare float with float, or `damp < max_damp` never turns false
+    # for a max_damp that fp32 rounds down (1e-2) and the loop cannot stop at maximum damping
+    init_damp, min_damp, max_damp, damp_dec, damp_inc = f(init_damp), f(min_damp), f(max_damp), f(damp_dec), f(damp_inc)
+    jac_thresh, min_grad, min_param_inc = f(jac_thresh), f(min_grad), f(min_param_inc)
     R, t, scale = np.asarray(R, f), np.asarray(t, f), f(scale)
     prev_error, curr_error = f(0), f(1)
     damp, it = f(init_damp), 0
@@ -747,6 +751,9 @@ def tracker_lm(jac_fn, err_fn, R, t, init_damp=1e-4, min_damp=1e-6, max_damp=1e-
     user-supplied jac_fn(R,t)->(AtA,Atb,err) / err_fn(R,t)->err.  fp32 state like the reference.
     Returns (R, t, error, trace) where trace records (iter, damp, accepted, error)."""
     f = np.float32
+    # float options like the reference's (see tracker_lm7)
+    init_damp, min_damp, max_damp, damp_dec, damp_inc = f(init_damp), f(min_damp), f(max_damp), f(damp_dec), f(damp_inc)
+    jac_thresh, min_grad, min_param_inc = f(jac_thresh), f(min_grad), f(min_param_inc)
     R, t = np.asarray(R, f), np.asarray(t, f)
     prev_error, curr_error = f(0), f(1)
     damp, it = f(init_damp), 0

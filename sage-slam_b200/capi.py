@@ -54,6 +54,9 @@ class LMReport(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, C.c_size_t, vp)
+LM_JAC_FN = C.CFUNCTYPE(None, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                        C.POINTER(C.c_float))
+LM_ERR_FN = C.CFUNCTYPE(C.c_float, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float)
 
 # name -> (restype, argtypes); every symbol include/sage_ba.h declares
 F = C.c_float
@@ -94,6 +97,8 @@ SIGNATURES = {
                                           C.POINTER(TrackerReport)]),
     "sage_ba_tracker_solve": (C.c_int, [vp, vp, C.c_int, F, vp]),
     "sage_ba_se3_exp": (C.c_int, [vp, vp, vp, vp]),
+    "sage_ba_tracker_lm_callbacks": (C.c_int, [C.c_int, C.POINTER(TrackerConfig), vp, vp, vp, LM_JAC_FN, LM_ERR_FN, vp,
+                                               C.POINTER(TrackerReport)]),
     "sage_ba_problem_create": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]),
     "sage_ba_problem_destroy": (None, [vp]),
     "sage_ba_problem_add_photometric": (C.c_int, [vp, C.c_int, C.c_int, vp]),

@@ -197,6 +197,117 @@ void rotation_to_angle_axis(const float *R, float eps, float *out)
     out[i] = k * q[1 + i];
 }
 
+// The damped Gauss-Newton loop of CameraTracker::TrackNewFrame (core/system/camera_tracker.cpp:1156-1279, DOF = 6: relative pose)
+// and CameraTracker::TrackFrame (:1479-1630, DOF = 7: + depth scale of the tracked frame), statement by statement: the Jacobian
+// is recomputed only when the relative error change is large enough (:1159), the error of the linearisation is taken on the
+// first iteration only (:1167), the damped system is solved with Eigen's colPivHouseholderQr in float (solve_small), the step
+// is tested with LMConvergence (:527-573: max |Atb| and the SIGNED max of delta / (|x| + 1e-8)), applied with UpdateVariables
+// (:467-512: T <- exp([v, w]) T, scale += delta[6]) and retried with more damping until it lowers the error or the damping is at
+// its maximum.  jac(R, t, s, AtA, Atb, &err), err(R, t, s) -> error.  no_overlap_error >= 0 (TrackFrame without the match-geometry
+// factor, :1500-1504): stop with return code 2 when the error says that nothing overlaps.
+// The same code runs behind sage_ba_track_new_frame / sage_ba_track_frame (cost = the GPU factor kernels) and behind
+// sage_ba_tracker_lm_callbacks (cost = the caller's), which is how tests/test_loop_pins.py holds it to the reference's own loops.
+template <int DOF, class JacFn, class ErrFn>
+static int lm_loop(const sage_ba_tracker_config *cfg, float *R, float *t, float *scale, float no_overlap_error, JacFn &&jac_fn, ErrFn &&err_fn,
+                   sage_ba_tracker_report &rep)
+{
+  static_assert(DOF == 6 || DOF == 7, "relative pose (+ scale)");
+  auto clampd = [&](float d) { return std::min(std::max(cfg->min_damp, d), cfg->max_damp); };
+  float Rg[9], tg[3], Rc[9], tc[3], sg = scale ? *scale : 1.f, sc = sg;
+  memcpy(Rg, R, sizeof(Rg));
+  memcpy(tg, t, sizeof(tg));
+  float AtA[DOF * DOF], Atb[DOF], damped[DOF * DOF], sol[DOF];
+  float prev_error = 0.f, curr_error = 1.f, cand_error = 1.f; // :1056-1057
+  float damp = cfg->init_damp;
+  long iter = 0;
+  bool update_jac = true;
+  int rc = 0;
+  while (true)
+  {
+    if (std::fabs(curr_error - prev_error) / prev_error > cfg->jac_update_err_inc_threshold)
+    {
+      float e = 0.f;
+      jac_fn(Rg, tg, sg, AtA, Atb, &e);
+      rep.jacobian_evals++;
+      if (iter == 0)
+        curr_error = e;
+      update_jac = true;
+    }
+    else
+      update_jac = false;
+    if (no_overlap_error >= 0.f && curr_error >= no_overlap_error)
+    {
+      rc = 2;
+      break;
+    }
+    iter += 1;
+    auto solve = [&]() {
+      for (int i = 0; i < DOF * DOF; ++i)
+        damped[i] = AtA[i];
+      for (int i = 0; i < DOF; ++i)
+        damped[i * DOF + i] = AtA[i * DOF + i] + damp * AtA[i * DOF + i];
+      if (!solve_small(damped, Atb, DOF, sol))
+        for (int i = 0; i < DOF; ++i)
+          sol[i] = 0.f;
+    };
+    solve();
+    float rotvec[3];
+    rotation_to_angle_axis(Rg, 1.0e-6f, rotvec);
+    float max_grad = 0.f, max_inc = -INFINITY;
+    for (int i = 0; i < DOF; ++i)
+    {
+      max_grad = std::max(max_grad, std::fabs(Atb[i]));
+      const float x = i < 3 ? tg[i] : (i < 6 ? rotvec[i - 3] : sg);
+      max_inc = std::max(max_inc, sol[i] / (std::fabs(x) + 1.0e-8f));
+    }
+    if (max_grad < cfg->min_grad_thresh || max_inc < cfg->min_param_inc_thresh)
+      break;
+    while (true)
+    {
+      float dR[9], dt[3];
+      se3_exp_host(sol + 3, sol, dR, dt);
+      for (int r = 0; r < 3; ++r)
+      {
+        for (int c = 0; c < 3; ++c)
+          Rc[r * 3 + c] = dR[r * 3] * Rg[c] + dR[r * 3 + 1] * Rg[3 + c] + dR[r * 3 + 2] * Rg[6 + c];
+        tc[r] = dR[r * 3] * tg[0] + dR[r * 3 + 1] * tg[1] + dR[r * 3 + 2] * tg[2] + dt[r];
+      }
+      if constexpr (DOF == 7)
+        sc = sg + sol[6];
+      cand_error = err_fn(Rc, tc, sc);
+      rep.error_evals++;
+      if (cand_error < curr_error)
+        break;
+      else if (damp < cfg->max_damp)
+      {
+        damp = clampd(damp * cfg->damp_inc_factor);
+        solve();
+      }
+      else
+        break;
+    }
+    if (cand_error >= curr_error && damp >= cfg->max_damp)
+      break;
+    memcpy(Rg, Rc, sizeof(Rg));
+    memcpy(tg, tc, sizeof(tg));
+    sg = sc;
+    if (update_jac)
+      prev_error = curr_error;
+    curr_error = cand_error;
+    damp = clampd(damp / cfg->damp_dec_factor);
+    if (iter >= cfg->max_num_iters)
+      break;
+  }
+  memcpy(R, Rg, sizeof(Rg));
+  memcpy(t, tg, sizeof(tg));
+  if (scale)
+    *scale = sg;
+  rep.iterations = (int)iter;
+  rep.final_error = curr_error;
+  rep.final_damp = damp;
+  return rc;
+}
+
 } // namespace
 
 extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyframe *kf0, const sage_ba_keyframe *frame1,
@@ -224,7 +335,7 @@ extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyfr
 
     sage_ba_tracker_report rep;
     memset(&rep, 0, sizeof(rep));
-    auto jac_fn = [&](const float *Rg, const float *tg, float *AtA, float *Atb, float *err) {
+    auto jac_fn = [&](const float *Rg, const float *tg, float, float *AtA, float *Atb, float *err) {
       for (int i = 0; i < 36; ++i)
         AtA[i] = 0.f;
       for (int i = 0; i < 6; ++i)
@@ -251,9 +362,8 @@ extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyfr
           Atb[i] += b[i];
       }
       *err = e_photo + e_rep;
-      rep.jacobian_evals++;
     };
-    auto err_fn = [&](const float *Rg, const float *tg) -> float {
+    auto err_fn = [&](const float *Rg, const float *tg, float) -> float {
       float e_photo = 0.f, e_rep = 0.f;
       if (use_photo)
         SAGE_CHECK(sage_ba_tracker_photo_error(ctx, frame1, Rg, tg, d_dpts, d_homo, d_feats, N, cfg->dpt_eps, cfg->photo_weights,
@@ -263,93 +373,9 @@ extern "C" int sage_ba_track_new_frame(sage_ba_context *ctx, const sage_ba_keyfr
         SAGE_CHECK(sage_ba_tracker_reproj_error(ctx, &cam, Rg, tg, match_dpts, match_homo, match2d, num_matches, cfg->dpt_eps,
                                                 cfg->reproj_loss_param, cfg->reproj_weight, &e_rep, nullptr) == 0,
                    ctx->err);
-      rep.error_evals++;
       return e_photo + e_rep;
     };
-    auto clampd = [&](float d) { return std::min(std::max(cfg->min_damp, d), cfg->max_damp); };
-
-    float Rg[9], tg[3], Rc[9], tc[3];
-    memcpy(Rg, R, sizeof(Rg));
-    memcpy(tg, t, sizeof(tg));
-    float AtA[36], Atb[6], damped[36], sol[6];
-    float prev_error = 0.f, curr_error = 1.f, cand_error = 1.f; // :1056-1057
-    float damp = cfg->init_damp;
-    long iter = 0;
-    bool update_jac = true;
-    while (true)
-    {
-      // recompute the Jacobian only when the relative error change is large enough (:1159)
-      if (std::fabs(curr_error - prev_error) / prev_error > cfg->jac_update_err_inc_threshold)
-      {
-        float e = 0.f;
-        jac_fn(Rg, tg, AtA, Atb, &e);
-        if (iter == 0)
-          curr_error = e; // update_error only on the first iteration (:1167)
-        update_jac = true;
-      }
-      else
-        update_jac = false;
-      iter += 1;
-      auto solve = [&]() {
-        for (int i = 0; i < 36; ++i)
-          damped[i] = AtA[i];
-        for (int i = 0; i < 6; ++i)
-          damped[i * 6 + i] = AtA[i * 6 + i] + damp * AtA[i * 6 + i];
-        if (!solve_small(damped, Atb, 6, sol))
-          for (int i = 0; i < 6; ++i)
-            sol[i] = 0.f;
-      };
-      solve();
-      // LMConvergence (:552-573): max |Atb| and the SIGNED max of delta / (|x| + 1e-8)
-      float rotvec[3];
-      rotation_to_angle_axis(Rg, 1.0e-6f, rotvec);
-      float max_grad = 0.f, max_inc = -INFINITY;
-      for (int i = 0; i < 6; ++i)
-      {
-        max_grad = std::max(max_grad, std::fabs(Atb[i]));
-        const float x = i < 3 ? tg[i] : rotvec[i - 3];
-        max_inc = std::max(max_inc, sol[i] / (std::fabs(x) + 1.0e-8f));
-      }
-      if (max_grad < cfg->min_grad_thresh || max_inc < cfg->min_param_inc_thresh)
-        break;
-      while (true)
-      {
-        // UpdateVariables (:491-512): T <- exp([v, w]) * T
-        float dR[9], dt[3];
-        se3_exp_host(sol + 3, sol, dR, dt);
-        for (int r = 0; r < 3; ++r)
-        {
-          for (int c = 0; c < 3; ++c)
-            Rc[r * 3 + c] = dR[r * 3] * Rg[c] + dR[r * 3 + 1] * Rg[3 + c] + dR[r * 3 + 2] * Rg[6 + c];
-          tc[r] = dR[r * 3] * tg[0] + dR[r * 3 + 1] * tg[1] + dR[r * 3 + 2] * tg[2] + dt[r];
-        }
-        cand_error = err_fn(Rc, tc);
-        if (cand_error < curr_error)
-          break;
-        else if (damp < cfg->max_damp)
-        {
-          damp = clampd(damp * cfg->damp_inc_factor);
-          solve();
-        }
-        else
-          break;
-      }
-      if (cand_error >= curr_error && damp >= cfg->max_damp)
-        break;
-      memcpy(Rg, Rc, sizeof(Rg));
-      memcpy(tg, tc, sizeof(tg));
-      if (update_jac)
-        prev_error = curr_error;
-      curr_error = cand_error;
-      damp = clampd(damp / cfg->damp_dec_factor);
-      if (iter >= cfg->max_num_iters)
-        break;
-    }
-    memcpy(R, Rg, sizeof(Rg));
-    memcpy(t, tg, sizeof(tg));
-    rep.iterations = (int)iter;
-    rep.final_error = curr_error;
-    rep.final_damp = damp;
+    lm_loop<6>(cfg, R, t, nullptr, -1.f, jac_fn, err_fn, rep);
     if (report)
       *report = rep;
     return 0;
@@ -416,7 +442,6 @@ extern "C" int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe 
           Atb[i] += b[i];
       }
       *err = e_photo + e_mg;
-      rep.jacobian_evals++;
     };
     auto err_fn = [&](const float *Rg, const float *tg, float sg) -> float {
       float e_photo = 0.f, e_mg = 0.f;
@@ -426,99 +451,9 @@ extern "C" int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe 
       if (use_mg)
         run_match_geom_single(ctx, false, Rg, tg, m_udpts0, m_dpts1, m_homo0, m_homo1, num_matches, sg, 0.f, cfg->match_geom_loss_param,
                               cfg->match_geom_weight, nullptr, nullptr, &e_mg);
-      rep.error_evals++;
       return e_photo + e_mg;
     };
-    auto clampd = [&](float d) { return std::min(std::max(cfg->min_damp, d), cfg->max_damp); };
-
-    float Rg[9], tg[3], Rc[9], tc[3], sg = *scale, sc = *scale;
-    memcpy(Rg, R, sizeof(Rg));
-    memcpy(tg, t, sizeof(tg));
-    float AtA[49], Atb[7], damped[49], sol[7];
-    float prev_error = 0.f, curr_error = 1.f, cand_error = 1.f;
-    float damp = cfg->init_damp;
-    long iter = 0;
-    bool update_jac = true;
-    int rc = 0;
-    while (true)
-    {
-      if (std::fabs(curr_error - prev_error) / prev_error > cfg->jac_update_err_inc_threshold)
-      {
-        float e = 0.f;
-        jac_fn(Rg, tg, sg, AtA, Atb, &e);
-        if (iter == 0)
-          curr_error = e;
-        update_jac = true;
-      }
-      else
-        update_jac = false;
-      if (curr_error >= wsum * 9.9f && !use_mg) // no overlap (:1500-1504)
-      {
-        rc = 2;
-        break;
-      }
-      iter += 1;
-      auto solve = [&]() {
-        for (int i = 0; i < 49; ++i)
-          damped[i] = AtA[i];
-        for (int i = 0; i < 7; ++i)
-          damped[i * 7 + i] = AtA[i * 7 + i] + damp * AtA[i * 7 + i];
-        if (!solve_small(damped, Atb, 7, sol))
-          for (int i = 0; i < 7; ++i)
-            sol[i] = 0.f;
-      };
-      solve();
-      float rotvec[3];
-      rotation_to_angle_axis(Rg, 1.0e-6f, rotvec);
-      float max_grad = 0.f, max_inc = -INFINITY;
-      for (int i = 0; i < 7; ++i)
-      {
-        max_grad = std::max(max_grad, std::fabs(Atb[i]));
-        const float x = i < 3 ? tg[i] : (i < 6 ? rotvec[i - 3] : sg);
-        max_inc = std::max(max_inc, sol[i] / (std::fabs(x) + 1.0e-8f));
-      }
-      if (max_grad < cfg->min_grad_thresh || max_inc < cfg->min_param_inc_thresh)
-        break;
-      while (true)
-      {
-        float dR[9], dt[3];
-        se3_exp_host(sol + 3, sol, dR, dt);
-        for (int r = 0; r < 3; ++r)
-        {
-          for (int c = 0; c < 3; ++c)
-            Rc[r * 3 + c] = dR[r * 3] * Rg[c] + dR[r * 3 + 1] * Rg[3 + c] + dR[r * 3 + 2] * Rg[6 + c];
-          tc[r] = dR[r * 3] * tg[0] + dR[r * 3 + 1] * tg[1] + dR[r * 3 + 2] * tg[2] + dt[r];
-        }
-        sc = sg + sol[6];
-        cand_error = err_fn(Rc, tc, sc);
-        if (cand_error < curr_error)
-          break;
-        else if (damp < cfg->max_damp)
-        {
-          damp = clampd(damp * cfg->damp_inc_factor);
-          solve();
-        }
-        else
-          break;
-      }
-      if (cand_error >= curr_error && damp >= cfg->max_damp)
-        break;
-      memcpy(Rg, Rc, sizeof(Rg));
-      memcpy(tg, tc, sizeof(tg));
-      sg = sc;
-      if (update_jac)
-        prev_error = curr_error;
-      curr_error = cand_error;
-      damp = clampd(damp / cfg->damp_dec_factor);
-      if (iter >= cfg->max_num_iters)
-        break;
-    }
-    memcpy(R, Rg, sizeof(Rg));
-    memcpy(t, tg, sizeof(tg));
-    *scale = sg;
-    rep.iterations = (int)iter;
-    rep.final_error = curr_error;
-    rep.final_damp = damp;
+    const int rc = lm_loop<7>(cfg, R, t, scale, use_mg ? -1.f : wsum * 9.9f, jac_fn, err_fn, rep); // no overlap: :1500-1504
     if (report)
       *report = rep;
     return rc;
@@ -531,6 +466,22 @@ extern "C" int sage_ba_track_frame(sage_ba_context *ctx, const sage_ba_keyframe 
 }
 
 extern "C" {
+
+// The LM loop of sage_ba_track_new_frame (dof 6) / sage_ba_track_frame (dof 7) over a caller-supplied cost.  Host code only.
+int sage_ba_tracker_lm_callbacks(int dof, const sage_ba_tracker_config *cfg, float *R, float *t, float *scale, sage_ba_lm_jac_callback jac,
+                                 sage_ba_lm_err_callback err, void *user, sage_ba_tracker_report *report)
+{
+  if (!cfg || !R || !t || !jac || !err || (dof != 6 && dof != 7) || (dof == 7 && !scale))
+    return 1;
+  sage_ba_tracker_report rep;
+  memset(&rep, 0, sizeof(rep));
+  auto jac_fn = [&](const float *Rg, const float *tg, float sg, float *AtA, float *Atb, float *e) { jac(user, Rg, tg, sg, AtA, Atb, e); };
+  auto err_fn = [&](const float *Rg, const float *tg, float sg) -> float { return err(user, Rg, tg, sg); };
+  const int rc = dof == 6 ? lm_loop<6>(cfg, R, t, nullptr, -1.f, jac_fn, err_fn, rep) : lm_loop<7>(cfg, R, t, scale, -1.f, jac_fn, err_fn, rep);
+  if (report)
+    *report = rep;
+  return rc;
+}
 
 /* The tracker's linear solve, exposed for callers that keep their own LM loop and for the parity tests:
  * x = (AtA + damp * diag(AtA)).colPivHouseholderQr().solve(Atb), n = 6 | 7, float (camera_tracker.cpp:1182-1183). */
