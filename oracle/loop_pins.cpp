@@ -2,7 +2,8 @@
 // cost and prints every cost evaluation they make.
 //
 // The loops -- CameraTracker::TrackNewFrame (core/system/camera_tracker.cpp:1156-1279, 6-DoF) and CameraTracker::TrackFrame
-// (:1479-1630, 7-DoF) -- their declaration blocks, UpdateVariables (:467-512) and LMConvergence (:527-573) are #included from files
+// (:1479-1630, 7-DoF) -- their declaration blocks, UpdateVariables (:467-512) and LMConvergence (:527-573) -- and UpdateDepth
+// (core/mapping/mapping_utils.h:216-222, second mode below) are #included from files
 // that oracle/build_loop_ref.py extracts verbatim from /root/reference at build time (git-ignored; nothing is copied into the
 // repository).  This file only supplies what those pieces refer to: the members config_ / tracker_name_ / kf_ / photo_weights_tensor_,
 // a VLOG sink, and ComputeJacobianAndError / ComputeError over a pinhole reprojection cost on a point cloud
@@ -214,13 +215,40 @@ struct LoopHarness
 };
 } // namespace df
 
+// "0 H W C scale" then H*W bias values, H*W*C basis values (row = pixel), C code values -> the H*W values UpdateDepth writes
+static int update_depth_mode()
+{
+  long H, W, C;
+  float scale;
+  std::cin >> H >> W >> C >> scale;
+  std::vector<float> bias(H * W), jac(H * W * C), code(C);
+  for (float &v : bias)
+    std::cin >> v;
+  for (float &v : jac)
+    std::cin >> v;
+  for (float &v : code)
+    std::cin >> v;
+  const at::Tensor b = torch::from_blob(bias.data(), {1, 1, H, W}, torch::kFloat32), J = torch::from_blob(jac.data(), {H * W, C}, torch::kFloat32),
+                   c = torch::from_blob(code.data(), {C}, torch::kFloat32);
+  at::Tensor dpt_map;
+  df::UpdateDepth<float>(b, J, c, scale, dpt_map);
+  const at::Tensor out = dpt_map.reshape({-1}).contiguous();
+  for (long i = 0; i < H * W; ++i)
+    std::printf("%.9g\n", (double)out.data_ptr<float>()[i]);
+  return 0;
+}
+
 int main()
 {
   torch::NoGradGuard no_grad;
   df::LoopHarness h;
   int dof = 0, n = 0;
   auto &c = h.config_;
-  if (!(std::cin >> dof >> n >> c.init_damp >> c.min_damp >> c.max_damp >> c.damp_inc_factor >> c.damp_dec_factor >> c.jac_update_err_inc_threshold >>
+  if (!(std::cin >> dof))
+    return 2;
+  if (dof == 0)
+    return update_depth_mode();
+  if (!(std::cin >> n >> c.init_damp >> c.min_damp >> c.max_damp >> c.damp_inc_factor >> c.damp_dec_factor >> c.jac_update_err_inc_threshold >>
         c.min_grad_thresh >> c.min_param_inc_thresh >> c.max_num_iters >> h.cost.fx >> h.cost.fy >> h.cost.cx >> h.cost.cy >> h.cost.wz))
     return 2;
   float R[9], t[3], s;

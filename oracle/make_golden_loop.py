@@ -124,6 +124,24 @@ def run_reference_loop(exe, c):
     return "".join(kinds), np.array(rows), final
 
 
+def update_depth_cases():
+    rng = np.random.default_rng(77)
+    cases = []
+    for name, (H, W, C) in (("ud_24x32_c32", (24, 32, 32)), ("ud_48x64_c16", (48, 64, 16)), ("ud_40x30_c8", (40, 30, 8))):
+        cases.append(dict(name=name, H=H, W=W, C=C, bias=rng.uniform(0.5, 3.0, H * W).astype(np.float32),
+                          jac=(0.2 * rng.standard_normal((H * W, C))).astype(np.float32), code=(0.5 * rng.standard_normal(C)).astype(np.float32),
+                          scale=np.float32(rng.uniform(0.7, 1.6))))
+    return cases
+
+
+def run_reference_update_depth(exe, c):
+    text = f"0 {c['H']} {c['W']} {c['C']} {float(c['scale'])!r}\n"
+    for a in (c["bias"], c["jac"].reshape(-1), c["code"]):
+        text += " ".join(repr(float(v)) for v in a) + "\n"
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.split()
+    return np.array([float(v) for v in out], np.float32)
+
+
 def main():
     import build_loop_ref
 
@@ -137,6 +155,9 @@ def main():
         out[n + "/opt"] = np.array([c["opt"][k] for k in sorted(c["opt"])], np.float64)
         out[n + "/kinds"], out[n + "/log"], out[n + "/final"] = np.array(kinds), rows, final
         print(f"{n}: {kinds}  final error {final[-2]:.6g} after {int(final[-1])} iterations")
+    for c in update_depth_cases():  # Mapper::UpdateMap's depth write-back, the reference's own UpdateDepth
+        out[c["name"] + "/dpt_map"] = run_reference_update_depth(exe, c)
+        print(f"{c['name']}: {len(out[c['name'] + '/dpt_map'])} depths")
     out["opt_keys"] = np.array(sorted(FLAGS))
     out["cam"] = np.array(CAM)
     np.savez_compressed(OUT, **out)

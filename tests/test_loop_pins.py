@@ -155,3 +155,15 @@ def test_library_loop_makes_the_reference_loops_evaluations(name):
     np.testing.assert_allclose(R, fin[:9], atol=TOL_STATE)
     np.testing.assert_allclose(t, fin[9:12], atol=TOL_STATE)
     assert abs(s - fin[12]) <= TOL_STATE and abs(e - fin[13]) <= TOL_ERR * abs(fin[13])
+
+
+@pytest.mark.parametrize("case", G.update_depth_cases(), ids=lambda c: c["name"])
+def test_update_depth_matches_the_references_own_function(case):
+    """Row f4 (Mapper::UpdateMap's depth write-back): oracle.update_depth -- the checker of sage_ba_problem_update_map and of the
+    mapper adapters (tests/test_mapper.py, tests/test_gpu_solver.py) -- against UpdateDepth<float> itself
+    (core/mapping/mapping_utils.h:216-222, extracted at build time, run with libtorch on the CPU)."""
+    pins = np.load(PINS)
+    got = O.update_depth(case["bias"], case["jac"], case["code"], case["scale"])
+    want = pins[case["name"] + "/dpt_map"]
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=5e-7)  # one fp32 GEMV: summation order is the only freedom (1 ulp where bias + jac.code cancels)
