@@ -113,3 +113,34 @@ def test_full_size_round_trip(sage_ctx):
     np.testing.assert_array_equal(r["cyc_matched_locations_1d_0"], kp)
     assert len(r["inlier_within_keypoint_indexes"]) == K
     assert r["kernel_ms"] > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The reference's OWN statements (core/gtsam/reprojection_factor.cpp:42-89, extracted at build time, libtorch CPU):
+# tests/golden/match_pins.npz, oracle/match_pins.cpp, oracle/make_golden_match.py
+@pytest.mark.parametrize("name", list(desc_case.CASES))
+def test_keypoint_draw_and_cycle_matching_match_the_references_own_statements(name):
+    import make_golden_match as M
+    import make_golden_desc as D
+    import sage_slam_b200 as sage
+    import torch
+
+    pins = np.load(os.path.join(GOLDEN, "match_pins.npz"))
+    c = desc_case.build(name)
+    loc = M.valid_locations(c)
+    kf_id, fr_id = M.IDS[name]
+    # 1. the keypoint draw: std::shuffle(iota(N), mt19937(kf id * frame id)), first K (the reference image links libstdc++ of GCC 9;
+    #    this container's g++ 13 built the harness, and frames.std_shuffle restates both)
+    drawn = pins[name + "/keypoint_indexes"]
+    np.testing.assert_array_equal(sage.frames.std_shuffle(len(loc), kf_id * fr_id, libstdcxx="13")[:c["K"]], drawn)
+    kp = loc[drawn]
+    # 2. the cycle matching on those keypoints: the torch replay that generated desc_*.npz, and the oracle's restatement
+    with torch.no_grad():
+        r = D.reference_chain(torch.from_numpy(c["desc0"][None]), torch.from_numpy(c["desc1"][None]), torch.from_numpy(kp), c["W"], c["H"],
+                              c["thresh"])
+    o = oracle.cycle_match(c["desc0"], c["desc1"], kp, c["thresh"])
+    for got in (r, o):
+        np.testing.assert_array_equal(np.asarray(got["raw_matched_locations_1d_1"]), pins[name + "/raw_matched_locations_1d_1"])
+        np.testing.assert_array_equal(np.asarray(got["cyc_matched_locations_1d_0"]), pins[name + "/cyc_matched_locations_1d_0"])
+        inl = np.asarray(got["inlier_within_keypoint_indexes"])
+        np.testing.assert_array_equal(drawn[inl], pins[name + "/matched_keypoint_indexes"])
