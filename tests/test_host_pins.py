@@ -80,3 +80,31 @@ def test_tracker_solve_matches_eigen_colpiv_householder_qr():
         assert e <= max(1e-5, 4e-7 * cond), (k, n, damp, cond, e)
         worst = max(worst, e if cond < 1e3 else 0.0)
     assert worst <= 1e-5
+
+
+def test_retract_matches_the_references_se3_traits():
+    """Row a9 for the mapping variables: gtsam::traits<Sophus::SE3<Scalar>>::Retract (core/gtsam/gtsam_traits.h:45-70), the struct
+    extracted verbatim at build time and compiled against the vendored Sophus + Eigen (oracle/retract_pins.cpp,
+    oracle/make_golden_retract.py).  The reference re-projects the product on SO(3) (AngleAxis round trip + Sophus' unit quaternion);
+    oracle.retract and the library's update (se3_exp, then R' = dR R, t' = dR t + dt: csrc/problem.cu retract_kernel) do not, so they
+    agree to rounding, not bit for bit: 1e-15 in double, 4e-7 in float, and the float result stays orthonormal to 1e-6."""
+    P = np.load(os.path.join(helpers.ROOT, "tests", "golden", "retract_pins.npz"))
+    lib = sage.capi.load()
+    worst64 = worst32 = 0.0
+    for case, p32, r32, r64 in zip(P["cases"], P["pose32"], P["retract32"], P["retract64"]):
+        R, t, d = case[:9].reshape(3, 3), case[9:12], case[12:18]
+        Rn, tn = O.retract(R.astype(np.float64), t.astype(np.float64), d.astype(np.float64))
+        worst64 = max(worst64, np.abs(Rn.reshape(-1) - r64[:9]).max(), np.abs(tn - r64[9:]).max() / max(1.0, np.abs(r64[9:]).max()))
+        # float: the library's own se3_exp, composed as retract_kernel does, from the float pose the reference started from
+        Rf, tf = p32[:9].reshape(3, 3).astype(np.float32), p32[9:].astype(np.float32)
+        w, v = d[3:].astype(np.float32), d[:3].astype(np.float32)
+        dR, dt = np.zeros(9, np.float32), np.zeros(3, np.float32)
+        assert lib.sage_ba_se3_exp(w.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), dR.ctypes.data_as(C.c_void_p),
+                                   dt.ctypes.data_as(C.c_void_p)) == 0
+        dR = dR.reshape(3, 3)
+        R1 = (dR @ Rf).astype(np.float32)
+        t1 = (dR @ tf + dt).astype(np.float32)
+        worst32 = max(worst32, np.abs(R1.reshape(-1) - r32[:9]).max(), np.abs(t1 - r32[9:]).max() / max(1.0, np.abs(r32[9:]).max()))
+        assert np.abs(R1.astype(np.float64) @ R1.astype(np.float64).T - np.eye(3)).max() <= 1e-6
+    assert worst64 <= 1e-14, worst64
+    assert worst32 <= 6e-7, worst32
