@@ -4,7 +4,7 @@
 // The loops -- CameraTracker::TrackNewFrame (core/system/camera_tracker.cpp:1156-1279, 6-DoF) and CameraTracker::TrackFrame
 // (:1479-1630, 7-DoF) -- their declaration blocks, UpdateVariables (:467-512) and LMConvergence (:527-573) -- and UpdateDepth
 // (core/mapping/mapping_utils.h:216-222, second mode below) are #included from files
-// that oracle/build_loop_ref.py extracts verbatim from /root/reference at build time (git-ignored; nothing is copied into the
+// that oracle/build_loop_ref.py extracts verbatim from /root/reference at build time (into a scratch directory removed after the build; nothing is copied into the
 // repository).  This file only supplies what those pieces refer to: the members config_ / tracker_name_ / kf_ / photo_weights_tensor_,
 // a VLOG sink, and ComputeJacobianAndError / ComputeError over a pinhole reprojection cost on a point cloud
 //     x_i = R (s p_i) + t,   r_i = [pi(x_i) - uv_i ; wz (x_i.z - d_i)],   error = mean |r_i|^2,   AtA = mean J^T J,  Atb = -mean J^T r,

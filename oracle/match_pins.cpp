@@ -1,7 +1,7 @@
 // match_pins.cpp -- TEST INFRASTRUCTURE (never linked into the product): the reference's OWN keypoint draw and descriptor
 // cycle-matching statements (ReprojectionFactor's constructor, core/gtsam/reprojection_factor.cpp:42-89 -- the same statements
 // stand in match_geometry_factor.cpp:62-97 and camera_tracker.cpp:798-834), #included from a file oracle/build_loop_ref.py extracts
-// verbatim at build time (git-ignored), run with libtorch on the CPU.  This file supplies the names the block reads: kf_ / fr_ with an
+// verbatim at build time (scratch directory, removed after the build), run with libtorch on the CPU.  This file supplies the names the block reads: kf_ / fr_ with an
 // id and a descriptor map, valid_locations_1d, width, height, num_points, num_keypoints_, cyc_consis_thresh.
 //   stdin:  C H W  num_keypoints  kf_id fr_id  thresh  N   then N valid locations, C*H*W values of desc0, C*H*W of desc1
 //   stdout: "I n" keypoint_indexes_, "R n" raw_matched_locations_1d_1, "C n" cyc_matched_locations_1d_0, "M n" matched_keypoint_indexes_

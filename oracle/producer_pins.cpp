@@ -1,6 +1,6 @@
 // producer_pins.cpp -- TEST INFRASTRUCTURE (never linked into the product): runs the reference's OWN input producers on the CPU.
 //
-// #included from files that oracle/build_loop_ref.py extracts verbatim from /root/reference at build time (git-ignored; nothing is
+// #included from files that oracle/build_loop_ref.py extracts verbatim from /root/reference at build time (scratch directory, removed after the build; nothing is
 // copied into the repository):
 //   * GenerateMaskPyramid            core/mapping/mapping_utils.cpp:321-342
 //   * ComputeSpatialGrad             core/mapping/mapping_utils.h:236-256

@@ -1,6 +1,6 @@
 // retract_pins.cpp -- TEST INFRASTRUCTURE (never linked into the product): the reference's OWN SE(3) manifold for the mapping
 // variables, gtsam::traits<Sophus::SE3<Scalar>> (core/gtsam/gtsam_traits.h:13-138: Retract, Local, its se3_exp), #included from a file
-// that oracle/build_host_ref.py extracts verbatim at build time (git-ignored) and compiled against the Sophus and Eigen the reference
+// that oracle/build_host_ref.py extracts verbatim at build time (scratch directory, removed after the build) and compiled against the Sophus and Eigen the reference
 // vendors.  This file supplies the two GTSAM names the struct mentions (the primary template and gtsam::Vector).
 //   stdin:  n, then n lines: R(9 row-major) t(3) delta(6: v, omega)
 //   stdout: per line: float Retract -> R'(9) t'(3), double Retract -> R'(9) t'(3), Local(pose, Retract(pose, delta)) (6, float instantiation)
